@@ -1,0 +1,208 @@
+/*
+ * emc.h — C ABI of libemc.so, the B200 batch engine behind the drop-in Python API.
+ *
+ * The reference (smcconoughey/erpl_monte_carlo_sim) has no FFI layer; its boundary for this
+ * path is the Python call FlightSimulator.simulate_flight(initial_conditions, wind_profile,
+ * altitude_profile) (rocket_simulation/simulator.py:127) made once per dispersed sample by
+ * MonteCarloAnalyzer._run_single_simulation (rocket_simulation/monte_carlo.py:291-295).
+ * The entry points below are what a ctypes binding placed at those two call sites binds
+ * (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, doubles and 32/64-bit integers only; no exceptions cross the ABI.
+ *  - every function returns 0 on success or a negative emc_status; emc_last_error() gives text.
+ *  - the library copies what it needs; the caller keeps ownership of every buffer it passes.
+ *  - calls on one context are serialised by the caller; a context owns one CUDA device.
+ *  - all arithmetic is IEEE-754 binary64 (the reference's Python floats / NumPy float64).
+ *  - there is NO CPU implementation behind these symbols: without a CUDA device emc_create fails.
+ */
+#ifndef EMC_H
+#define EMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMC_ABI_VERSION 1
+
+/* ---- limits of the run-constant tables (rocket.py:43-53, motor.py:31-41) ---- */
+#define EMC_MAX_CD_KNOTS 16
+#define EMC_MAX_CP_KNOTS 16
+#define EMC_MAX_THRUST_KNOTS 32
+#define EMC_MAX_WIND_KNOTS 1024
+
+typedef enum emc_status {
+    EMC_OK = 0,
+    EMC_ERR_INVALID = -1,   /* bad argument (NULL, size, table not increasing, ...) */
+    EMC_ERR_NO_DEVICE = -2, /* no CUDA device / wrong architecture: there is no CPU fallback */
+    EMC_ERR_CUDA = -3,      /* a CUDA runtime call failed; see emc_last_error */
+    EMC_ERR_NO_MODEL = -4,  /* emc_set_model has not been called */
+    EMC_ERR_CAPACITY = -5   /* caller-provided buffer too small (tape) */
+} emc_status;
+
+enum { EMC_MOTOR_LIQUID = 0, EMC_MOTOR_SOLID = 1 };
+
+/*
+ * Run-constant model: every attribute the hot path reads from the reference's parameter objects.
+ * Raw attribute values go in; constants derived from them (layer base pressures, interpolation
+ * slopes, fin aspect ratio ...) are computed inside the library the way the reference computes them.
+ */
+typedef struct emc_model {
+    /* Rocket (rocket.py:15-66); dry_mass / propellant_mass are per-sample inputs */
+    double center_of_mass_dry;
+    double Ixx_dry, Iyy_dry;          /* Izz_dry is never read by the path (rocket.py:127) */
+    double diameter;                  /* rocket.py:122 propellant Ixx uses diameter/4 */
+    double reference_area, reference_diameter;
+    double fin_root_chord, fin_tip_chord, fin_span, fin_sweep_angle;
+    double cp_location;               /* Barrowman result, rocket.py:56,68-103 */
+    double parachute_area, parachute_cd, parachute_deployment_altitude;
+    double power_off_drag_factor;
+    int32_t n_cd;                     /* rocket.py:43-47 */
+    int32_t n_cp;                     /* rocket.py:50-53 */
+    double cd_mach[EMC_MAX_CD_KNOTS], cd0[EMC_MAX_CD_KNOTS], cda[EMC_MAX_CD_KNOTS];
+    double cp_mach[EMC_MAX_CP_KNOTS], cp_shift[EMC_MAX_CP_KNOTS];
+    /* Motor (motor.py): scalars are per-sample inputs; the Solid base curve is run-constant */
+    int32_t motor_kind;               /* EMC_MOTOR_LIQUID | EMC_MOTOR_SOLID */
+    int32_t n_thrust;                 /* Solid only, motor.py:31-41 */
+    double thrust_time[EMC_MAX_THRUST_KNOTS], thrust_curve[EMC_MAX_THRUST_KNOTS];
+    /* StandardAtmosphere (environment.py:13-24); sea_level_density/gamma are not read by the path */
+    double sea_level_pressure, sea_level_temperature, temperature_lapse_rate;
+    double gas_constant, gravity;
+    double troposphere_height, stratosphere_height, stratosphere_temp;
+    /* FlightSimulator knobs (simulator.py:19-37,42) */
+    double max_time, dt_initial, pitch_damping, yaw_damping, rail_length;
+    /* Wind table grid (environment.py:267-276): shared altitude grid, per-sample (or shared) values */
+    int32_t has_wind;                 /* 0: wind_profile/altitude_profile were None (simulator.py:333) */
+    int32_t n_wind;                   /* knots in the altitude grid (<= EMC_MAX_WIND_KNOTS) */
+    const double *wind_altitudes;     /* [n_wind], host pointer, copied by emc_set_model */
+} emc_model;
+
+/* ---- per-sample inputs: one field-major block  scalars[EMC_IN_COUNT][ld] ---- */
+enum emc_in_field {
+    EMC_IN_X = 0, EMC_IN_Y, EMC_IN_Z,         /* initial position (simulator.py:134) */
+    EMC_IN_VX, EMC_IN_VY, EMC_IN_VZ,          /* initial velocity (simulator.py:137) */
+    EMC_IN_Q0, EMC_IN_Q1, EMC_IN_Q2, EMC_IN_Q3, /* attitude quaternion [w,x,y,z] (utils.py:129-136) */
+    EMC_IN_WX, EMC_IN_WY, EMC_IN_WZ,          /* body angular velocity (simulator.py:150) */
+    EMC_IN_DRY_MASS, EMC_IN_PROP_MASS,        /* rocket.dry_mass / rocket.propellant_mass (monte_carlo.py:315-316) */
+    EMC_IN_THRUST_A,                          /* Liquid: thrust_vacuum; Solid: multiplier on the base curve */
+    EMC_IN_NOZZLE_AREA,                       /* motor.nozzle_exit_area */
+    EMC_IN_MDOT,                              /* motor.mass_flow_rate */
+    EMC_IN_BURN_TIME,                         /* motor.burn_time (monte_carlo.py:258-260) */
+    EMC_IN_CD_SCALE,                          /* multiplier on Cd_data['cd0'] (1.0 = reference) */
+    EMC_IN_COUNT
+};
+
+typedef struct emc_inputs {
+    const double *scalars;       /* [EMC_IN_COUNT][ld], field-major */
+    int64_t ld;                  /* leading dimension (>= n) */
+    const double *wind;          /* [n][n_wind][3] (u,v,w) rows as numpy (N,3); NULL iff !has_wind */
+    int64_t wind_sample_stride;  /* doubles between consecutive samples' tables; 0 = one shared table */
+} emc_inputs;
+
+/* ---- per-sample outputs: field-major blocks  out[EMC_OUT_COUNT][ld], iout[EMC_IOUT_COUNT][ld] ---- */
+enum emc_out_field {
+    EMC_OUT_RAIL_EXIT_TIME = 0,               /* simulator.py:104 */
+    EMC_OUT_RAIL_EXIT_X, EMC_OUT_RAIL_EXIT_Y, EMC_OUT_RAIL_EXIT_Z,
+    EMC_OUT_RAIL_EXIT_VX, EMC_OUT_RAIL_EXIT_VY, EMC_OUT_RAIL_EXIT_VZ,
+    EMC_OUT_RAIL_EXIT_SPEED,                  /* simulator.py:107 */
+    EMC_OUT_RAIL_EXIT_ROLL, EMC_OUT_RAIL_EXIT_PITCH, EMC_OUT_RAIL_EXIT_YAW, /* simulator.py:108 */
+    EMC_OUT_RAIL_EXIT_AOA, EMC_OUT_RAIL_EXIT_SIDESLIP, /* simulator.py:121-122 */
+    EMC_OUT_WIND_AT_EXIT_U, EMC_OUT_WIND_AT_EXIT_V, EMC_OUT_WIND_AT_EXIT_W, /* simulator.py:123 */
+    EMC_OUT_APOGEE_ALTITUDE, EMC_OUT_APOGEE_TIME, /* simulator.py:488-490 (time since rail exit) */
+    EMC_OUT_RANGE,                            /* simulator.py:493-494 */
+    EMC_OUT_FLIGHT_TIME,                      /* simulator.py:582 */
+    EMC_OUT_FINAL_X, EMC_OUT_FINAL_Y, EMC_OUT_FINAL_Z,     /* landing point */
+    EMC_OUT_FINAL_VX, EMC_OUT_FINAL_VY, EMC_OUT_FINAL_VZ,
+    /* maxima/minima over the stored states, NumPy max/min semantics (NaN wins) */
+    EMC_OUT_MAX_MACH,                         /* simulator.py:530-532 */
+    EMC_OUT_MAX_Q,                            /* simulator.py:541 */
+    EMC_OUT_MAX_SPEED,                        /* simulator.py:476; analyze_outlier.py:20 */
+    EMC_OUT_MAX_ABS_OMEGA,                    /* analyze_outlier.py:25: max |component| */
+    EMC_OUT_MIN_STABILITY, EMC_OUT_MAX_STABILITY, /* simulator.py:549; analyze_outlier.py:24 */
+    EMC_OUT_MAX_ABS_AOA,                      /* simulator.py:533 */
+    EMC_OUT_BURNOUT_TIME,                     /* simulator.py:479-480: time[argmax(time > burn_time)] */
+    EMC_OUT_CHUTE_TIME,                       /* time since ignition of the derivative call that latched simulator.py:366-369; NaN if never */
+    EMC_OUT_COUNT
+};
+
+enum emc_iout_field {
+    EMC_IOUT_N_STEPS = 0,     /* accepted RK4 steps = stored states - 1 (simulator.py:216-264) */
+    EMC_IOUT_TERMINATION,     /* emc_termination */
+    EMC_IOUT_APOGEE_INDEX,    /* simulator.py:488 np.argmax(altitudes) */
+    EMC_IOUT_FIRST_NAN_STEP,  /* first stored-state index whose altitude is NaN, -1 if none */
+    EMC_IOUT_RAIL_STEPS,      /* Euler steps on the rail (simulator.py:63-96) */
+    EMC_IOUT_COUNT
+};
+
+typedef enum emc_termination {
+    EMC_TERM_NONE = 0,
+    EMC_TERM_GROUND = 1,      /* simulator.py:238-239 */
+    EMC_TERM_ALTITUDE = 2,    /* simulator.py:242-244 */
+    EMC_TERM_COAST = 3,       /* simulator.py:260-264 */
+    EMC_TERM_MAX_TIME = 4     /* loop guard, simulator.py:216 */
+} emc_termination;
+
+typedef struct emc_outputs {
+    double *out;     /* [EMC_OUT_COUNT][ld] */
+    int32_t *iout;   /* [EMC_IOUT_COUNT][ld] */
+    int64_t ld;
+} emc_outputs;
+
+/* Tape row layout for emc_run_tape: t (since ignition) followed by the 14 state components */
+#define EMC_TAPE_WIDTH 15
+
+typedef struct emc_run_opts {
+    int32_t refill_threshold; /* idle lanes per warp before the warp refills from the work queue; 0 = default */
+    int32_t block_threads;    /* 0 = default */
+    int32_t blocks_per_sm;    /* 0 = default */
+    int32_t nan_fast_forward; /* 1 (default when opts==NULL): replay t += dt only once the state is all-NaN */
+} emc_run_opts;
+
+typedef struct emc_ctx emc_ctx;
+
+/* Kernel-side counters of the last emc_run_* call */
+typedef struct emc_counters {
+    int64_t rk4_steps;        /* accepted RK4 steps integrated (excludes NaN fast-forward replays) */
+    int64_t replay_steps;     /* t += dt replays of all-NaN trajectories */
+    int64_t rail_steps;       /* Euler steps on the rail */
+    int64_t refills;          /* work-queue fetches */
+    int64_t kernel_launches;  /* kernels launched by the call */
+    double rail_ms, flight_ms;/* device time of the two kernels (CUDA events on the context stream) */
+} emc_counters;
+
+int emc_abi_version(void);
+const char *emc_last_error(const emc_ctx *ctx);     /* ctx may be NULL: error of a failed emc_create */
+
+int emc_create(emc_ctx **ctx, int device);          /* replaces FlightSimulator.__init__ state (simulator.py:12-40) */
+int emc_destroy(emc_ctx *ctx);
+int emc_set_model(emc_ctx *ctx, const emc_model *model);
+
+/* Host-buffer entry: simulate n samples, launch -> termination (simulator.py:127-293 per sample). */
+int emc_run_batch(emc_ctx *ctx, const emc_inputs *in, int64_t n, const emc_outputs *out,
+                  const emc_run_opts *opts);
+
+/* Device-buffer entry: same, all pointers are device pointers owned by the caller (resident inputs). */
+int emc_run_batch_device(emc_ctx *ctx, const emc_inputs *in_dev, int64_t n, const emc_outputs *out_dev,
+                         const emc_run_opts *opts);
+
+/* One sample with every stored state written to tape[cap][EMC_TAPE_WIDTH] (simulator.py:212-231). */
+int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_outputs *out,
+                 double *tape, int64_t cap, int64_t *n_states);
+
+/* Test seam: out[i][14] = _rocket_dynamics(t[i], state[i]) (simulator.py:295-460) for sample i.
+ * chute[i] is the sticky parachute flag, read and written back (simulator.py:366-369). */
+int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t n, const double *t,
+                         const double *state /*[n][14]*/, int32_t *chute /*[n]*/,
+                         double *state_dot /*[n][14]*/);
+
+int emc_get_counters(const emc_ctx *ctx, emc_counters *c);
+
+/* Register-resident DFMA chain: measures this GPU's FP64 FMA peak (the roofline denominator). */
+int emc_fp64_peak(emc_ctx *ctx, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMC_H */
