@@ -1,0 +1,208 @@
+"""Loader and thin object wrapper of libemc.so (the C ABI of include/emc.h).
+
+There is no CPU fallback: if the library or a B200-class device is missing every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from . import _abi
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(PKG_DIR, "libemc.so")
+CSRC = os.path.join(PKG_DIR, "csrc")
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-fvisibility=hidden", "-shared"]
+
+
+class EmcError(RuntimeError):
+    pass
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/emc_engine.cu for sm_100a into the in-tree libemc.so (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in ("emc_engine.cu", "emc_physics.cuh", "emc_model_build.h", "emc_stats.cuh")]
+    srcs = [s for s in srcs if os.path.isfile(s)] + [os.path.join(os.path.dirname(PKG_DIR), "include", "emc.h")]
+    if not force and os.path.isfile(SO_PATH) and os.path.getmtime(SO_PATH) >= max(os.path.getmtime(s) for s in srcs):
+        return SO_PATH
+    nvcc = os.environ.get("NVCC") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.isfile(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, os.path.join(CSRC, "emc_engine.cu")]
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)          # let nvcc pick the system g++
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout)
+    if r.returncode != 0:
+        raise EmcError("nvcc failed building libemc.so:\n" + r.stdout[-4000:])
+    return SO_PATH
+
+
+_LIB = None
+
+
+def load():
+    """dlopen libemc.so and declare the prototypes.  Raises EmcError if it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.isfile(SO_PATH):
+        raise EmcError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(this engine has no CPU fallback)")
+    L = C.CDLL(SO_PATH)
+    vp, i64 = C.c_void_p, C.c_int64
+    L.emc_abi_version.restype = C.c_int
+    L.emc_last_error.restype = C.c_char_p
+    L.emc_last_error.argtypes = [vp]
+    L.emc_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.emc_destroy.argtypes = [vp]
+    L.emc_set_model.argtypes = [vp, C.POINTER(_abi.EmcModel)]
+    L.emc_run_batch.argtypes = [vp, C.POINTER(_abi.EmcInputs), i64, C.POINTER(_abi.EmcOutputs), C.POINTER(_abi.EmcRunOpts)]
+    L.emc_run_batch_device.argtypes = L.emc_run_batch.argtypes
+    L.emc_run_tape.argtypes = [vp, C.POINTER(_abi.EmcInputs), C.POINTER(_abi.EmcOutputs), _dp, i64, C.POINTER(i64)]
+    L.emc_derivative_debug.argtypes = [vp, C.POINTER(_abi.EmcInputs), i64, _dp, _dp, _ip, _dp]
+    L.emc_get_counters.argtypes = [vp, C.POINTER(_abi.EmcCounters)]
+    L.emc_fp64_peak.argtypes = [vp, _dp, _dp]
+    for name in ("emc_create", "emc_destroy", "emc_set_model", "emc_run_batch", "emc_run_batch_device",
+                 "emc_run_tape", "emc_derivative_debug", "emc_get_counters", "emc_fp64_peak"):
+        getattr(L, name).restype = C.c_int
+    if L.emc_abi_version() != _abi.ABI_VERSION:
+        raise EmcError(f"libemc.so ABI {L.emc_abi_version()} != binding ABI {_abi.ABI_VERSION}; rebuild")
+    _LIB = L
+    return L
+
+
+def run_opts(refill_threshold=0, block_threads=0, blocks_per_sm=0, nan_fast_forward=True):
+    o = _abi.EmcRunOpts()
+    o.refill_threshold = int(refill_threshold)
+    o.block_threads = int(block_threads)
+    o.blocks_per_sm = int(blocks_per_sm)
+    o.nan_fast_forward = 1 if nan_fast_forward else 0
+    return o
+
+
+class Engine:
+    """One emc_ctx: owns one CUDA device, a stream and its staging buffers."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.emc_create(C.byref(self._ctx), int(device))
+        if rc != 0:
+            msg = self._lib.emc_last_error(None).decode()
+            self._ctx = C.c_void_p()
+            raise EmcError(f"emc_create failed ({_abi.STATUS.get(rc, rc)}): {msg}")
+        self.device = int(device)
+        self._model_keep = None
+        self.model_dict = None
+
+    # -- lifetime -------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._lib.emc_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EmcError(f"{what} failed ({_abi.STATUS.get(rc, rc)}): {self._lib.emc_last_error(self._ctx).decode()}")
+
+    # -- model ----------------------------------------------------------------------------------
+    def set_model(self, md: dict):
+        m, keep = _abi.pack_model(md)
+        self._check(self._lib.emc_set_model(self._ctx, C.byref(m)), "emc_set_model")
+        self._model_keep = (m, keep)
+        self.model_dict = md
+        self.has_wind = bool(m.has_wind)
+        self.n_wind = int(m.n_wind)
+
+    # -- host-buffer path (the drop-in boundary) ------------------------------------------------
+    def run_batch(self, scalars, wind=None, opts=None, wind_shared=False):
+        """scalars [IN_COUNT][n] float64, wind [n][N][3] (or [N][3] with wind_shared) -> (out, iout)."""
+        scalars = np.ascontiguousarray(scalars, np.float64)
+        n = scalars.shape[1]
+        w = None
+        if self.has_wind:
+            if wind is None:
+                raise ValueError("the model has a wind grid: a wind table is required")
+            w = np.ascontiguousarray(wind, np.float64)
+            if w.ndim == 2:
+                wind_shared = True
+            if w.shape[-2] != self.n_wind or w.shape[-1] != 3 or (not wind_shared and w.shape[0] != n):
+                raise ValueError(f"wind table shape {w.shape} does not match n={n}, n_wind={self.n_wind}")
+        ins = _abi.inputs_struct(scalars, w, wind_shared=wind_shared)
+        outs, out, iout = _abi.outputs_alloc(n)
+        self._check(self._lib.emc_run_batch(self._ctx, C.byref(ins), n, C.byref(outs),
+                                            C.byref(opts) if opts is not None else None), "emc_run_batch")
+        return out, iout
+
+    # -- device-buffer path (resident inputs; pointers are raw CUDA device addresses) -----------
+    def run_batch_device(self, scalars_ptr, ld, wind_ptr, wind_stride, out_ptr, iout_ptr, out_ld, n, opts=None):
+        ins = _abi.EmcInputs()
+        ins.scalars = scalars_ptr
+        ins.ld = ld
+        ins.wind = wind_ptr
+        ins.wind_sample_stride = wind_stride
+        outs = _abi.EmcOutputs()
+        outs.out = out_ptr
+        outs.iout = iout_ptr
+        outs.ld = out_ld
+        self._check(self._lib.emc_run_batch_device(self._ctx, C.byref(ins), n, C.byref(outs),
+                                                   C.byref(opts) if opts is not None else None), "emc_run_batch_device")
+
+    def run_tape(self, scalars, wind=None, cap=70000):
+        scalars = np.ascontiguousarray(scalars, np.float64).reshape(_abi.IN_COUNT, 1)
+        w = np.ascontiguousarray(wind, np.float64) if (self.has_wind and wind is not None) else None
+        if self.has_wind and w is None:
+            raise ValueError("the model has a wind grid: a wind table is required")
+        ins = _abi.inputs_struct(scalars, w, wind_shared=True)
+        outs, out, iout = _abi.outputs_alloc(1)
+        tape = np.empty((cap, _abi.TAPE_WIDTH), np.float64)
+        ns = C.c_int64(0)
+        self._check(self._lib.emc_run_tape(self._ctx, C.byref(ins), C.byref(outs), tape.ctypes.data_as(_dp), cap,
+                                           C.byref(ns)), "emc_run_tape")
+        return out, iout, tape[:ns.value]
+
+    def derivative_debug(self, scalars, wind, t, state, chute):
+        scalars = np.ascontiguousarray(scalars, np.float64)
+        n = scalars.shape[1]
+        w = np.ascontiguousarray(wind, np.float64) if (self.has_wind and wind is not None and np.size(wind)) else None
+        ins = _abi.inputs_struct(scalars, w, wind_shared=(w is not None and w.ndim == 2))
+        t = np.ascontiguousarray(t, np.float64)
+        state = np.ascontiguousarray(state, np.float64)
+        ch = np.ascontiguousarray(chute, np.int32).copy()
+        sd = np.empty((n, 14), np.float64)
+        self._check(self._lib.emc_derivative_debug(self._ctx, C.byref(ins), n, t.ctypes.data_as(_dp),
+                                                   state.ctypes.data_as(_dp), ch.ctypes.data_as(_ip),
+                                                   sd.ctypes.data_as(_dp)), "emc_derivative_debug")
+        return sd, ch
+
+    def counters(self) -> dict:
+        c = _abi.EmcCounters()
+        self._lib.emc_get_counters(self._ctx, C.byref(c))
+        return {k: getattr(c, k) for k, _ in _abi.EmcCounters._fields_}
+
+    def fp64_peak(self):
+        tf, ms = C.c_double(), C.c_double()
+        self._check(self._lib.emc_fp64_peak(self._ctx, C.byref(tf), C.byref(ms)), "emc_fp64_peak")
+        return tf.value, ms.value

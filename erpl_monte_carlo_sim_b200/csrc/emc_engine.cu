@@ -1,0 +1,566 @@
+/*
+ * emc_engine.cu — libemc.so: the sm_100a kernels and the C ABI of include/emc.h.
+ *
+ * Kernels
+ *   emc_rail_kernel        one thread per sample, convergent: the launch-rail Euler loop
+ *                          (reference simulator.py:42-125) -> rail_* outputs = state at rail exit.
+ *   emc_flight_kernel      PERSISTENT: one trajectory per lane, state in registers; lanes whose
+ *                          trajectory ended (simulator.py:238-264) are found with a warp ballot and
+ *                          refilled from a global atomic work queue, so a warp never idles behind its
+ *                          longest flight.  Run-constant tables (Cd/CP vs Mach, thrust curve, wind
+ *                          altitude grid) are staged once into shared memory; scalars sit in
+ *                          __constant__ memory.  Summaries are written as field-major SoA.
+ *   emc_derivative_kernel  test seam: one derivative evaluation per thread (simulator.py:295-460).
+ *   emc_dfma_kernel        register-resident DFMA chains: measures the FP64 roofline denominator.
+ *
+ * There is no CPU implementation in this library: every entry point needs a CUDA device.
+ */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "emc_model_build.h"
+
+using namespace emc;
+
+#define EMC_EXPORT extern "C" __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------ */
+__constant__ DevModel c_model;
+__constant__ DevTables c_tables;
+
+struct KernelArgs {
+    const double *scalars; int64_t ld;
+    const double *wind; int64_t wind_stride;
+    const double *wind_alt;            /* device copy of the altitude grid */
+    double *out; int32_t *iout; int64_t old;
+    int64_t n;
+    unsigned long long *queue;         /* [0] next sample index */
+    unsigned long long *counters;      /* [0] rk4 steps [1] replays [2] rail steps [3] refills */
+    double *tape; int64_t tape_cap; int64_t *tape_n;
+    int32_t refill_threshold; int32_t nan_ff;
+};
+
+/* stage the run-constant tables into shared memory: [DevTables][wind altitude grid] */
+__device__ __forceinline__ void stage_tables(double *smem, const KernelArgs &a)
+{
+    const double *src = reinterpret_cast<const double *>(&c_tables);
+    constexpr int NT = sizeof(DevTables) / sizeof(double);
+    for (int i = threadIdx.x; i < NT; i += blockDim.x) smem[i] = src[i];
+    const int nw = c_model.n_wind;
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) smem[NT + i] = a.wind_alt[i];
+    __syncthreads();
+}
+
+static size_t smem_bytes(int n_wind) { return sizeof(DevTables) + sizeof(double) * (size_t)(n_wind > 0 ? n_wind : 0); }
+
+/* ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(128) emc_rail_kernel(KernelArgs a)
+{
+    extern __shared__ double smem[];
+    stage_tables(smem, a);
+    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
+    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    unsigned long long steps = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+        Sample S;
+        load_sample(c_model, a.scalars + i, a.ld, a.wind ? a.wind + i * a.wind_stride : nullptr, S);
+        int rs = rail_phase(c_model, Tb, alt, S, a.scalars + i, a.ld, a.out + i, a.old);
+        a.iout[EMC_IOUT_RAIL_STEPS * a.old + i] = rs;
+        steps += (unsigned long long)rs;
+    }
+    for (int o = 16; o > 0; o >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, o);
+    if ((threadIdx.x & 31) == 0 && steps) atomicAdd(a.counters + 2, steps);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+template <int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
+{
+    extern __shared__ double smem[];
+    stage_tables(smem, a);
+    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
+    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+
+    bool active = false, drained = false;
+    int64_t idx = -1;
+    Sample S; State s; Track K; WindBracket WB;
+    unsigned long long n_steps = 0, n_replay = 0, n_refill = 0;
+    const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
+
+    for (;;) {
+        /* ---- retire/refill: ballot the idle lanes, one atomic per warp, ranks by popc ---- */
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle != 0u && !drained) {
+            const int nidle = __popc(idle);
+            if (nidle >= thr) {
+                const int leader = __ffs(idle) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)nidle);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + (unsigned long long)nidle >= (unsigned long long)a.n) drained = true;
+                if (!active) {
+                    const int64_t my = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                    if (my < a.n) {
+                        idx = my;
+                        load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
+                        double t_rail;
+                        load_flight_state(S, a.scalars + idx, a.ld, a.out + idx, a.old, s, t_rail);
+                        track_init(K, s, t_rail);
+                        wind_bracket_reset(WB);
+                        if (!(K.t < c_model.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
+                        if (a.tape && a.tape_cap > 0) {
+                            a.tape[0] = K.t;
+                            const double *sp = reinterpret_cast<const double *>(&s);
+                            for (int c = 0; c < 14; ++c) a.tape[1 + c] = sp[c];
+                        }
+                        active = true;
+                        ++n_refill;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0u) {
+            if (drained) break;
+            continue;
+        }
+        if (active) {
+            bool stepped; int64_t rep = 0;
+            const bool retired = lane_advance(c_model, Tb, alt, S, WB, K, s, a.nan_ff != 0, stepped, rep);
+            if (stepped) {
+                ++n_steps;
+                if (a.tape && (int64_t)K.n_steps < a.tape_cap) {
+                    double *row = a.tape + (int64_t)K.n_steps * EMC_TAPE_WIDTH;
+                    row[0] = K.t;
+                    const double *sp = reinterpret_cast<const double *>(&s);
+                    for (int c = 0; c < 14; ++c) row[1 + c] = sp[c];
+                }
+            }
+            if (retired) {
+                n_replay += (unsigned long long)rep;
+                write_flight_outputs(K, s, a.out + idx, a.iout + idx, a.old);
+                if (a.tape_n) *a.tape_n = (int64_t)K.n_steps + 1 - rep;
+                active = false;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        n_steps += __shfl_down_sync(FULL, n_steps, o);
+        n_replay += __shfl_down_sync(FULL, n_replay, o);
+        n_refill += __shfl_down_sync(FULL, n_refill, o);
+    }
+    if (lane == 0) {
+        if (n_steps) atomicAdd(a.counters + 0, n_steps);
+        if (n_replay) atomicAdd(a.counters + 1, n_replay);
+        if (n_refill) atomicAdd(a.counters + 3, n_refill);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const double *t, const double *state,
+                                                             int32_t *chute, double *state_dot)
+{
+    extern __shared__ double smem[];
+    stage_tables(smem, a);
+    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
+    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    Sample S;
+    load_sample(c_model, a.scalars + i, a.ld, a.wind ? a.wind + i * a.wind_stride : nullptr, S);
+    WindBracket WB; wind_bracket_reset(WB);
+    State s, k; Diag dg;
+    const double *sp = state + 14 * i;
+    s.x = sp[0]; s.y = sp[1]; s.z = sp[2]; s.vx = sp[3]; s.vy = sp[4]; s.vz = sp[5];
+    s.q0 = sp[6]; s.q1 = sp[7]; s.q2 = sp[8]; s.q3 = sp[9]; s.wx = sp[10]; s.wy = sp[11]; s.wz = sp[12]; s.pf = sp[13];
+    bool ch = chute[i] != 0; double ct = 0.0;
+    derivative(c_model, Tb, alt, S, WB, t[i], s, ch, ct, k, true, dg);
+    chute[i] = ch ? 1 : 0;
+    double *kp = state_dot + 14 * i;
+    kp[0] = k.x; kp[1] = k.y; kp[2] = k.z; kp[3] = k.vx; kp[4] = k.vy; kp[5] = k.vz;
+    kp[6] = k.q0; kp[7] = k.q1; kp[8] = k.q2; kp[9] = k.q3; kp[10] = k.wx; kp[11] = k.wy; kp[12] = k.wz; kp[13] = k.pf;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* 8 independent DFMA chains per thread, all in registers: 2*8*iters flop per thread */
+__global__ void __launch_bounds__(256) emc_dfma_kernel(double *sink, int iters, double a, double b)
+{
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1e-3, x2 = x0 + 2e-3, x3 = x0 + 3e-3;
+    double x4 = x0 + 4e-3, x5 = x0 + 5e-3, x6 = x0 + 6e-3, x7 = x0 + 7e-3;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123456.789) sink[0] = r;     /* never true; keeps the chains alive */
+}
+
+/* ================================================================================================
+ *  C ABI
+ * ============================================================================================== */
+struct emc_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    bool has_model = false;
+    emc_model model;              /* raw copy (wind_altitudes pointer is NOT valid after set_model) */
+    DevModel dmodel;
+    double *d_wind_alt = nullptr;
+    unsigned long long *d_ctrl = nullptr;   /* [0] queue head, [1..4] counters, [5] tape_n */
+    /* staging buffers for the host-buffer entry points (grown on demand) */
+    double *d_scalars = nullptr; size_t cap_scalars = 0;
+    double *d_wind = nullptr; size_t cap_wind = 0;
+    double *d_out = nullptr; size_t cap_out = 0;
+    int32_t *d_iout = nullptr; size_t cap_iout = 0;
+    double *d_tape = nullptr; size_t cap_tape = 0;
+    emc_counters counters;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(emc_ctx *c, int code, const std::string &msg)
+{
+    if (c) c->err = msg; else g_create_err = msg;
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(ctx, EMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+EMC_EXPORT int emc_abi_version(void) { return EMC_ABI_VERSION; }
+
+EMC_EXPORT const char *emc_last_error(const emc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+EMC_EXPORT int emc_create(emc_ctx **out, int device)
+{
+    emc_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, EMC_ERR_INVALID, "emc_create: ctx is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, EMC_ERR_NO_DEVICE,
+                    std::string("emc_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count = 0") +
+                        "); this engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, EMC_ERR_INVALID, "emc_create: device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, EMC_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, EMC_ERR_NO_DEVICE,
+                    std::string("emc_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                        "; libemc.so carries sm_100a code only");
+    ctx = new (std::nothrow) emc_ctx();
+    if (!ctx) return fail(nullptr, EMC_ERR_INVALID, "out of host memory");
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    memset(&ctx->counters, 0, sizeof ctx->counters);
+    e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctrl, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        std::string m = std::string("emc_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return fail(nullptr, EMC_ERR_CUDA, m);
+    }
+    *out = ctx;
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_destroy(emc_ctx *ctx)
+{
+    if (!ctx) return EMC_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape);
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_set_model(emc_ctx *ctx, const emc_model *model)
+{
+    if (!ctx || !model) return fail(ctx, EMC_ERR_INVALID, "emc_set_model: NULL argument");
+    if (const char *why = validate_model(*model)) return fail(ctx, EMC_ERR_INVALID, std::string("emc_set_model: ") + why);
+    CK(cudaSetDevice(ctx->device));
+    DevModel D; DevTables T;
+    build_dev_model(*model, D, T);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyToSymbol(c_model, &D, sizeof D));
+    CK(cudaMemcpyToSymbol(c_tables, &T, sizeof T));
+    cudaFree(ctx->d_wind_alt); ctx->d_wind_alt = nullptr;
+    if (D.has_wind) {
+        CK(cudaMalloc(&ctx->d_wind_alt, sizeof(double) * D.n_wind));
+        CK(cudaMemcpy(ctx->d_wind_alt, model->wind_altitudes, sizeof(double) * D.n_wind, cudaMemcpyHostToDevice));
+    }
+    ctx->model = *model;
+    ctx->model.wind_altitudes = nullptr;
+    ctx->dmodel = D;
+    ctx->has_model = true;
+    return EMC_OK;
+}
+
+template <typename T>
+static cudaError_t grow(T **p, size_t *cap, size_t need)
+{
+    if (need <= *cap) return cudaSuccess;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc(p, need * sizeof(T));
+    if (e == cudaSuccess) *cap = need;
+    return e;
+}
+
+static int check_run_args(emc_ctx *ctx, const emc_inputs *in, int64_t n, const emc_outputs *out)
+{
+    if (!ctx || !in || !out) return fail(ctx, EMC_ERR_INVALID, "NULL argument");
+    if (!ctx->has_model) return fail(ctx, EMC_ERR_NO_MODEL, "emc_set_model has not been called");
+    if (n < 0) return fail(ctx, EMC_ERR_INVALID, "n < 0");
+    if (n > 0 && (!in->scalars || !out->out || !out->iout)) return fail(ctx, EMC_ERR_INVALID, "NULL buffer");
+    if (in->ld < n || out->ld < n) return fail(ctx, EMC_ERR_INVALID, "leading dimension smaller than n");
+    if (ctx->dmodel.has_wind && n > 0 && !in->wind) return fail(ctx, EMC_ERR_INVALID, "model has a wind grid but inputs.wind is NULL");
+    if (ctx->dmodel.has_wind && in->wind_sample_stride != 0 && in->wind_sample_stride < (int64_t)ctx->dmodel.n_wind * 3)
+        return fail(ctx, EMC_ERR_INVALID, "wind_sample_stride smaller than n_wind*3");
+    return EMC_OK;
+}
+
+template <int BLOCK, int MINB>
+static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
+{
+    auto kern = emc_flight_kernel<BLOCK, MINB>;
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    if (blocks_per_sm_req > 0 && blocks_per_sm_req < occ) occ = blocks_per_sm_req;
+    int64_t grid = (int64_t)ctx->sm_count * occ;
+    const int64_t need = (a.n + BLOCK - 1) / BLOCK;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, BLOCK, smem, ctx->stream>>>(a);
+    return cudaGetLastError();
+}
+
+/* all pointers in `a` are device pointers */
+static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
+{
+    emc_run_opts o = { 0, 0, 0, 1 };
+    if (opts) o = *opts;
+    a.refill_threshold = o.refill_threshold > 0 ? o.refill_threshold : 1;
+    a.nan_ff = o.nan_fast_forward;
+    a.wind_alt = ctx->d_wind_alt;
+    a.queue = ctx->d_ctrl; a.counters = ctx->d_ctrl + 1;
+    if (a.tape) a.tape_n = reinterpret_cast<int64_t *>(ctx->d_ctrl + 5);
+    if (!ctx->dmodel.has_wind) { a.wind = nullptr; a.wind_stride = 0; }
+    const size_t smem = smem_bytes(ctx->dmodel.n_wind);
+    CK(cudaMemsetAsync(ctx->d_ctrl, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    memset(&ctx->counters, 0, sizeof ctx->counters);
+    if (a.n == 0) return EMC_OK;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    {
+        int64_t grid = (a.n + 127) / 128;
+        const int64_t cap = (int64_t)ctx->sm_count * 16;
+        if (grid > cap) grid = cap;
+        emc_rail_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    const int bt = o.block_threads > 0 ? o.block_threads : 128;
+    const int bps = o.blocks_per_sm;
+    cudaError_t e;
+    if (bt == 64) e = launch_flight<64, 1>(ctx, a, smem, bps);
+    else if (bt == 256) e = launch_flight<256, 1>(ctx, a, smem, bps);
+    else if (bt == 128 && bps == 3) e = launch_flight<128, 3>(ctx, a, smem, bps);
+    else if (bt == 128 && bps >= 4) e = launch_flight<128, 4>(ctx, a, smem, bps);
+    else if (bt == 128) e = launch_flight<128, 1>(ctx, a, smem, bps);
+    else return fail(ctx, EMC_ERR_INVALID, "block_threads must be 64, 128 or 256");
+    if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("flight kernel launch: ") + cudaGetErrorString(e));
+    CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+    ctx->counters.kernel_launches = 2;
+    return EMC_OK;
+}
+
+static int finish_counters(emc_ctx *ctx)
+{
+    unsigned long long h[8];
+    CK(cudaMemcpyAsync(h, ctx->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->counters.rk4_steps = (int64_t)h[1];
+    ctx->counters.replay_steps = (int64_t)h[2];
+    ctx->counters.rail_steps = (int64_t)h[3];
+    ctx->counters.refills = (int64_t)h[4];
+    float ms = 0.f;
+    if (ctx->counters.kernel_launches) {
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->counters.rail_ms = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->counters.flight_ms = ms;
+    }
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_run_batch_device(emc_ctx *ctx, const emc_inputs *in, int64_t n, const emc_outputs *out,
+                                    const emc_run_opts *opts)
+{
+    if (int rc = check_run_args(ctx, in, n, out)) return rc;
+    CK(cudaSetDevice(ctx->device));
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    a.scalars = in->scalars; a.ld = in->ld; a.wind = in->wind; a.wind_stride = in->wind_sample_stride;
+    a.out = out->out; a.iout = out->iout; a.old = out->ld; a.n = n;
+    if (int rc = run_device(ctx, a, opts)) return rc;
+    return finish_counters(ctx);
+}
+
+static int upload_inputs(emc_ctx *ctx, const emc_inputs *in, int64_t n, KernelArgs &a)
+{
+    const size_t ns = (size_t)EMC_IN_COUNT * (size_t)n;
+    CK(grow(&ctx->d_scalars, &ctx->cap_scalars, ns));
+    /* compact the leading dimension to n on the way up */
+    CK(cudaMemcpy2DAsync(ctx->d_scalars, sizeof(double) * n, in->scalars, sizeof(double) * in->ld, sizeof(double) * n,
+                         EMC_IN_COUNT, cudaMemcpyHostToDevice, ctx->stream));
+    a.scalars = ctx->d_scalars; a.ld = n;
+    if (ctx->dmodel.has_wind) {
+        const size_t row = (size_t)ctx->dmodel.n_wind * 3;
+        if (in->wind_sample_stride == 0) {
+            CK(grow(&ctx->d_wind, &ctx->cap_wind, row));
+            CK(cudaMemcpyAsync(ctx->d_wind, in->wind, sizeof(double) * row, cudaMemcpyHostToDevice, ctx->stream));
+            a.wind_stride = 0;
+        } else {
+            CK(grow(&ctx->d_wind, &ctx->cap_wind, row * (size_t)n));
+            CK(cudaMemcpy2DAsync(ctx->d_wind, sizeof(double) * row, in->wind, sizeof(double) * in->wind_sample_stride,
+                                 sizeof(double) * row, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+            a.wind_stride = (int64_t)row;
+        }
+        a.wind = ctx->d_wind;
+    }
+    CK(grow(&ctx->d_out, &ctx->cap_out, (size_t)EMC_OUT_COUNT * (size_t)n));
+    CK(grow(&ctx->d_iout, &ctx->cap_iout, (size_t)EMC_IOUT_COUNT * (size_t)n));
+    a.out = ctx->d_out; a.iout = ctx->d_iout; a.old = n; a.n = n;
+    return EMC_OK;
+}
+
+static int download_outputs(emc_ctx *ctx, const emc_outputs *out, int64_t n)
+{
+    CK(cudaMemcpy2DAsync(out->out, sizeof(double) * out->ld, ctx->d_out, sizeof(double) * n, sizeof(double) * n,
+                         EMC_OUT_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpy2DAsync(out->iout, sizeof(int32_t) * out->ld, ctx->d_iout, sizeof(int32_t) * n, sizeof(int32_t) * n,
+                         EMC_IOUT_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_run_batch(emc_ctx *ctx, const emc_inputs *in, int64_t n, const emc_outputs *out,
+                             const emc_run_opts *opts)
+{
+    if (int rc = check_run_args(ctx, in, n, out)) return rc;
+    if (n == 0) { memset(&ctx->counters, 0, sizeof ctx->counters); return EMC_OK; }
+    CK(cudaSetDevice(ctx->device));
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    if (int rc = upload_inputs(ctx, in, n, a)) return rc;
+    if (int rc = run_device(ctx, a, opts)) return rc;
+    if (int rc = download_outputs(ctx, out, n)) return rc;
+    return finish_counters(ctx);
+}
+
+EMC_EXPORT int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_outputs *out, double *tape, int64_t cap,
+                            int64_t *n_states)
+{
+    if (int rc = check_run_args(ctx, in, 1, out)) return rc;
+    if (!tape || cap < 1 || !n_states) return fail(ctx, EMC_ERR_INVALID, "emc_run_tape: tape/cap/n_states");
+    CK(cudaSetDevice(ctx->device));
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    if (int rc = upload_inputs(ctx, in, 1, a)) return rc;
+    CK(grow(&ctx->d_tape, &ctx->cap_tape, (size_t)cap * EMC_TAPE_WIDTH));
+    a.tape = ctx->d_tape; a.tape_cap = cap;
+    emc_run_opts o = { 1, 64, 1, 0 };       /* every state is integrated: no fast-forward on the tape path */
+    if (int rc = run_device(ctx, a, &o)) return rc;
+    if (int rc = download_outputs(ctx, out, 1)) return rc;
+    if (int rc = finish_counters(ctx)) return rc;
+    unsigned long long h[8];
+    CK(cudaMemcpy(h, ctx->d_ctrl, sizeof h, cudaMemcpyDeviceToHost));
+    const int64_t ns = (int64_t)h[5];
+    *n_states = ns;
+    const int64_t rows = ns < cap ? ns : cap;
+    CK(cudaMemcpy(tape, ctx->d_tape, sizeof(double) * (size_t)rows * EMC_TAPE_WIDTH, cudaMemcpyDeviceToHost));
+    if (ns > cap) return fail(ctx, EMC_ERR_CAPACITY, "emc_run_tape: tape capacity too small; n_states holds the required rows");
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t n, const double *t, const double *state,
+                                    int32_t *chute, double *state_dot)
+{
+    emc_outputs dummy = { (double *)1, (int32_t *)1, n };
+    if (int rc = check_run_args(ctx, in, n, &dummy)) return rc;
+    if (!t || !state || !chute || !state_dot) return fail(ctx, EMC_ERR_INVALID, "emc_derivative_debug: NULL buffer");
+    if (n == 0) return EMC_OK;
+    CK(cudaSetDevice(ctx->device));
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    if (int rc = upload_inputs(ctx, in, n, a)) return rc;
+    a.wind_alt = ctx->d_wind_alt;
+    if (!ctx->dmodel.has_wind) { a.wind = nullptr; a.wind_stride = 0; }
+    double *d_t = nullptr, *d_s = nullptr, *d_k = nullptr; int32_t *d_c = nullptr;
+    cudaError_t e = cudaMalloc(&d_t, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_s, sizeof(double) * 14 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_k, sizeof(double) * 14 * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, sizeof(int32_t) * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_t, t, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_s, state, sizeof(double) * 14 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, chute, sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        emc_derivative_kernel<<<(unsigned)((n + 127) / 128), 128, smem_bytes(ctx->dmodel.n_wind), ctx->stream>>>(a, d_t, d_s, d_c, d_k);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(state_dot, d_k, sizeof(double) * 14 * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(chute, d_c, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_t); cudaFree(d_s); cudaFree(d_k); cudaFree(d_c);
+    if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("emc_derivative_debug: ") + cudaGetErrorString(e));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_get_counters(const emc_ctx *ctx, emc_counters *c)
+{
+    if (!ctx || !c) return EMC_ERR_INVALID;
+    *c = ctx->counters;
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_fp64_peak(emc_ctx *ctx, double *tflops, double *ms_out)
+{
+    if (!ctx || !tflops) return fail(ctx, EMC_ERR_INVALID, "emc_fp64_peak: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    double *sink = reinterpret_cast<double *>(ctx->d_ctrl + 6);
+    const int iters = 1 << 16, threads = 256;
+    const int blocks = ctx->sm_count * 8;
+    emc_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, 1024, 0.999999, 1e-9);   /* warm-up */
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+        emc_dfma_kernel<<<blocks, threads, 0, ctx->stream>>>(sink, iters, 0.999999, 1e-9);
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+        if (ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    const double flop = 2.0 * 8.0 * (double)iters * (double)threads * (double)blocks;
+    *tflops = flop / ((double)best * 1e-3) * 1e-12;
+    if (ms_out) *ms_out = best;
+    return EMC_OK;
+}

@@ -1,0 +1,98 @@
+/*
+ * emc_model_build.h — host-side folding of the raw reference attributes (emc_model, include/emc.h)
+ * into the constants the kernels read (DevModel / DevTables).  Each derived value is computed with
+ * the expression the reference itself evaluates (file:line cited), in double, on the host.
+ */
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "emc_physics.cuh"
+
+namespace emc {
+
+inline const char *validate_model(const emc_model &m)
+{
+    if (m.n_cd < 2 || m.n_cd > EMC_MAX_CD_KNOTS) return "Cd_data needs 2..16 knots";
+    if (m.n_cp < 2 || m.n_cp > EMC_MAX_CP_KNOTS) return "CP_shift_data needs 2..16 knots";
+    for (int i = 1; i < m.n_cd; ++i) if (!(m.cd_mach[i] > m.cd_mach[i - 1])) return "Cd_data['mach'] must be strictly increasing";
+    for (int i = 1; i < m.n_cp; ++i) if (!(m.cp_mach[i] > m.cp_mach[i - 1])) return "CP_shift_data['mach'] must be strictly increasing";
+    if (m.motor_kind != EMC_MOTOR_LIQUID && m.motor_kind != EMC_MOTOR_SOLID) return "motor_kind must be 0 (liquid) or 1 (solid)";
+    if (m.motor_kind == EMC_MOTOR_SOLID) {
+        if (m.n_thrust < 2 || m.n_thrust > EMC_MAX_THRUST_KNOTS) return "thrust curve needs 2..32 knots";
+        for (int i = 1; i < m.n_thrust; ++i) if (!(m.thrust_time[i] > m.thrust_time[i - 1])) return "thrust_curve_time must be strictly increasing";
+    }
+    if (m.has_wind) {
+        if (m.n_wind < 2 || m.n_wind > EMC_MAX_WIND_KNOTS) return "altitude_profile needs 2..1024 knots";
+        if (!m.wind_altitudes) return "wind_altitudes is NULL";
+        for (int i = 1; i < m.n_wind; ++i) if (!(m.wind_altitudes[i] > m.wind_altitudes[i - 1])) return "altitude_profile must be strictly increasing";
+    }
+    if (!(m.dt_initial > 0.0)) return "dt_initial must be > 0";
+    if (!(m.reference_diameter != 0.0)) return "reference_diameter must be non-zero";
+    return nullptr;
+}
+
+inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
+{
+    memset(&D, 0, sizeof D);
+    memset(&T, 0, sizeof T);
+    const double g = m.gravity, R = m.gas_constant, L = m.temperature_lapse_rate;
+    D.T0 = m.sea_level_temperature; D.lapse = L; D.inv_T0 = 1.0 / m.sea_level_temperature;
+    D.p0 = m.sea_level_pressure; D.h_tropo = m.troposphere_height; D.h_strat = m.stratosphere_height;
+    D.T_strat = m.stratosphere_temp; D.inv_T_strat = 1.0 / m.stratosphere_temp;
+    D.expo_tropo = g / (R * L);                                                       /* environment.py:33 */
+    D.p11 = m.sea_level_pressure * pow(m.stratosphere_temp / m.sea_level_temperature, g / (R * L)); /* :38-40 */
+    D.k_iso = -g / (R * m.stratosphere_temp);                                         /* :43-44 */
+    D.p20 = D.p11 * exp(-g * (m.stratosphere_height - m.troposphere_height) / (R * m.stratosphere_temp)); /* :56-62 */
+    D.p25 = D.p20 * exp(-g * 5000.0 / (R * m.stratosphere_temp));                     /* :72-75 */
+    D.expo_25 = g / (R * 0.0028);                                                     /* :76,81 */
+    D.R_gas = R; D.g0 = g;
+
+    D.cg_dry = m.center_of_mass_dry; D.prop_cg = m.center_of_mass_dry - 0.5;          /* rocket.py:116 */
+    const double d4 = m.diameter / 4;
+    D.d4sq = d4 * d4;                                                                 /* rocket.py:122 */
+    D.len2_12 = 2.0 * 2.0 / 12;                                                       /* rocket.py:121,123 */
+    D.Ixx_dry = m.Ixx_dry; D.Iyy_dry = m.Iyy_dry;
+
+    D.ref_area = m.reference_area; D.ref_diam = m.reference_diameter; D.inv_ref_diam = 1.0 / m.reference_diameter;
+    D.area_diam = m.reference_area * m.reference_diameter;
+    D.cp_location = m.cp_location;
+    const double cr = m.fin_root_chord, ct = m.fin_tip_chord, s = m.fin_span;
+    const double fin_area = 0.5 * (cr + ct) * s;                                      /* rocket.py:176 */
+    const double AR = (fin_area > 0) ? 2 * (s * s) / fin_area : 0.0;                  /* rocket.py:177 */
+    const double cs = cos(m.fin_sweep_angle);
+    D.cos_sweep = cs;
+    D.AR_over_cos = AR / ((1e-6 > cs) ? 1e-6 : cs);                                   /* rocket.py:179 */
+    D.two_pi_AR = 2 * M_PI * AR;                                                      /* rocket.py:180 */
+    D.power_off_factor = m.power_off_drag_factor;
+    D.stall_angle = 15.0 * (M_PI / 180.0);                                            /* rocket.py:167 */
+    D.inv_stall_span = 1.0 / (45.0 * (M_PI / 180.0) - 15.0 * (M_PI / 180.0));         /* rocket.py:168,185 */
+    D.chute_cd = m.parachute_cd; D.chute_area = m.parachute_area; D.chute_alt = m.parachute_deployment_altitude;
+
+    D.max_time = m.max_time; D.dt_rail = m.dt_initial;
+    D.dt = (0.005 < m.dt_initial) ? 0.005 : m.dt_initial;                             /* simulator.py:209 */
+    D.half_dt = 0.5 * D.dt; D.dt_over_6 = D.dt / 6.0;
+    D.pitch_damping = m.pitch_damping; D.yaw_damping = m.yaw_damping; D.rail_length = m.rail_length;
+
+    D.motor_kind = m.motor_kind; D.n_cd = m.n_cd; D.n_cp = m.n_cp;
+    D.n_thrust = (m.motor_kind == EMC_MOTOR_SOLID) ? m.n_thrust : 0;
+    D.has_wind = m.has_wind ? 1 : 0; D.n_wind = m.has_wind ? m.n_wind : 0;
+    if (D.has_wind) {
+        const double *a = m.wind_altitudes;
+        const double dz = (a[m.n_wind - 1] - a[0]) / (m.n_wind - 1);
+        bool uni = dz > 0;
+        for (int i = 0; i < m.n_wind && uni; ++i) if (fabs(a[i] - (a[0] + i * dz)) > 1e-6 * dz) uni = false;
+        D.wind_uniform = uni ? 1 : 0; D.wind_alt0 = a[0]; D.wind_inv_dz = uni ? 1.0 / dz : 0.0;
+    }
+    for (int i = 0; i < m.n_cd; ++i) { T.cd_mach[i] = m.cd_mach[i]; T.cd0[i] = m.cd0[i]; T.cda[i] = m.cda[i]; }
+    for (int i = 0; i + 1 < m.n_cd; ++i) {        /* np.interp slope, compiled_base.c */
+        T.cd0_s[i] = (m.cd0[i + 1] - m.cd0[i]) / (m.cd_mach[i + 1] - m.cd_mach[i]);
+        T.cda_s[i] = (m.cda[i + 1] - m.cda[i]) / (m.cd_mach[i + 1] - m.cd_mach[i]);
+    }
+    for (int i = 0; i < m.n_cp; ++i) { T.cp_mach[i] = m.cp_mach[i]; T.cp_shift[i] = m.cp_shift[i]; }
+    for (int i = 0; i + 1 < m.n_cp; ++i) T.cp_s[i] = (m.cp_shift[i + 1] - m.cp_shift[i]) / (m.cp_mach[i + 1] - m.cp_mach[i]);
+    for (int i = 0; i < D.n_thrust; ++i) { T.th_t[i] = m.thrust_time[i]; T.th_f[i] = m.thrust_curve[i]; }
+    for (int i = 0; i + 1 < D.n_thrust; ++i) T.th_s[i] = (m.thrust_curve[i + 1] - m.thrust_curve[i]) / (m.thrust_time[i + 1] - m.thrust_time[i]);
+}
+
+}  // namespace emc

@@ -1,0 +1,700 @@
+/*
+ * emc_physics.cuh — the 6-DOF flight physics of the engine, written for one trajectory per
+ * thread with all state in registers.  Everything here is `__host__ __device__` so the SAME code
+ * can also be compiled by g++ into the test seam (tests/hostseam) and checked against the oracle
+ * in a container without a GPU.  The shipped library (libemc.so) only ever runs it on the device.
+ *
+ * What it mirrors (file:line under rocket_simulation/ of the reference):
+ *   derivative            simulator.py:295-460
+ *   rail phase            simulator.py:42-125
+ *   RK4 step + events     simulator.py:209-264
+ *   summary               simulator.py:474-494,579-582 (+ per-state diagnostics :511-552)
+ *   atmosphere/gravity    environment.py:26-108        wind interp environment.py:267-276
+ *   mass / aero           rocket.py:105-218            thrust / mdot motor.py:54-93,152-169
+ *   quaternion helpers    utils.py:76-121,139-205
+ *
+ * It is NOT a transliteration.  Per-run constants are folded on the host (DevModel), table slopes
+ * are precomputed, reciprocals are shared, sin/cos of the aerodynamic angles come from velocity
+ * ratios instead of sincos(atan2()), pow() is exp(e*log()) with one shared exp() for all five
+ * atmosphere layers, and the four RK4 stages share one copy of the derivative code.  These changes
+ * move results by a few ulp per evaluation; the parity bar is 1e-6 relative per flight (tests/).
+ * Python/NumPy NaN semantics of max()/min()/np.interp/np.argmax are kept where they decide control
+ * flow.
+ */
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/emc.h"
+
+#if defined(__CUDACC__)
+#define EMC_HD __host__ __device__ __forceinline__
+#else
+#define EMC_HD inline
+#endif
+
+namespace emc {
+
+/* ------------------------------------------------------------------------------------------------
+ * Run constants (device: __constant__ memory, so they are instruction operands, not registers)
+ * ---------------------------------------------------------------------------------------------- */
+struct DevModel {
+    /* atmosphere, environment.py:13-24 + literals of :52-90 */
+    double T0, lapse, inv_T0, p0, h_tropo, h_strat, T_strat, inv_T_strat;
+    double expo_tropo;   /* g/(R*L)                        :33 */
+    double p11;          /* p0*(Ts/T0)^expo                :38-40 */
+    double k_iso;        /* -g/(R*Ts)                      :43-44 */
+    double p20, p25;     /* :56-62, :72-75 */
+    double expo_25;      /* g/(R*0.0028)                   :81 */
+    double R_gas, g0;
+    /* mass properties, rocket.py:110-136 */
+    double cg_dry, prop_cg, d4sq, len2_12, Ixx_dry, Iyy_dry;
+    /* aerodynamics, rocket.py:138-218 */
+    double ref_area, ref_diam, inv_ref_diam, area_diam, cp_location;
+    double AR_over_cos, two_pi_AR, cos_sweep, power_off_factor;
+    double stall_angle, inv_stall_span;
+    double chute_cd, chute_area, chute_alt;
+    /* simulator knobs, simulator.py:19-37,42,209 */
+    double max_time, dt_rail, dt, half_dt, dt_over_6, pitch_damping, yaw_damping, rail_length;
+    /* wind grid */
+    double wind_alt0, wind_inv_dz;
+    int32_t motor_kind, n_cd, n_cp, n_thrust, has_wind, n_wind, wind_uniform, pad_;
+};
+
+/* Tables staged into shared memory by the kernels (host seam: plain struct). Slopes are computed on
+ * the host with the same (f1-f0)/(x1-x0) expression np.interp uses, so they are bit-identical. */
+struct DevTables {
+    double cd_mach[EMC_MAX_CD_KNOTS], cd0[EMC_MAX_CD_KNOTS], cda[EMC_MAX_CD_KNOTS];
+    double cd0_s[EMC_MAX_CD_KNOTS], cda_s[EMC_MAX_CD_KNOTS];
+    double cp_mach[EMC_MAX_CP_KNOTS], cp_shift[EMC_MAX_CP_KNOTS], cp_s[EMC_MAX_CP_KNOTS];
+    double th_t[EMC_MAX_THRUST_KNOTS], th_f[EMC_MAX_THRUST_KNOTS], th_s[EMC_MAX_THRUST_KNOTS];
+};
+
+/* Per-sample parameters (registers) */
+struct Sample {
+    double dry_mass, prop_mass, dry_cg;      /* dry_cg = dry_mass*cg_dry, rocket.py:117 */
+    double thrust_a, nozzle_area, burn_time;
+    double pf_rate;                          /* -mdot/propellant_mass, simulator.py:444 */
+    double cd_scale;
+    const double *wind;                      /* this sample's [n_wind][3] table (global memory) */
+};
+
+/* Cached wind bracket: valid while lo <= z < hi (altitude moves <= ~10 m per step against
+ * hundreds of metres of knot spacing, so reloads are rare). */
+struct WindBracket {
+    double lo, hi, x0;
+    double f0[3], s[3];
+};
+
+struct State {
+    double x, y, z, vx, vy, vz, q0, q1, q2, q3, wx, wy, wz, pf;
+};
+
+/* What stage 0 of a step exports about the stored state it is evaluated at (simulator.py:511-552) */
+struct Diag {
+    double mach2, qdyn, abs_aoa, stab;
+};
+
+/* ---------------- NaN-faithful selects ---------------- */
+EMC_HD double py_max(double a, double b) { return (b > a) ? b : a; }   /* Python max(a, b) */
+EMC_HD double py_min(double a, double b) { return (b < a) ? b : a; }   /* Python min(a, b) */
+/* running np.max / np.min over a series: NaN propagates and sticks */
+EMC_HD void np_max_acc(double &m, double v) { m = (v > m || v != v) ? ((m != m) ? m : v) : m; }
+EMC_HD void np_min_acc(double &m, double v) { m = (v < m || v != v) ? ((m != m) ? m : v) : m; }
+
+/* index of the bracket: number of interior knots <= x, i.e. largest j in [0, n-2] with xp[j] <= x
+ * (x already known to be inside [xp[0], xp[n-1]]) */
+EMC_HD int bracket_small(const double *xp, int n, double x)
+{
+    int j = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 1; k < n - 1; ++k) j += (xp[k] <= x) ? 1 : 0;
+    return j;
+}
+
+/* np.interp with precomputed slopes (utils.py:147-149): clamps outside, NaN -> NaN */
+EMC_HD double interp_tab(const double *xp, const double *fp, const double *sl, int n, double x)
+{
+    if (x != x) return x;
+    if (x >= xp[n - 1]) return fp[n - 1];
+    if (x <= xp[0]) return fp[0];
+    int j = bracket_small(xp, n, x);
+    return sl[j] * (x - xp[j]) + fp[j];
+}
+
+/* ---------------- atmosphere: T and 1/(R*T), p  (environment.py:26-103) ---------------- */
+EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, double &p)
+{
+    /* every layer is p = base * exp(arg); the two pow() layers use arg = e*log(T/Tb) */
+    double base, arg, lx = 1.0, le = 0.0;
+    bool use_log = false;
+    if (z <= M.h_tropo) {
+        T = M.T0 - M.lapse * z;
+        base = M.p0; lx = T * M.inv_T0; le = M.expo_tropo; use_log = true; arg = 0.0;
+    } else if (z <= M.h_strat) {
+        T = M.T_strat;
+        base = M.p11; arg = M.k_iso * (z - M.h_tropo);
+    } else if (z <= 32000.0) {
+        T = M.T_strat + 0.001 * (z - M.h_strat);
+        T = py_min(T, 228.65);
+        if (z <= 25000.0) { base = M.p20; arg = M.k_iso * (z - M.h_strat); }
+        else { base = M.p25; lx = T * M.inv_T_strat; le = M.expo_25; use_log = true; arg = 0.0; }
+    } else {
+        T = 228.65 - 0.0028 * (z - 32000.0);
+        T = py_max(T, 180.0);
+        base = 868.02; arg = 0.0;     /* filled below once 1/(R*T) is known */
+    }
+    inv_RT = 1.0 / (M.R_gas * T);
+    if (use_log) arg = le * log(lx);
+    if (z > 32000.0 || z != z) arg = -(z - 32000.0) * (M.g0 * inv_RT);   /* -(z-32000)/(R*T/g) */
+    p = base * exp(arg);
+}
+
+/* environment.py:105-108 */
+EMC_HD double gravity(const DevModel &M, double z)
+{
+    const double Re = 6.371e6;
+    double r = Re / (Re + z);
+    return M.g0 * (r * r);
+}
+
+/* ---------------- wind table (environment.py:267-276 -> three np.interp on one grid) ------------- */
+EMC_HD void wind_bracket_load(const DevModel &M, const double *alt, const double *w, double z, WindBracket &B)
+{
+    const int n = M.n_wind;
+    if (z != z) {                               /* NaN altitude -> NaN wind, never valid */
+        B.lo = z; B.hi = z; B.x0 = 0.0;
+        B.f0[0] = B.f0[1] = B.f0[2] = z; B.s[0] = B.s[1] = B.s[2] = 0.0;
+        return;
+    }
+    int j; bool clamp = false;
+    if (z >= alt[n - 1]) { j = n - 1; clamp = true; B.lo = alt[n - 1]; B.hi = INFINITY; }
+    else if (z < alt[0]) { j = 0; clamp = true; B.lo = -INFINITY; B.hi = alt[0]; }
+    else {
+        int lo = 0, hi = n - 1;
+        if (M.wind_uniform) {                   /* guess, then fix up against the real knots */
+            int g = (int)((z - M.wind_alt0) * M.wind_inv_dz);
+            g = g < 0 ? 0 : (g > n - 2 ? n - 2 : g);
+            while (g > 0 && alt[g] > z) --g;
+            while (g < n - 2 && alt[g + 1] <= z) ++g;
+            lo = g;
+        } else {
+            while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (alt[mid] <= z) lo = mid; else hi = mid; }
+        }
+        j = lo; B.lo = alt[j]; B.hi = alt[j + 1];
+    }
+    B.x0 = alt[j];
+    for (int k = 0; k < 3; ++k) {
+        double f0 = w[3 * j + k];
+        B.f0[k] = f0;
+        B.s[k] = clamp ? 0.0 : (w[3 * (j + 1) + k] - f0) / (alt[j + 1] - alt[j]);
+    }
+}
+
+EMC_HD void wind_at(const DevModel &M, const double *alt, const Sample &S, double z, WindBracket &B, double w[3])
+{
+    if (!M.has_wind) { w[0] = w[1] = w[2] = 0.0; return; }
+    if (!(z >= B.lo && z < B.hi)) wind_bracket_load(M, alt, S.wind, z, B);
+    double dz = z - B.x0;
+    w[0] = B.s[0] * dz + B.f0[0];
+    w[1] = B.s[1] * dz + B.f0[1];
+    w[2] = B.s[2] * dz + B.f0[2];
+}
+
+/* ---------------- thrust (motor.py:54-76, 152-156), caller has checked pf>0 && t<=burn ---------- */
+EMC_HD double thrust_at(const DevModel &M, const DevTables &Tb, const Sample &S, double t, double p)
+{
+    if (t < 0.0 || t > S.burn_time) return 0.0;
+    if (M.motor_kind == EMC_MOTOR_SOLID) {
+        double f = interp_tab(Tb.th_t, Tb.th_f, Tb.th_s, M.n_thrust, t) * S.thrust_a;
+        return f + S.nozzle_area * (101325.0 - p);
+    }
+    return S.thrust_a - S.nozzle_area * p;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * The derivative, simulator.py:295-460.
+ *   chute      : sticky parachute flag (self.parachute_deployed), may be latched by any stage (F12)
+ *   want_diag  : stage 0 only — export Mach^2, q_inf, |alpha|, stability margin of this state
+ * ---------------------------------------------------------------------------------------------- */
+EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
+                       WindBracket &WB, double t, const State &s, bool &chute, double &chute_time,
+                       State &k, bool want_diag, Diag &dg)
+{
+    /* :305  pf = max(0.0, pf)  (NaN -> 0.0) */
+    const double pf = (s.pf > 0.0) ? s.pf : 0.0;
+    const bool burning = (pf > 0.0) && (t <= S.burn_time);
+
+    /* :308  normalise the quaternion (identity if |q| <= 1e-12 or NaN), utils.py:76-82 */
+    double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
+    double qw, qx, qy, qz;
+    if (n2 > 1e-24) { double rn = 1.0 / sqrt(n2); qw = s.q0 * rn; qx = s.q1 * rn; qy = s.q2 * rn; qz = s.q3 * rn; }
+    else { qw = 1.0; qx = 0.0; qy = 0.0; qz = 0.0; }
+
+    /* :311-321  mass properties, rocket.py:110-136 */
+    double mp = S.prop_mass * pf;
+    double mass = S.dry_mass + mp;
+    if (mass < S.dry_mass) { mass = S.dry_mass; mp = S.prop_mass * 0.0; }      /* :315-318 */
+    const double inv_m = 1.0 / mass;
+    const double cg = (S.dry_cg + mp * M.prop_cg) * inv_m;
+    const double dcg = M.prop_cg - cg;
+    const double Ixx = M.Ixx_dry + mp * M.d4sq;
+    const double Iyy = M.Iyy_dry + mp * (M.len2_12 + dcg * dcg);
+
+    /* :324  rotation matrix body->inertial, utils.py:100-111 (q already unit) */
+    const double r00 = 1.0 - 2.0 * (qy * qy + qz * qz), r01 = 2.0 * (qx * qy - qw * qz), r02 = 2.0 * (qx * qz + qw * qy);
+    const double r10 = 2.0 * (qx * qy + qw * qz), r11 = 1.0 - 2.0 * (qx * qx + qz * qz), r12 = 2.0 * (qy * qz - qw * qx);
+    const double r20 = 2.0 * (qx * qz - qw * qy), r21 = 2.0 * (qy * qz + qw * qx), r22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+
+    /* :328-338  atmosphere + wind */
+    double T, inv_RT, p;
+    atmosphere(M, s.z, T, inv_RT, p);
+    const double rho = p * inv_RT;
+    double w[3];
+    wind_at(M, wind_alt, S, s.z, WB, w);
+
+    /* :341-352 */
+    const double ux = s.vx - w[0], uy = s.vy - w[1], uz = s.vz - w[2];
+    const double vbx = r00 * ux + r10 * uy + r20 * uz;
+    const double vby = r01 * ux + r11 * uy + r21 * uz;
+    const double vbz = r02 * ux + r12 * uy + r22 * uz;
+    const double v2 = ux * ux + uy * uy + uz * uz;
+    const double mach2 = v2 * (inv_RT * (1.0 / 1.4));       /* (|v|/sqrt(1.4*R*T))^2, utils.py:152-157 */
+    const double mach = sqrt(mach2);
+    const double qdyn = 0.5 * rho * v2;
+
+    /* :359-363 thrust along body x */
+    double fbx = burning ? thrust_at(M, Tb, S, t, p) : 0.0;
+    double fby = 0.0, fbz = 0.0;
+    double my = 0.0, mz = 0.0;
+    /* :394-399: croll = 0.0 but q*0.0 keeps the reference's NaN/Inf propagation into roll */
+    double mx = 0.0;
+
+    /* :366-369 sticky parachute latch */
+    if (!chute && s.z <= M.chute_alt && s.vz < 0.0) { chute = true; chute_time = t; }
+
+    const bool aero = (!chute) && (qdyn > 0.0);
+    double alpha = 0.0, beta = 0.0;
+    const double vxz2 = vbx * vbx + vbz * vbz;
+    const double vb2 = vxz2 + vby * vby;
+    if (aero || want_diag) {
+        /* utils.py:160-172 */
+        const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
+        alpha = a_dead ? 0.0 : atan2(vbz, vbx);
+        if (aero) {
+            const double vxz = sqrt(vxz2);
+            const bool b_dead = vxz < 1e-6;
+            beta = b_dead ? 0.0 : atan2(vby, vxz);
+            /* sin/cos of alpha, beta from the velocity ratios (== sin/cos(atan2(...)) to rounding) */
+            double ca, sa, cb, sb;
+            if (a_dead) { ca = 1.0; sa = 0.0; } else { double iv = 1.0 / vxz; ca = vbx * iv; sa = vbz * iv; }
+            if (b_dead) { cb = 1.0; sb = 0.0; } else { double iv = 1.0 / sqrt(vb2); cb = vxz * iv; sb = vby * iv; }
+
+            /* rocket.py:138-218 */
+            double cd0, cda;
+            {
+                const int n = M.n_cd;
+                if (mach != mach) { cd0 = mach; cda = mach; }
+                else if (mach >= Tb.cd_mach[n - 1]) { cd0 = Tb.cd0[n - 1]; cda = Tb.cda[n - 1]; }
+                else if (mach <= Tb.cd_mach[0]) { cd0 = Tb.cd0[0]; cda = Tb.cda[0]; }
+                else {
+                    int j = bracket_small(Tb.cd_mach, n, mach);
+                    double dm = mach - Tb.cd_mach[j];
+                    cd0 = Tb.cd0_s[j] * dm + Tb.cd0[j];
+                    cda = Tb.cda_s[j] * dm + Tb.cda[j];
+                }
+            }
+            cd0 *= S.cd_scale;
+            double cd = cd0 + cda * (alpha * alpha);
+            if (!(pf > 0.0)) cd *= M.power_off_factor;
+            const double abs_alpha = fabs(alpha);
+            const double beta_m = sqrt(fabs(1.0 - mach2));
+            const double tt = M.AR_over_cos * beta_m;
+            const double cl_alpha = (M.two_pi_AR / (2.0 + sqrt(4.0 + tt * tt))) * M.cos_sweep;
+            double cl = cl_alpha * alpha;
+            double cy = cl_alpha * beta;
+            if (abs_alpha > M.stall_angle) {
+                const double over = (abs_alpha - M.stall_angle) * M.inv_stall_span;
+                double sf = 1.0 - over;
+                sf = (sf > 0.0) ? sf : 0.0;
+                const double sgn = (alpha > 0.0) ? 1.0 : ((alpha < 0.0) ? -1.0 : alpha);
+                cl = cl_alpha * M.stall_angle * sf * sgn;
+                cd *= 1.0 + 0.5 * over;
+                cy *= sf;
+            }
+            const double cp = M.cp_location + interp_tab(Tb.cp_mach, Tb.cp_shift, Tb.cp_s, M.n_cp, mach);
+            const double sm = cp - cg;
+            const double cm = -cl_alpha * sm * alpha;
+            const double cyaw = -cl_alpha * sm * beta;
+            dg.stab = sm * M.inv_ref_diam;
+
+            /* :385-391  F_b += W2B(alpha,beta) @ [-D,-S,-L], utils.py:199-205 */
+            const double qa = qdyn * M.ref_area;
+            const double D = qa * cd, L = qa * cl, Sd = qa * cy;
+            fbx += (ca * cb) * (-D) + (-sb) * (-Sd) + (sa * cb) * (-L);
+            fby += (ca * sb) * (-D) + cb * (-Sd) + (sa * sb) * (-L);
+            fbz += (-sa) * (-D) + ca * (-L);
+            /* :394-411 */
+            const double qad = qdyn * M.area_diam;
+            mx = qdyn * 0.0;
+            my = qad * cm;
+            mz = qad * cyaw;
+        }
+    }
+    if (chute) {
+        /* :372-377 */
+        const double rel = sqrt(vb2);
+        if (rel > 0.0) {
+            const double drag = (0.5 * rho * vb2 * M.chute_cd) * M.chute_area;
+            const double f = -drag / rel;
+            fbx += f * vbx; fby += f * vby; fbz += f * vbz;
+        }
+    }
+    if (want_diag) {
+        dg.mach2 = mach2;
+        dg.qdyn = qdyn;
+        dg.abs_aoa = fabs(alpha);
+        if (!aero) dg.stab = (M.cp_location + interp_tab(Tb.cp_mach, Tb.cp_shift, Tb.cp_s, M.n_cp, mach) - cg) * M.inv_ref_diam;
+    }
+
+    /* :414-415 damping */
+    my += -M.pitch_damping * s.wy;
+    mz += -M.yaw_damping * s.wz;
+
+    /* :418-425 */
+    const double g = gravity(M, s.z);
+    const double fix = r00 * fbx + r01 * fby + r02 * fbz;
+    const double fiy = r10 * fbx + r11 * fby + r12 * fbz;
+    const double fiz = r20 * fbx + r21 * fby + r22 * fbz - mass * g;
+    k.x = s.vx; k.y = s.vy; k.z = s.vz;
+    k.vx = fix * inv_m; k.vy = fiy * inv_m; k.vz = fiz * inv_m;
+
+    /* :431-436  Euler equations with Izz == Iyy (rocket.py:127); Ixx, Iyy > 0 */
+    const double inv_Iyy = 1.0 / Iyy;
+    /* roll: (mx - (Izz-Iyy)*wy*wz)/Ixx with Izz-Iyy == 0 and mx in {0, NaN}: no division needed */
+    k.wx = (Ixx > 0.0) ? (mx - 0.0 * (s.wy * s.wz)) : 0.0;
+    k.wy = (Iyy > 0.0) ? (my - (Ixx - Iyy) * s.wz * s.wx) * inv_Iyy : 0.0;
+    k.wz = (Iyy > 0.0) ? (mz - (Iyy - Ixx) * s.wx * s.wy) * inv_Iyy : 0.0;
+
+    /* :439  q_dot = 0.5 * q (x) (0,w) - 0.5*(q.q - 1)*q on the unit quaternion, utils.py:114-121 */
+    const double ne = (qw * qw + qx * qx + qy * qy + qz * qz) - 1.0;
+    const double hc = 0.5 * ne;
+    k.q0 = 0.5 * (-qx * s.wx - qy * s.wy - qz * s.wz) - hc * qw;
+    k.q1 = 0.5 * (qw * s.wx + qy * s.wz - qz * s.wy) - hc * qx;
+    k.q2 = 0.5 * (qw * s.wy - qx * s.wz + qz * s.wx) - hc * qy;
+    k.q3 = 0.5 * (qw * s.wz + qx * s.wy - qy * s.wx) - hc * qz;
+
+    /* :442-450 propellant; the 10 ms taper test pf/|rate| < 0.01 is written as pf < 0.01*|rate|
+     * (the two branches are continuous at the boundary) */
+    double pfr = 0.0;
+    if (burning) {
+        pfr = S.pf_rate;
+        if (pfr != 0.0 && pf < 0.01 * fabs(pfr)) pfr = -pf / 0.01;
+    }
+    k.pf = pfr;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Flight bookkeeping: everything the loop of simulator.py:216-264 and the summary of :474-494 need
+ * ---------------------------------------------------------------------------------------------- */
+struct Track {
+    double t, t_rail;
+    double apogee_alt, apogee_t;      /* running np.argmax(altitudes), :488 */
+    double apogee_time_latch, max_coast;  /* :247-257 */
+    double burnout_time, chute_time;
+    double max_mach2, max_q, max_v2, max_om, min_stab, max_stab, max_aoa;
+    int32_t n_steps, apogee_index, first_nan, term;
+    bool chute, apogee_detected, burnout_found;
+    bool finishing;   /* loop ended: one more stage-0 pass exports the last stored state's diagnostics */
+    bool replay;      /* ended by the all-NaN fast-forward: t is replayed to max_time before retiring */
+};
+
+EMC_HD void track_init(Track &K, const State &s, double t_rail)
+{
+    K.t = t_rail; K.t_rail = t_rail;
+    K.apogee_alt = s.z; K.apogee_t = t_rail; K.apogee_index = 0;
+    K.first_nan = (s.z != s.z) ? 0 : -1;
+    K.apogee_time_latch = 0.0; K.max_coast = 0.0;
+    K.burnout_time = 0.0; K.burnout_found = false;
+    K.chute_time = NAN; K.chute = false; K.apogee_detected = false;
+    K.n_steps = 0; K.term = EMC_TERM_NONE; K.finishing = false; K.replay = false;
+    K.max_mach2 = -INFINITY; K.max_q = -INFINITY; K.max_v2 = -INFINITY; K.max_om = -INFINITY;
+    K.min_stab = INFINITY; K.max_stab = -INFINITY; K.max_aoa = -INFINITY;
+}
+
+/* diagnostics of a stored state (stage 0 of the next step, or the final extra evaluation) */
+EMC_HD void track_diag(Track &K, const State &s, const Diag &d)
+{
+    np_max_acc(K.max_mach2, d.mach2);
+    np_max_acc(K.max_q, d.qdyn);
+    np_max_acc(K.max_v2, s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);
+    double om = fabs(s.wx);
+    np_max_acc(om, fabs(s.wy));
+    np_max_acc(om, fabs(s.wz));
+    np_max_acc(K.max_om, om);
+    np_min_acc(K.min_stab, d.stab);
+    np_max_acc(K.max_stab, d.stab);
+    np_max_acc(K.max_aoa, d.abs_aoa);
+}
+
+/* After an accepted step: t already advanced, s is the new stored state (:229-264).
+ * Returns true when the loop of :216 ends (break or guard). */
+EMC_HD bool track_post_step(const DevModel &M, const Sample &S, Track &K, const State &s)
+{
+    K.n_steps += 1;
+    const double z = s.z, vz = s.vz;
+    if (!(K.apogee_alt != K.apogee_alt) && ((z != z) || z > K.apogee_alt)) {
+        K.apogee_alt = z; K.apogee_index = K.n_steps; K.apogee_t = K.t;
+    }
+    if (K.first_nan < 0 && (z != z)) K.first_nan = K.n_steps;
+    if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
+    if (z <= 0.5 && vz <= 0.0) { K.term = EMC_TERM_GROUND; return true; }
+    if (z > 100000.0) { K.term = EMC_TERM_ALTITUDE; return true; }
+    if (z > 1000.0 && vz < 0.0 && !K.apogee_detected) {
+        K.apogee_detected = true;
+        K.apogee_time_latch = K.t;
+        K.max_coast = (z > 50000.0) ? 60.0 : ((z > 25000.0) ? 120.0 : 300.0);
+    }
+    if (K.apogee_detected && z > 25000.0) {
+        if (K.t - K.apogee_time_latch > K.max_coast) { K.term = EMC_TERM_COAST; return true; }
+    }
+    if (!(K.t < M.max_time)) { K.term = EMC_TERM_MAX_TIME; return true; }
+    return false;
+}
+
+/* One classical RK4 step (simulator.py:217-229): the four stages share ONE copy of the derivative.
+ * Stage 0 doubles as the diagnostics pass of the stored state s (simulator.py:511-552 evaluates the
+ * same quantities at the same state).  A lane whose loop has ended (K.finishing) runs stage 0 only,
+ * for the diagnostics of its last stored state, with the sticky flag protected: the reference never
+ * evaluates the derivative there.  Returns true if a full step was taken. */
+EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
+                     WindBracket &WB, Track &K, State &s)
+{
+    State ys = s, acc = s, k;     /* acc is overwritten by stage 0 */
+    Diag dg;
+    dg.mach2 = dg.qdyn = dg.abs_aoa = dg.stab = 0.0;
+    const bool fin = K.finishing;
+    const bool chute_keep = K.chute;
+    const double chute_time_keep = K.chute_time;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int stage = 0; stage < 4; ++stage) {
+        const double ts = (stage == 0) ? K.t : ((stage == 3) ? K.t + M.dt : K.t + M.half_dt);
+        derivative(M, Tb, wind_alt, S, WB, ts, ys, K.chute, K.chute_time, k, stage == 0, dg);
+        if (stage == 0) {
+            track_diag(K, s, dg);
+            if (fin) { K.chute = chute_keep; K.chute_time = chute_time_keep; return false; }
+            acc = k;
+        } else {
+            const double wgt = (stage == 3) ? 1.0 : 2.0;
+            acc.x += wgt * k.x; acc.y += wgt * k.y; acc.z += wgt * k.z;
+            acc.vx += wgt * k.vx; acc.vy += wgt * k.vy; acc.vz += wgt * k.vz;
+            acc.q0 += wgt * k.q0; acc.q1 += wgt * k.q1; acc.q2 += wgt * k.q2; acc.q3 += wgt * k.q3;
+            acc.wx += wgt * k.wx; acc.wy += wgt * k.wy; acc.wz += wgt * k.wz;
+            acc.pf += wgt * k.pf;
+        }
+        if (stage < 3) {
+            const double c = (stage == 2) ? M.dt : M.half_dt;
+            ys.x = s.x + c * k.x; ys.y = s.y + c * k.y; ys.z = s.z + c * k.z;
+            ys.vx = s.vx + c * k.vx; ys.vy = s.vy + c * k.vy; ys.vz = s.vz + c * k.vz;
+            ys.q0 = s.q0 + c * k.q0; ys.q1 = s.q1 + c * k.q1; ys.q2 = s.q2 + c * k.q2; ys.q3 = s.q3 + c * k.q3;
+            ys.wx = s.wx + c * k.wx; ys.wy = s.wy + c * k.wy; ys.wz = s.wz + c * k.wz;
+            ys.pf = s.pf + c * k.pf;
+        }
+    }
+    const double h = M.dt_over_6;
+    s.x += h * acc.x; s.y += h * acc.y; s.z += h * acc.z;
+    s.vx += h * acc.vx; s.vy += h * acc.vy; s.vz += h * acc.vz;
+    s.q0 += h * acc.q0; s.q1 += h * acc.q1; s.q2 += h * acc.q2; s.q3 += h * acc.q3;
+    s.wx += h * acc.wx; s.wy += h * acc.wy; s.wz += h * acc.wz;
+    s.pf += h * acc.pf;
+    /* :227 renormalise */
+    const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
+    if (n2 > 1e-24) { const double rn = 1.0 / sqrt(n2); s.q0 *= rn; s.q1 *= rn; s.q2 *= rn; s.q3 *= rn; }
+    else { s.q0 = 1.0; s.q1 = 0.0; s.q2 = 0.0; s.q3 = 0.0; }
+    K.t += M.dt;
+    return true;
+}
+
+/* True once nothing but `t` can change any more: position and velocity are all NaN, so no break
+ * test of simulator.py:238-264 can fire and every later stored state is NaN. */
+EMC_HD bool all_nan(const State &s)
+{
+    return (s.x != s.x) && (s.y != s.y) && (s.z != s.z) && (s.vx != s.vx) && (s.vy != s.vy) && (s.vz != s.vz);
+}
+
+/* NaN fast-forward: replay only the time accumulation of :229 (and the burnout-index test of
+ * :479-480, which reads nothing but the time) until the guard of :216 ends the loop */
+EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K)
+{
+    int64_t n = 0;
+    while (!K.burnout_found && K.t < M.max_time) {
+        K.t += M.dt; K.n_steps += 1; ++n;
+        if ((K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
+    }
+    while (K.t < M.max_time) { K.t += M.dt; K.n_steps += 1; ++n; }
+    K.term = EMC_TERM_MAX_TIME;
+    return n;
+}
+
+/* One scheduling quantum of a lane, shared by the flight kernel and the test seam: a full RK4 step
+ * plus the event logic, or the closing diagnostics pass.  Returns true when the lane retires (its
+ * outputs are final).  `stepped` reports whether a stored state was produced (tape). */
+EMC_HD bool lane_advance(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
+                         WindBracket &WB, Track &K, State &s, bool nan_ff, bool &stepped, int64_t &replayed)
+{
+    stepped = rk4_step(M, Tb, wind_alt, S, WB, K, s);
+    if (!stepped) {                       /* closing pass done */
+        if (K.replay) replayed += replay_time(M, S, K);
+        return true;
+    }
+    bool done = track_post_step(M, S, K, s);
+    if (!done && nan_ff && all_nan(s)) { K.replay = true; done = true; }
+    K.finishing = done;
+    return false;
+}
+
+/* write the flight part of the summary (strided SoA column) */
+EMC_HD void write_flight_outputs(const Track &K, const State &s, double *out, int32_t *iout, int64_t ld)
+{
+    out[EMC_OUT_APOGEE_ALTITUDE * ld] = K.apogee_alt;
+    out[EMC_OUT_APOGEE_TIME * ld] = K.apogee_t - K.t_rail;
+    out[EMC_OUT_RANGE * ld] = sqrt(s.x * s.x + s.y * s.y);
+    out[EMC_OUT_FLIGHT_TIME * ld] = K.t - K.t_rail;
+    out[EMC_OUT_FINAL_X * ld] = s.x; out[EMC_OUT_FINAL_Y * ld] = s.y; out[EMC_OUT_FINAL_Z * ld] = s.z;
+    out[EMC_OUT_FINAL_VX * ld] = s.vx; out[EMC_OUT_FINAL_VY * ld] = s.vy; out[EMC_OUT_FINAL_VZ * ld] = s.vz;
+    out[EMC_OUT_MAX_MACH * ld] = sqrt(K.max_mach2);
+    out[EMC_OUT_MAX_Q * ld] = K.max_q;
+    out[EMC_OUT_MAX_SPEED * ld] = sqrt(K.max_v2);
+    out[EMC_OUT_MAX_ABS_OMEGA * ld] = K.max_om;
+    out[EMC_OUT_MIN_STABILITY * ld] = K.min_stab;
+    out[EMC_OUT_MAX_STABILITY * ld] = K.max_stab;
+    out[EMC_OUT_MAX_ABS_AOA * ld] = K.max_aoa;
+    out[EMC_OUT_BURNOUT_TIME * ld] = K.burnout_time;
+    out[EMC_OUT_CHUTE_TIME * ld] = K.chute_time;
+    iout[EMC_IOUT_N_STEPS * ld] = K.n_steps;
+    iout[EMC_IOUT_TERMINATION * ld] = K.term;
+    iout[EMC_IOUT_APOGEE_INDEX * ld] = K.apogee_index;
+    iout[EMC_IOUT_FIRST_NAN_STEP * ld] = K.first_nan;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Sample loading and the rail phase (simulator.py:42-125)
+ * ---------------------------------------------------------------------------------------------- */
+EMC_HD void load_sample(const DevModel &M, const double *col, int64_t ld, const double *wind, Sample &S)
+{
+    S.dry_mass = col[EMC_IN_DRY_MASS * ld];
+    S.prop_mass = col[EMC_IN_PROP_MASS * ld];
+    S.dry_cg = S.dry_mass * M.cg_dry;
+    S.thrust_a = col[EMC_IN_THRUST_A * ld];
+    S.nozzle_area = col[EMC_IN_NOZZLE_AREA * ld];
+    S.burn_time = col[EMC_IN_BURN_TIME * ld];
+    S.pf_rate = -col[EMC_IN_MDOT * ld] / S.prop_mass;
+    S.cd_scale = col[EMC_IN_CD_SCALE * ld];
+    S.wind = wind;
+}
+
+EMC_HD void wind_bracket_reset(WindBracket &B)
+{
+    B.lo = 1.0; B.hi = 0.0; B.x0 = 0.0;     /* empty interval: first use loads */
+    B.f0[0] = B.f0[1] = B.f0[2] = 0.0; B.s[0] = B.s[1] = B.s[2] = 0.0;
+}
+
+/* motor.py:86-93 */
+EMC_HD double propellant_remaining(const Sample &S, double t)
+{
+    if (t <= 0.0) return 1.0;
+    if (t >= S.burn_time) return 0.0;
+    double r = 1.0 - t / S.burn_time;
+    return (r > 0.0) ? r : 0.0;
+}
+
+/* Rail phase for one sample; writes the rail_* outputs and returns the number of Euler steps.
+ * The state at rail exit is (out[RAIL_EXIT_X..VZ], q and omega unchanged, pf = remaining(t)). */
+EMC_HD int rail_phase(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
+                      const double *col, int64_t ld, double *out, int64_t old)
+{
+    double px = col[EMC_IN_X * ld], py = col[EMC_IN_Y * ld], pz = col[EMC_IN_Z * ld];
+    double vx = col[EMC_IN_VX * ld], vy = col[EMC_IN_VY * ld], vz = col[EMC_IN_VZ * ld];
+    const double q0 = col[EMC_IN_Q0 * ld], q1 = col[EMC_IN_Q1 * ld], q2 = col[EMC_IN_Q2 * ld], q3 = col[EMC_IN_Q3 * ld];
+    double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+    double qw, qx, qy, qz;
+    if (n2 > 1e-24) { double rn = 1.0 / sqrt(n2); qw = q0 * rn; qx = q1 * rn; qy = q2 * rn; qz = q3 * rn; }
+    else { qw = 1.0; qx = 0.0; qy = 0.0; qz = 0.0; }
+    const double r00 = 1.0 - 2.0 * (qy * qy + qz * qz), r01 = 2.0 * (qx * qy - qw * qz), r02 = 2.0 * (qx * qz + qw * qy);
+    const double r10 = 2.0 * (qx * qy + qw * qz), r11 = 1.0 - 2.0 * (qx * qx + qz * qz), r12 = 2.0 * (qy * qz - qw * qx);
+    const double r20 = 2.0 * (qx * qz - qw * qy), r21 = 2.0 * (qy * qz + qw * qx), r22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+    const double dx = r00, dy = r10, dz = r20;                /* :57 body x in inertial axes */
+    WindBracket WB;
+    wind_bracket_reset(WB);
+    double dist = 0.0, t = 0.0, pf = 1.0;
+    const double dt = M.dt_rail;
+    int steps = 0;
+    while (dist < M.rail_length && t < S.burn_time) {          /* :63 */
+        const double pfc = pf;
+        const double mp = S.prop_mass * pfc;
+        const double mass = S.dry_mass + mp;
+        double T, inv_RT, p;
+        atmosphere(M, pz, T, inv_RT, p);
+        const double rho = p * inv_RT;
+        double w[3];
+        wind_at(M, wind_alt, S, pz, WB, w);
+        double speed = vx * dx + vy * dy + vz * dz;            /* :75 */
+        const double rx = dx * speed - w[0], ry = dy * speed - w[1], rz = dz * speed - w[2];
+        const double rel_speed = rx * dx + ry * dy + rz * dz;  /* :80 */
+        const double mach = sqrt((rx * rx + ry * ry + rz * rz) * (inv_RT * (1.0 / 1.4)));
+        double cd = interp_tab(Tb.cd_mach, Tb.cd0, Tb.cd0_s, M.n_cd, mach) * S.cd_scale
+                    + interp_tab(Tb.cd_mach, Tb.cda, Tb.cda_s, M.n_cd, mach) * 0.0;   /* alpha = 0, :82-83 */
+        const double drag = 0.5 * rho * (rel_speed * rel_speed) * cd * M.ref_area;     /* :84 */
+        const double thrust = thrust_at(M, Tb, S, t, p);       /* :86 */
+        const double g = gravity(M, pz);
+        const double accel = (thrust - mass * g - drag) / mass; /* :88 */
+        speed += accel * dt;
+        px += dx * speed * dt; py += dy * speed * dt; pz += dz * speed * dt;
+        dist += speed * dt;
+        vx = dx * speed; vy = dy * speed; vz = dz * speed;
+        t += dt;
+        pf = propellant_remaining(S, t);                       /* :96 */
+        ++steps;
+    }
+    /* :103-123 */
+    out[EMC_OUT_RAIL_EXIT_TIME * old] = t;
+    out[EMC_OUT_RAIL_EXIT_X * old] = px; out[EMC_OUT_RAIL_EXIT_Y * old] = py; out[EMC_OUT_RAIL_EXIT_Z * old] = pz;
+    out[EMC_OUT_RAIL_EXIT_VX * old] = vx; out[EMC_OUT_RAIL_EXIT_VY * old] = vy; out[EMC_OUT_RAIL_EXIT_VZ * old] = vz;
+    out[EMC_OUT_RAIL_EXIT_SPEED * old] = sqrt(vx * vx + vy * vy + vz * vz);
+    {   /* utils.py:139-144,46-69 on the RAW quaternion */
+        const double x = q1, y = q2, z = q3, ww = q0;
+        out[EMC_OUT_RAIL_EXIT_ROLL * old] = atan2(2.0 * (ww * x + y * z), 1.0 - 2.0 * (x * x + y * y));
+        const double sinp = 2.0 * (ww * y - z * x);
+        out[EMC_OUT_RAIL_EXIT_PITCH * old] = (fabs(sinp) >= 1.0) ? copysign(1.5707963267948966, sinp) : asin(sinp);
+        out[EMC_OUT_RAIL_EXIT_YAW * old] = atan2(2.0 * (ww * z + x * y), 1.0 - 2.0 * (y * y + z * z));
+    }
+    double w[3];
+    wind_at(M, wind_alt, S, pz, WB, w);
+    const double ux = vx - w[0], uy = vy - w[1], uz = vz - w[2];
+    const double vbx = r00 * ux + r10 * uy + r20 * uz;
+    const double vby = r01 * ux + r11 * uy + r21 * uz;
+    const double vbz = r02 * ux + r12 * uy + r22 * uz;
+    out[EMC_OUT_RAIL_EXIT_AOA * old] = ((fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6)) ? 0.0 : atan2(vbz, vbx);
+    const double vxz = sqrt(vbx * vbx + vbz * vbz);
+    out[EMC_OUT_RAIL_EXIT_SIDESLIP * old] = (vxz < 1e-6) ? 0.0 : atan2(vby, vxz);
+    out[EMC_OUT_WIND_AT_EXIT_U * old] = w[0]; out[EMC_OUT_WIND_AT_EXIT_V * old] = w[1]; out[EMC_OUT_WIND_AT_EXIT_W * old] = w[2];
+    return steps;
+}
+
+/* State at rail exit, rebuilt from the inputs and the rail outputs (simulator.py:98-100,161) */
+EMC_HD void load_flight_state(const Sample &S, const double *col, int64_t ld, const double *out, int64_t old,
+                              State &s, double &t_rail)
+{
+    t_rail = out[EMC_OUT_RAIL_EXIT_TIME * old];
+    s.x = out[EMC_OUT_RAIL_EXIT_X * old]; s.y = out[EMC_OUT_RAIL_EXIT_Y * old]; s.z = out[EMC_OUT_RAIL_EXIT_Z * old];
+    s.vx = out[EMC_OUT_RAIL_EXIT_VX * old]; s.vy = out[EMC_OUT_RAIL_EXIT_VY * old]; s.vz = out[EMC_OUT_RAIL_EXIT_VZ * old];
+    s.q0 = col[EMC_IN_Q0 * ld]; s.q1 = col[EMC_IN_Q1 * ld]; s.q2 = col[EMC_IN_Q2 * ld]; s.q3 = col[EMC_IN_Q3 * ld];
+    s.wx = col[EMC_IN_WX * ld]; s.wy = col[EMC_IN_WY * ld]; s.wz = col[EMC_IN_WZ * ld];
+    s.pf = propellant_remaining(S, t_rail);
+}
+
+}  // namespace emc

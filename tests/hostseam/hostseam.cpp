@@ -1,0 +1,74 @@
+/*
+ * hostseam.cpp — TEST SEAM.  Compiles the engine's device physics (csrc/emc_physics.cuh, the very
+ * code the CUDA kernels inline) with g++ so that parity against the oracle and the golden vectors
+ * can be checked in a container without a GPU.  It is built into tests/hostseam/_build only, is
+ * loaded only by tests/, and is neither part of libemc.so nor reachable from the Python package:
+ * the product has no CPU path.
+ */
+#include <stdint.h>
+#include <string.h>
+
+#include "../../erpl_monte_carlo_sim_b200/csrc/emc_model_build.h"
+
+using namespace emc;
+
+extern "C" {
+
+__attribute__((visibility("default")))
+int hs_derivative(const emc_model *m, const emc_inputs *in, int64_t n, const double *t, const double *state,
+                  int32_t *chute, double *state_dot)
+{
+    if (validate_model(*m)) return -1;
+    DevModel D; DevTables T;
+    build_dev_model(*m, D, T);
+    for (int64_t i = 0; i < n; ++i) {
+        Sample S;
+        load_sample(D, in->scalars + i, in->ld, in->wind ? in->wind + i * in->wind_sample_stride : nullptr, S);
+        WindBracket WB; wind_bracket_reset(WB);
+        State s, k; Diag dg;
+        memcpy(&s, state + 14 * i, sizeof s);
+        bool ch = chute[i] != 0; double ct = NAN;
+        derivative(D, T, m->wind_altitudes, S, WB, t[i], s, ch, ct, k, true, dg);
+        chute[i] = ch ? 1 : 0;
+        memcpy(state_dot + 14 * i, &k, sizeof k);
+    }
+    return 0;
+}
+
+/* n flights, rail + RK4 loop, exactly the per-lane sequence of the flight kernel */
+__attribute__((visibility("default")))
+int hs_batch(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outputs *o, int nan_fast_forward,
+             double *tape, int64_t tape_cap, int64_t *n_states)
+{
+    if (validate_model(*m)) return -1;
+    DevModel D; DevTables T;
+    build_dev_model(*m, D, T);
+    for (int64_t i = 0; i < n; ++i) {
+        const double *col = in->scalars + i;
+        double *out = o->out + i; int32_t *iout = o->iout + i;
+        Sample S;
+        load_sample(D, col, in->ld, in->wind ? in->wind + i * in->wind_sample_stride : nullptr, S);
+        iout[EMC_IOUT_RAIL_STEPS * o->ld] = rail_phase(D, T, m->wind_altitudes, S, col, in->ld, out, o->ld);
+        State s; double t_rail;
+        load_flight_state(S, col, in->ld, out, o->ld, s, t_rail);
+        Track K; track_init(K, s, t_rail);
+        WindBracket WB; wind_bracket_reset(WB);
+        int64_t ns = 1, replayed = 0;
+        if (tape && tape_cap > 0) { tape[0] = K.t; memcpy(tape + 1, &s, sizeof s); }
+        if (!(K.t < D.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
+        for (;;) {
+            bool stepped;
+            bool retired = lane_advance(D, T, m->wind_altitudes, S, WB, K, s, nan_fast_forward != 0, stepped, replayed);
+            if (stepped) {
+                if (tape && ns < tape_cap) { tape[ns * EMC_TAPE_WIDTH] = K.t; memcpy(tape + ns * EMC_TAPE_WIDTH + 1, &s, sizeof s); }
+                ++ns;
+            }
+            if (retired) break;
+        }
+        write_flight_outputs(K, s, out, iout, o->ld);
+        if (n_states) *n_states = ns;
+    }
+    return 0;
+}
+
+}

@@ -1,0 +1,200 @@
+"""GPU (-m gpu): the CUDA engine, called through the C ABI (libemc.so via ctypes), against
+  * the golden vectors of the unmodified Python reference (tests/golden, oracle/make_golden.py),
+  * the C oracle (oracle/emc_oracle.c) on larger seeded batches,
+  * size-independent properties at full batch size (determinism, shard invariance, scheduling
+    invariance).
+Bar (BASELINE.json north_star): integers exact (step counts, termination codes, apogee indices),
+FP64 summaries within 1e-6 relative."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import util
+from erpl_monte_carlo_sim_b200 import _abi, _lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", util.DERIV_SETS)
+def test_gpu_derivative(engine, name):
+    z = util.golden(name)
+    engine.set_model(_abi.model_from_npz(z))
+    sd, ch = engine.derivative_debug(z["scalars"], z["wind"] if z["wind"].size else None, z["t"], z["state"], z["chute_in"])
+    ref = z["state_dot"]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.nanmax(np.abs(sd - ref) / np.maximum(scale, 1e-300)) < 1e-12
+    assert np.array_equal(np.isnan(sd), np.isnan(ref))
+    assert np.array_equal(ch, z["chute_out"])
+
+
+def test_gpu_single_flights(engine):
+    z = util.golden("flights_single")
+    for name in z["names"]:
+        md, sc, wind, ref, iref = util.single_case(z, str(name))
+        engine.set_model(md)
+        out, iout = engine.run_batch(sc, wind)
+        np.testing.assert_array_equal(iout, iref, err_msg=str(name))
+        util.assert_summary_close(out, ref, what=str(name))
+
+
+@pytest.mark.parametrize("name", util.MC_SETS)
+def test_gpu_mc_sets(engine, name):
+    z = util.golden(name)
+    engine.set_model(_abi.model_from_npz(z))
+    out, iout = engine.run_batch(z["scalars"], z["wind"])
+    np.testing.assert_array_equal(iout, z["iout"])
+    util.assert_summary_close(out, z["out"], what=name)
+    c = engine.counters()
+    assert c["kernel_launches"] == 2 and c["refills"] == z["scalars"].shape[1]
+    nan_ff = z["iout"][_abi.IOUT["first_nan_step"]] >= 0
+    assert c["rk4_steps"] + c["replay_steps"] == int(z["iout"][0].sum())
+    assert (c["replay_steps"] > 0) == bool(nan_ff.any())
+
+
+def test_gpu_tape(engine):
+    z = util.golden("flights_single")
+    for name in ("c1b_example_liquid_csv", "c1c_planar_liquid"):
+        md, sc, wind, ref, iref = util.single_case(z, name)
+        engine.set_model(md)
+        out, iout, tape = engine.run_tape(sc, wind)
+        assert tape.shape[0] == iref[0, 0] + 1
+        np.testing.assert_array_equal(iout, iref)
+        util.assert_summary_close(out, ref, what=name)
+        idx = z[name + "__series__idx"]
+        ref_rows = z[name + "__series__tape"]
+        ok = np.abs(ref_rows) < 1e15
+        scale = np.maximum(np.abs(ref_rows), np.abs(ref_rows).max(axis=0, keepdims=True) * 1e-3)
+        assert np.max((np.abs(tape[idx] - ref_rows) / scale)[ok]) < 1e-6
+
+
+def test_gpu_tape_capacity_error(engine):
+    z = util.golden("flights_single")
+    md, sc, wind, ref, iref = util.single_case(z, "c1b_example_liquid_csv")
+    engine.set_model(md)
+    with pytest.raises(_lib.EmcError, match="EMC_ERR_CAPACITY"):
+        engine.run_tape(sc, wind, cap=100)
+
+
+def test_gpu_scheduling_invariance(engine):
+    """Results do not depend on how lanes are scheduled: refill threshold, block size, occupancy and the
+    NaN fast-forward give bit-identical outputs (each trajectory is integrated by one lane alone)."""
+    z = util.golden("mc_liquid_default")
+    engine.set_model(_abi.model_from_npz(z))
+    base = engine.run_batch(z["scalars"], z["wind"])
+    for kw in (dict(refill_threshold=32), dict(refill_threshold=8, block_threads=64), dict(block_threads=256),
+               dict(block_threads=128, blocks_per_sm=3), dict(block_threads=128, blocks_per_sm=4)):
+        got = engine.run_batch(z["scalars"], z["wind"], opts=_lib.run_opts(**kw))
+        np.testing.assert_array_equal(got[0], base[0], err_msg=str(kw))
+        np.testing.assert_array_equal(got[1], base[1], err_msg=str(kw))
+    few = np.flatnonzero(z["iout"][_abi.IOUT["first_nan_step"]] >= 0)[:2]
+    a = engine.run_batch(z["scalars"][:, few], z["wind"][few], opts=_lib.run_opts(nan_fast_forward=False))
+    np.testing.assert_array_equal(a[0], base[0][:, few])
+    np.testing.assert_array_equal(a[1], base[1][:, few])
+    assert engine.counters()["replay_steps"] == 0
+
+
+def _synth(z, n, seed):
+    """n seeded synthetic samples around a golden set: resample columns, jitter masses/thrust/attitude/wind."""
+    rng = np.random.RandomState(seed)
+    pick = rng.randint(0, z["scalars"].shape[1], n)
+    sc = z["scalars"][:, pick].copy()
+    wind = z["wind"][pick].copy()
+    IN = _abi.IN
+    k = rng.normal(1.0, 0.02, n)
+    sc[IN["dry_mass"]] *= k; sc[IN["prop_mass"]] *= k
+    sc[IN["burn_time"]] = sc[IN["prop_mass"]] / sc[IN["mdot"]]
+    q = sc[IN["q0"]:IN["q3"] + 1] + rng.normal(0, 2e-3, (4, n))
+    sc[IN["q0"]:IN["q3"] + 1] = q / np.linalg.norm(q, axis=0)
+    sc[IN["vx"]:IN["vz"] + 1] += rng.normal(0, 0.1, (3, n))
+    wind *= rng.uniform(0.5, 1.5, (n, 1, 1))
+    return np.ascontiguousarray(sc), np.ascontiguousarray(wind)
+
+
+@pytest.mark.parametrize("name,n", [("mc_solid_csv", 768), ("mc_liquid_default", 512), ("mc_planar_solid", 24)])
+def test_gpu_vs_oracle_seeded_batch(engine, name, n):
+    z = util.golden(name)
+    md = _abi.model_from_npz(z)
+    sc, wind = _synth(z, n, seed=2024)
+    if name.startswith("mc_planar"):
+        wind[:, :, 1] = 0.0
+    engine.set_model(md)
+    out, iout = engine.run_batch(sc, wind)
+    ref, iref = O.batch(md, sc, wind)
+    # a step count may differ only where an event test sits within rounding of its threshold
+    same = np.all(iout == iref, axis=0)
+    assert same.mean() >= 0.995, f"{(~same).sum()} of {n} samples differ in step count/termination"
+    util.assert_summary_close(out[:, same], ref[:, same], what=name)
+
+
+def test_gpu_full_size_properties(engine):
+    """BASELINE config C3 size (100k samples, Solid + 6-knot wind table): determinism, shard invariance,
+    valid termination codes, counters consistent with the per-sample step counts."""
+    z = util.golden("mc_solid_csv")
+    md = _abi.model_from_npz(z)
+    n = 100_000
+    sc, wind = _synth(z, n, seed=7)
+    engine.set_model(md)
+    out, iout = engine.run_batch(sc, wind)
+    c = engine.counters()
+    steps = iout[_abi.IOUT["n_steps"]].astype(np.int64)
+    assert c["rk4_steps"] + c["replay_steps"] == int(steps.sum())
+    assert c["refills"] == n
+    term = iout[_abi.IOUT["termination"]]
+    assert np.all((term >= 1) & (term <= 4))
+    assert np.all(steps >= 1)
+    ft = out[_abi.OUT["flight_time"]]
+    assert np.allclose(ft, steps * 0.005, rtol=0, atol=1e-6)          # t accumulates n_steps * dt
+    assert np.all(out[_abi.OUT["rail_exit_speed"]] > 0)
+    out2, iout2 = engine.run_batch(sc, wind, opts=_lib.run_opts(refill_threshold=16))
+    assert np.array_equal(iout, iout2) and np.array_equal(out, out2, equal_nan=True)
+    h = n // 2                                                          # two shards == one batch
+    oa, ia = engine.run_batch(sc[:, :h].copy(), wind[:h])
+    ob, ib = engine.run_batch(sc[:, h:].copy(), wind[h:])
+    assert np.array_equal(np.concatenate([ia, ib], 1), iout)
+    assert np.array_equal(np.concatenate([oa, ob], 1), out, equal_nan=True)
+    # spot-check 256 of the 100k against the oracle
+    pick = np.random.RandomState(1).choice(n, 256, replace=False)
+    ref, iref = O.batch(md, sc[:, pick].copy(), wind[pick].copy())
+    same = np.all(iout[:, pick] == iref, axis=0)
+    assert same.mean() >= 0.99
+    util.assert_summary_close(out[:, pick][:, same], ref[:, same], what="100k spot check")
+
+
+def test_gpu_edge_cases(engine):
+    z = util.golden("mc_solid_csv")
+    md = _abi.model_from_npz(z)
+    engine.set_model(md)
+    out, iout = engine.run_batch(z["scalars"][:, :0].copy(), z["wind"][:0])          # empty batch
+    assert out.shape == (_abi.OUT_COUNT, 0)
+    out1, iout1 = engine.run_batch(z["scalars"][:, 5:6].copy(), z["wind"][5:6])      # ragged: one sample
+    np.testing.assert_array_equal(iout1[:, 0], z["iout"][:, 5])
+    out33, iout33 = engine.run_batch(z["scalars"][:, :33].copy(), z["wind"][:33])    # one lane past a warp
+    np.testing.assert_array_equal(iout33, z["iout"][:, :33])
+    # shared wind table (stride 0) == replicated table
+    w0 = z["wind"][3]
+    a = engine.run_batch(z["scalars"][:, :8].copy(), w0, wind_shared=True)
+    b = engine.run_batch(z["scalars"][:, :8].copy(), np.repeat(w0[None], 8, 0))
+    np.testing.assert_array_equal(a[0], b[0])
+    # max_time shorter than the rail time: zero RK4 steps, termination = max_time
+    md2 = dict(md); md2["max_time"] = 0.5
+    engine.set_model(md2)
+    o, i = engine.run_batch(z["scalars"][:, :4].copy(), z["wind"][:4])
+    ro, ri = O.batch(md2, z["scalars"][:, :4].copy(), z["wind"][:4])
+    np.testing.assert_array_equal(i, ri)
+    assert np.all(i[_abi.IOUT["n_steps"]] == 0) and np.all(i[_abi.IOUT["termination"]] == 4)
+    util.assert_summary_close(o, ro, what="zero-step flights")
+
+
+def test_gpu_errors(engine):
+    e2 = _lib.Engine(0)
+    z = util.golden("mc_readme_literal")
+    with pytest.raises(_lib.EmcError, match="EMC_ERR_NO_MODEL"):
+        e2.has_wind = True; e2.n_wind = 100
+        e2.run_batch(z["scalars"], z["wind"])
+    md = _abi.model_from_npz(z)
+    bad = dict(md); bad["cd_mach"] = np.array(md["cd_mach"])[::-1].copy()
+    with pytest.raises(_lib.EmcError, match="strictly increasing"):
+        e2.set_model(bad)
+    e2.close()
+    with pytest.raises(_lib.EmcError, match="out of range"):
+        _lib.Engine(99)

@@ -1,0 +1,53 @@
+"""CPU: the engine's own device physics (csrc/emc_physics.cuh) compiled by g++ through the test seam
+(tests/hostseam) against the reference goldens and the oracle.  This is the same code the CUDA kernels
+inline; it lets a container without a GPU catch parity regressions before GPU time is spent.  The
+seam is not part of the product (libemc.so has no CPU path)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import util
+from erpl_monte_carlo_sim_b200 import _abi
+
+
+@pytest.mark.parametrize("name", util.DERIV_SETS)
+def test_seam_derivative(name):
+    z = util.golden(name)
+    md = _abi.model_from_npz(z)
+    sd, ch = util.hostseam_derivative(md, z["scalars"], z["wind"] if z["wind"].size else None, z["t"], z["state"], z["chute_in"])
+    ref = z["state_dot"]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.nanmax(np.abs(sd - ref) / np.maximum(scale, 1e-300)) < 1e-13
+    assert np.array_equal(np.isnan(sd), np.isnan(ref))
+    assert np.array_equal(ch, z["chute_out"])
+
+
+def test_seam_single_flights():
+    z = util.golden("flights_single")
+    for name in z["names"]:
+        md, sc, wind, ref, iref = util.single_case(z, str(name))
+        out, iout = util.hostseam_batch(md, sc, wind)
+        np.testing.assert_array_equal(iout, iref, err_msg=str(name))
+        util.assert_summary_close(out, ref, what=str(name))
+
+
+@pytest.mark.parametrize("name", util.MC_SETS)
+def test_seam_mc_sets(name):
+    z = util.golden(name)
+    md = _abi.model_from_npz(z)
+    out, iout = util.hostseam_batch(md, z["scalars"], z["wind"])
+    np.testing.assert_array_equal(iout, z["iout"])
+    util.assert_summary_close(out, z["out"], what=name)
+
+
+def test_seam_nan_fast_forward_is_exact():
+    """Integrating the all-NaN tail (reference behaviour) and replaying only `t` give identical outputs."""
+    z = util.golden("mc_liquid_default")
+    md = _abi.model_from_npz(z)
+    nan_runs = np.flatnonzero(z["iout"][_abi.IOUT["first_nan_step"]] >= 0)[:3]
+    assert nan_runs.size > 0
+    sc, w = z["scalars"][:, nan_runs], z["wind"][nan_runs]
+    a = util.hostseam_batch(md, sc, w, nan_ff=True)
+    b = util.hostseam_batch(md, sc, w, nan_ff=False)
+    np.testing.assert_array_equal(a[1], b[1])
+    np.testing.assert_array_equal(a[0], b[0])

@@ -1,0 +1,115 @@
+"""Shared helpers of the test-suite: golden loading and the parity comparison."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from erpl_monte_carlo_sim_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+OUT = _abi.OUT
+RTOL = 1e-6          # BASELINE.json north_star: 1e-6 relative in FP64
+
+# vector-valued outputs are compared against the vector's norm; angles/times get a small floor
+VECTORS = [("rail_exit_x", "rail_exit_y", "rail_exit_z"), ("rail_exit_vx", "rail_exit_vy", "rail_exit_vz"),
+           ("wind_at_exit_u", "wind_at_exit_v", "wind_at_exit_w"), ("final_x", "final_y", "final_z"),
+           ("final_vx", "final_vy", "final_vz")]
+ANGLES = ["rail_exit_roll", "rail_exit_pitch", "rail_exit_yaw", "rail_exit_aoa", "rail_exit_sideslip", "max_abs_aoa"]
+ANGLE_ATOL = 1e-9    # rad
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def summary_errors(out, ref):
+    """Scaled error per (field, sample): |a-b| / scale, where scale is |ref| (scalars) or the norm of
+    the reference vector (vector groups).  NaN-vs-NaN and exact equality (incl. inf) count as 0."""
+    out = np.asarray(out, float); ref = np.asarray(ref, float)
+    with np.errstate(all="ignore"):
+        scale = np.abs(ref).copy()
+        for grp in VECTORS:
+            idx = [OUT[g] for g in grp]
+            nrm = np.sqrt(np.sum(ref[idx] ** 2, axis=0))
+            scale[idx] = nrm
+        err = np.abs(out - ref) / np.maximum(scale, 1e-300)
+        for a in ANGLES:
+            i = OUT[a]
+            err[i] = np.abs(out[i] - ref[i]) / np.maximum(scale[i], ANGLE_ATOL / RTOL)
+        # time-like fields that are exactly 0 in the reference (apogee_time, burnout_time)
+        for tname in ("apogee_time", "burnout_time", "rail_exit_time"):
+            i = OUT[tname]
+            err[i] = np.abs(out[i] - ref[i]) / np.maximum(scale[i], 1e-3)
+    same = (out == ref) | (np.isnan(out) & np.isnan(ref))
+    err[same] = 0.0
+    err[np.isnan(out) != np.isnan(ref)] = np.inf
+    err[np.isnan(err)] = np.inf
+    return err
+
+
+def assert_summary_close(out, ref, rtol=RTOL, what=""):
+    err = summary_errors(out, ref)
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err[worst] <= rtol, (f"{what}: field {_abi.OUT_FIELDS[worst[0]]} sample {worst[1]}: "
+                                f"{out[worst]!r} vs {ref[worst]!r} (scaled err {err[worst]:.3e} > {rtol})")
+    return float(err.max())
+
+
+def hostseam_lib():
+    """g++ build of the engine's device physics (tests/hostseam): CPU-side test seam only."""
+    d = os.path.join(HERE, "hostseam")
+    so = os.path.join(d, "_build", "libemc_hostseam.so")
+    srcs = [os.path.join(d, "hostseam.cpp"),
+            os.path.join(os.path.dirname(HERE), "erpl_monte_carlo_sim_b200", "csrc", "emc_physics.cuh"),
+            os.path.join(os.path.dirname(HERE), "erpl_monte_carlo_sim_b200", "csrc", "emc_model_build.h"),
+            os.path.join(os.path.dirname(HERE), "include", "emc.h")]
+    if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-std=c++17",
+                               "-o", so, srcs[0], "-lm"])
+    return C.CDLL(so)
+
+
+_dp = C.POINTER(C.c_double)
+
+
+def hostseam_derivative(md, scalars, wind, t, state, chute):
+    HS = hostseam_lib()
+    m, keep = _abi.pack_model(md)
+    scalars = np.ascontiguousarray(scalars, np.float64)
+    n = scalars.shape[1]
+    wind = np.ascontiguousarray(wind, np.float64) if wind is not None and np.size(wind) else None
+    ins = _abi.inputs_struct(scalars, wind)
+    ch = np.ascontiguousarray(chute, np.int32).copy()
+    sd = np.empty((n, 14))
+    t = np.ascontiguousarray(t, np.float64); state = np.ascontiguousarray(state, np.float64)
+    rc = HS.hs_derivative(C.byref(m), C.byref(ins), C.c_int64(n), t.ctypes.data_as(_dp), state.ctypes.data_as(_dp),
+                          ch.ctypes.data_as(C.POINTER(C.c_int32)), sd.ctypes.data_as(_dp))
+    assert rc == 0
+    return sd, ch
+
+
+def hostseam_batch(md, scalars, wind, nan_ff=True):
+    HS = hostseam_lib()
+    m, keep = _abi.pack_model(md)
+    scalars = np.ascontiguousarray(scalars, np.float64)
+    n = scalars.shape[1]
+    wind = np.ascontiguousarray(wind, np.float64) if wind is not None and np.size(wind) else None
+    ins = _abi.inputs_struct(scalars, wind, wind_shared=(wind is not None and wind.ndim == 2))
+    outs, out, iout = _abi.outputs_alloc(n)
+    rc = HS.hs_batch(C.byref(m), C.byref(ins), C.c_int64(n), C.byref(outs), C.c_int(1 if nan_ff else 0), None,
+                     C.c_int64(0), None)
+    assert rc == 0
+    return out, iout
+
+
+def single_case(z, name):
+    md = _abi.model_from_npz(z, name + "__")
+    wind = z[name + "__wind"][0] if (name + "__wind") in z.files else None
+    return md, z[name + "__scalars"], wind, z[name + "__out"], z[name + "__iout"]
+
+
+MC_SETS = ["mc_planar_liquid", "mc_planar_solid", "mc_liquid_default", "mc_solid_csv", "mc_readme_literal"]
+DERIV_SETS = ["derivative_liquid_wind100", "derivative_solid_csv", "derivative_liquid_nowind"]
