@@ -137,8 +137,9 @@ class Engine:
         self.n_wind = int(m.n_wind)
 
     # -- host-buffer path (the drop-in boundary) ------------------------------------------------
-    def run_batch(self, scalars, wind=None, opts=None, wind_shared=False):
-        """scalars [IN_COUNT][n] float64, wind [n][N][3] (or [N][3] with wind_shared) -> (out, iout)."""
+    def run_batch(self, scalars, wind=None, opts=None, wind_shared=False, outputs=None):
+        """scalars [IN_COUNT][n] float64, wind [n][N][3] (or [N][3] with wind_shared) -> (out, iout).
+        `outputs=(out, iout)` lets the caller supply (e.g. pinned) result arrays."""
         scalars = np.ascontiguousarray(scalars, np.float64)
         n = scalars.shape[1]
         w = None
@@ -151,7 +152,14 @@ class Engine:
             if w.shape[-2] != self.n_wind or w.shape[-1] != 3 or (not wind_shared and w.shape[0] != n):
                 raise ValueError(f"wind table shape {w.shape} does not match n={n}, n_wind={self.n_wind}")
         ins = _abi.inputs_struct(scalars, w, wind_shared=wind_shared)
-        outs, out, iout = _abi.outputs_alloc(n)
+        if outputs is None:
+            outs, out, iout = _abi.outputs_alloc(n)
+        else:
+            out, iout = outputs
+            assert out.dtype == np.float64 and iout.dtype == np.int32 and out.flags.c_contiguous and iout.flags.c_contiguous
+            assert out.shape == (_abi.OUT_COUNT, n) and iout.shape == (_abi.IOUT_COUNT, n)
+            outs = _abi.EmcOutputs()
+            outs.out, outs.iout, outs.ld = out.ctypes.data, iout.ctypes.data, n
         self._check(self._lib.emc_run_batch(self._ctx, C.byref(ins), n, C.byref(outs),
                                             C.byref(opts) if opts is not None else None), "emc_run_batch")
         return out, iout

@@ -408,7 +408,7 @@ struct Track {
     int32_t n_steps, apogee_index, first_nan, term;
     bool chute, apogee_detected, burnout_found;
     bool finishing;   /* loop ended: one more stage-0 pass exports the last stored state's diagnostics */
-    bool replay;      /* ended by the all-NaN fast-forward: t is replayed to max_time before retiring */
+    int32_t replay;   /* NaN fast-forward mode (0 none, 1 all-NaN, 2 altitude-NaN ballistic): t is replayed to max_time */
 };
 
 EMC_HD void track_init(Track &K, const State &s, double t_rail)
@@ -419,7 +419,7 @@ EMC_HD void track_init(Track &K, const State &s, double t_rail)
     K.apogee_time_latch = 0.0; K.max_coast = 0.0;
     K.burnout_time = 0.0; K.burnout_found = false;
     K.chute_time = NAN; K.chute = false; K.apogee_detected = false;
-    K.n_steps = 0; K.term = EMC_TERM_NONE; K.finishing = false; K.replay = false;
+    K.n_steps = 0; K.term = EMC_TERM_NONE; K.finishing = false; K.replay = 0;
     K.max_mach2 = -INFINITY; K.max_q = -INFINITY; K.max_v2 = -INFINITY; K.max_om = -INFINITY;
     K.min_stab = INFINITY; K.max_stab = -INFINITY; K.max_aoa = -INFINITY;
 }
@@ -519,23 +519,49 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
     return true;
 }
 
-/* True once nothing but `t` can change any more: position and velocity are all NaN, so no break
- * test of simulator.py:238-264 can fire and every later stored state is NaN. */
-EMC_HD bool all_nan(const State &s)
+/* NaN fast-forward.  Every break test of simulator.py:238-264 reads the altitude, so
+ * once z (and vz) are NaN the loop can only end at the guard `t < max_time` (:216); the reference
+ * grinds through ~57 k more steps.  Two cases let the engine replay that tail without the derivative:
+ *   mode 1  x, y, vx, vy are NaN as well: nothing but t changes any more.
+ *   mode 2  the motor is off for good and the attitude is finite: the body force is exactly zero (no
+ *           thrust; q_inf = NaN fails `q_dynamic > 0`, :378; a deployed parachute sees |v_body| = NaN
+ *           and fails `rel_speed > 0`, :374; a NaN altitude cannot latch the chute, :366-369), so
+ *           vx, vy keep their values (finite, +-inf or NaN) and x, y advance by the RK4 update of :224
+ *           with k = (vx, vy) in all four stages; the damped body rates stay finite.  Only x, y and t
+ *           are replayed, with the same IEEE arithmetic the full step would apply to them.
+ * Anything else (still burning, non-finite attitude) turns fully NaN within a few steps and is
+ * integrated until it reaches mode 1.  Apogee (first NaN, :488), the NaN maxima and the step count
+ * are what the reference produces; max|omega| keeps its value at the fast-forward point (NaN runs:
+ * category parity). */
+EMC_HD bool finite_d(double v) { return fabs(v) <= 1.7976931348623157e308; }
+
+EMC_HD int nan_mode(const DevModel &M, const Sample &S, const Track &K, const State &s)
 {
-    return (s.x != s.x) && (s.y != s.y) && (s.z != s.z) && (s.vx != s.vx) && (s.vy != s.vy) && (s.vz != s.vz);
+    if (!((s.z != s.z) && (s.vz != s.vz))) return 0;
+    if (!(K.t + 2.0 * M.dt < M.max_time)) return 0;          /* too close to the guard: just integrate */
+    if ((s.x != s.x) && (s.y != s.y) && (s.vx != s.vx) && (s.vy != s.vy)) return 1;
+    const double pf = (s.pf > 0.0) ? s.pf : 0.0;
+    const bool burning = (pf > 0.0) && (K.t <= S.burn_time);
+    if (burning) return 0;
+    const bool att_ok = finite_d(s.q0) && finite_d(s.q1) && finite_d(s.q2) && finite_d(s.q3) &&
+                        finite_d(s.wx) && finite_d(s.wy) && finite_d(s.wz) && finite_d(s.pf) &&
+                        (s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3 > 1e-24);
+    return att_ok ? 2 : 0;
 }
 
-/* NaN fast-forward: replay only the time accumulation of :229 (and the burnout-index test of
- * :479-480, which reads nothing but the time) until the guard of :216 ends the loop */
-EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K)
+EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K, State &s)
 {
     int64_t n = 0;
-    while (!K.burnout_found && K.t < M.max_time) {
+    /* RK4 combination of :224 for a constant derivative k: ((k + 2k) + 2k) + k, then x += (dt/6)*acc */
+    const double ax = ((s.vx + 2.0 * s.vx) + 2.0 * s.vx) + s.vx;
+    const double ay = ((s.vy + 2.0 * s.vy) + 2.0 * s.vy) + s.vy;
+    const bool ballistic = (K.replay == 2);
+    while (K.t < M.max_time) {
         K.t += M.dt; K.n_steps += 1; ++n;
-        if ((K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
+        if (ballistic) { s.x += M.dt_over_6 * ax; s.y += M.dt_over_6 * ay; }
+        /* burnout index of :479-480 reads nothing but the time */
+        if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
     }
-    while (K.t < M.max_time) { K.t += M.dt; K.n_steps += 1; ++n; }
     K.term = EMC_TERM_MAX_TIME;
     return n;
 }
@@ -548,11 +574,11 @@ EMC_HD bool lane_advance(const DevModel &M, const DevTables &Tb, const double *w
 {
     stepped = rk4_step(M, Tb, wind_alt, S, WB, K, s);
     if (!stepped) {                       /* closing pass done */
-        if (K.replay) replayed += replay_time(M, S, K);
+        if (K.replay) replayed += replay_time(M, S, K, s);
         return true;
     }
     bool done = track_post_step(M, S, K, s);
-    if (!done && nan_ff && all_nan(s)) { K.replay = true; done = true; }
+    if (!done && nan_ff) { K.replay = nan_mode(M, S, K, s); done = (K.replay != 0); }
     K.finishing = done;
     return false;
 }

@@ -1,0 +1,434 @@
+"""MonteCarloAnalyzer — drop-in for the reference's class (monte_carlo.py:17-473).
+
+Same constructor, attributes, `run_monte_carlo` signature and analysis-dict keys.  What changes is
+the execution: instead of one `FlightSimulator` per sample in a process pool (monte_carlo.py:67-83)
+all dispersed samples go to the CUDA engine as one batch through the C ABI.
+
+Host-seeded mode (this module): the dispersion draws are the reference's own NumPy draws, stream for
+stream (monte_carlo.py:156-201,225-335; motor.py:95-125,171-186; environment.py:125-200,218-265), so
+the engine sees bit-identical inputs.  tests/test_host_sampling.py pins that against golden inputs
+captured from the reference.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import time
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _abi, marshal
+from .motor import LiquidMotor, SolidMotor, is_solid
+from .simulator import FlightSimulator, get_engine, summary_extras
+
+PARAM_KEYS = ("initial_position_offset", "initial_velocity_offset", "initial_attitude_offset",
+              "initial_angular_velocity_offset", "mass_multiplier", "thrust_multiplier", "wind_speed",
+              "wind_direction", "density_multiplier", "random_seed")
+
+# physical bounds of the reference's outlier filter (monte_carlo.py:343-346,383-386)
+MAX_REASONABLE_APOGEE = 80000.0
+MAX_REASONABLE_RANGE = 200000.0
+MAX_REASONABLE_FLIGHT_TIME = 600.0
+MIN_REASONABLE_APOGEE = 100.0
+THEORETICAL_MAX_ALTITUDE = 1200.0 ** 2 / (2 * 9.81)
+
+
+class DispersionSet:
+    """Struct-of-arrays view of n parameter samples (the reference keeps a list of dicts)."""
+
+    def __init__(self, n):
+        self.n = n
+        self.pos = np.zeros((n, 3)); self.vel = np.zeros((n, 3)); self.att = np.zeros((n, 3)); self.omega = np.zeros((n, 3))
+        self.mass_multiplier = np.ones(n); self.thrust_multiplier = np.ones(n)
+        self.wind_speed = np.zeros(n); self.wind_direction = np.zeros(n); self.density_multiplier = np.ones(n)
+        self.seed = np.zeros(n, np.int64)
+
+    def as_dict(self, i):
+        return {"initial_position_offset": self.pos[i].copy(), "initial_velocity_offset": self.vel[i].copy(),
+                "initial_attitude_offset": self.att[i].copy(), "initial_angular_velocity_offset": self.omega[i].copy(),
+                "mass_multiplier": float(self.mass_multiplier[i]), "thrust_multiplier": float(self.thrust_multiplier[i]),
+                "wind_speed": float(self.wind_speed[i]), "wind_direction": float(self.wind_direction[i]),
+                "density_multiplier": float(self.density_multiplier[i]), "random_seed": int(self.seed[i])}
+
+    @classmethod
+    def from_dicts(cls, dicts):
+        d = cls(len(dicts))
+        for i, p in enumerate(dicts):
+            d.pos[i] = p["initial_position_offset"]; d.vel[i] = p["initial_velocity_offset"]
+            d.att[i] = p["initial_attitude_offset"]; d.omega[i] = p["initial_angular_velocity_offset"]
+            d.mass_multiplier[i] = p["mass_multiplier"]; d.thrust_multiplier[i] = p["thrust_multiplier"]
+            d.wind_speed[i] = p["wind_speed"]; d.wind_direction[i] = p["wind_direction"]
+            d.density_multiplier[i] = p["density_multiplier"]; d.seed[i] = p["random_seed"]
+        return d
+
+    def slice(self, lo, hi):
+        d = DispersionSet(hi - lo)
+        for k in ("pos", "vel", "att", "omega", "mass_multiplier", "thrust_multiplier", "wind_speed",
+                  "wind_direction", "density_multiplier", "seed"):
+            setattr(d, k, getattr(self, k)[lo:hi])
+        return d
+
+
+class SampleResults(Sequence):
+    """`analysis['results']` / `analysis['outliers']`: one dict per sample, built on access from the
+    engine's SoA summary (the reference materialises every time series of every sample in a list)."""
+
+    def __init__(self, owner, ids, reasons=None):
+        self._owner, self._ids, self._reasons = owner, np.asarray(ids, np.int64), reasons
+
+    def __len__(self):
+        return len(self._ids)
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        i = int(self._ids[k])
+        d = self._owner.sample_result(i)
+        if self._reasons is not None:
+            d["outlier_reasons"] = self._reasons[k]
+        return d
+
+
+class BatchRun:
+    """Everything one Monte Carlo batch produced: dispersions, inputs summary and the SoA outputs."""
+
+    def __init__(self, analyzer, base_ic, disp, out, iout, altitude_profile, scalars):
+        self.analyzer, self.base_ic, self.disp = analyzer, base_ic, disp
+        self.out, self.iout, self.altitude_profile, self.scalars = out, iout, altitude_profile, scalars
+
+    def sample_result(self, i):
+        O = _abi.OUT
+        o = self.out[:, i]
+        d = {
+            "simulation_id": i, "parameters": self.disp.as_dict(i),
+            "apogee_altitude": o[O["apogee_altitude"]], "apogee_time": o[O["apogee_time"]],
+            "range": o[O["range"]], "flight_time": o[O["flight_time"]],
+            "rail_exit_time": o[O["rail_exit_time"]],
+            "rail_exit_position": o[O["rail_exit_x"]:O["rail_exit_z"] + 1].copy(),
+            "rail_exit_velocity": o[O["rail_exit_vx"]:O["rail_exit_vz"] + 1].copy(),
+            "rail_exit_speed": float(o[O["rail_exit_speed"]]),
+            "rail_exit_euler": o[O["rail_exit_roll"]:O["rail_exit_yaw"] + 1].copy(),
+            "rail_exit_angle_of_attack": o[O["rail_exit_aoa"]], "rail_exit_sideslip": o[O["rail_exit_sideslip"]],
+            "wind_at_exit": o[O["wind_at_exit_u"]:O["wind_at_exit_w"] + 1].copy(),
+        }
+        d.update(summary_extras(self.out, self.iout, i))
+        return d
+
+    def full_result(self, i):
+        """Re-fly sample i with the tape on: the complete `simulate_flight` dict incl. time series."""
+        return self.analyzer.resimulate(self.base_ic, self.disp.as_dict(i))
+
+
+class MonteCarloAnalyzer:
+    def __init__(self, rocket, motor, atmosphere, wind_model, device: int = 0):
+        self.rocket = rocket
+        self.motor = motor
+        self.atmosphere = atmosphere
+        self.wind_model = wind_model
+        self.n_cores = os.cpu_count()
+        self.base_altitude_profile = None
+        self.base_wind_profile = None
+        self.uncertainty_params = {
+            "initial_position": [0.0, 0.0, 0.0],
+            "initial_velocity": [0.1, 0.1, 0.1],
+            "initial_attitude": [0.005, 0.005, 0.005],
+            "initial_angular_velocity": [0.005, 0.005, 0.005],
+            "mass_uncertainty": 0.02,
+            "thrust_uncertainty": 0.03,
+            "wind_speed_range": [0.0, 5.0],
+            "wind_direction_range": [0.0, 2 * np.pi],
+            "atmospheric_density_uncertainty": 0.05,
+        }
+        self.device = device
+        self.chunk_size = 1 << 16
+        self.run_opts = None
+        self.last_run = None
+
+    # ------------------------------------------------------------------------------------------
+    # dispersion draws (host-seeded: the reference's own NumPy streams)
+    # ------------------------------------------------------------------------------------------
+    def _generate_parameter_samples(self, n_samples):
+        """List of dicts, identical to the reference's (monte_carlo.py:156-179)."""
+        d = self.draw_parameters(n_samples)
+        return [d.as_dict(i) for i in range(n_samples)]
+
+    def _generate_parameter_samples_vectorized(self, n_samples):
+        d = self.draw_parameters(n_samples, optimized=True)
+        return [d.as_dict(i) for i in range(n_samples)]
+
+    def draw_parameters(self, n_samples, optimized=False, first_seed=0) -> DispersionSet:
+        up = self.uncertainty_params
+        d = DispersionSet(n_samples)
+        s_pos, s_vel = np.asarray(up["initial_position"], float), np.asarray(up["initial_velocity"], float)
+        s_att, s_om = np.asarray(up["initial_attitude"], float), np.asarray(up["initial_angular_velocity"], float)
+        ws_lo, ws_hi = up["wind_speed_range"]
+        wd_lo, wd_hi = up["wind_direction_range"]
+        if optimized:
+            # one stream, seed 42, drawn sample after sample (monte_carlo.py:181-201)
+            rs = np.random.RandomState(42)
+            for i in range(n_samples):
+                d.pos[i] = rs.normal(0, s_pos); d.vel[i] = rs.normal(0, s_vel)
+                d.att[i] = rs.normal(0, s_att); d.omega[i] = rs.normal(0, s_om)
+                d.mass_multiplier[i] = rs.normal(1.0, up["mass_uncertainty"])
+                d.thrust_multiplier[i] = rs.normal(1.0, up["thrust_uncertainty"])
+                d.wind_speed[i] = rs.uniform(ws_lo, ws_hi); d.wind_direction[i] = rs.uniform(wd_lo, wd_hi)
+                d.density_multiplier[i] = rs.normal(1.0, up["atmospheric_density_uncertainty"])
+                d.seed[i] = i
+            return d
+        # per-sample stream seeded with the sample index (monte_carlo.py:160-175): 14 normals,
+        # 2 uniforms, 1 normal, in that order
+        rs = np.random.RandomState(0)
+        g = np.empty((n_samples, 15)); u = np.empty((n_samples, 2))
+        for i in range(n_samples):
+            rs.seed(first_seed + i)
+            g[i, :14] = rs.standard_normal(14)
+            u[i] = rs.random_sample(2)
+            g[i, 14] = rs.standard_normal()
+        d.pos[:] = 0 + s_pos * g[:, 0:3]; d.vel[:] = 0 + s_vel * g[:, 3:6]
+        d.att[:] = 0 + s_att * g[:, 6:9]; d.omega[:] = 0 + s_om * g[:, 9:12]
+        d.mass_multiplier[:] = 1.0 + up["mass_uncertainty"] * g[:, 12]
+        d.thrust_multiplier[:] = 1.0 + up["thrust_uncertainty"] * g[:, 13]
+        d.wind_speed[:] = ws_lo + (ws_hi - ws_lo) * u[:, 0]
+        d.wind_direction[:] = wd_lo + (wd_hi - wd_lo) * u[:, 1]
+        d.density_multiplier[:] = 1.0 + up["atmospheric_density_uncertainty"] * g[:, 14]
+        d.seed[:] = first_seed + np.arange(n_samples)
+        return d
+
+    # ------------------------------------------------------------------------------------------
+    # per-sample perturbation -> engine inputs (monte_carlo.py:225-288)
+    # ------------------------------------------------------------------------------------------
+    def _altitude_grid(self):
+        if self.base_wind_profile is not None and self.base_altitude_profile is not None:
+            return np.ascontiguousarray(self.base_altitude_profile, np.float64)
+        return np.linspace(0, 25000, 100)
+
+    def build_inputs(self, initial_conditions, disp: DispersionSet):
+        """(scalars[IN_COUNT][n], wind[n][N][3], altitude grid) for a set of dispersions."""
+        n = disp.n
+        ic = initial_conditions
+        blk = marshal.initial_state_block(
+            n, np.asarray(ic.get("position", [0.0, 0.0, 0.0]), float) + disp.pos if "position" in ic else disp.pos,
+            np.asarray(ic.get("velocity", [0.0, 0.0, 0.0]), float) + disp.vel if "velocity" in ic else disp.vel,
+            np.asarray(ic.get("attitude", [0.0, 0.0, 0.0]), float) + disp.att if "attitude" in ic else disp.att,
+            np.asarray(ic.get("angular_velocity", [0.0, 0.0, 0.0]), float) + disp.omega if "angular_velocity" in ic else disp.omega)
+        IN = _abi.IN
+        dry = self.rocket.dry_mass * disp.mass_multiplier                 # monte_carlo.py:315-316
+        prop = self.rocket.propellant_mass * disp.mass_multiplier
+        alts = self._altitude_grid()
+        n_knots = len(alts)
+        # the motor and the wind generator each restart the sample's stream (RandomState(seed)), F11
+        rs = np.random.RandomState(0)
+        need = max(3 * n_knots, 3)
+        gw = np.empty((n, need))
+        for i in range(n):
+            rs.seed(int(disp.seed[i]))
+            gw[i] = rs.standard_normal(need)
+        m = self.motor
+        if type(m) is LiquidMotor:                                        # motor.py:171-186
+            k_t = 1.0 + m.thrust_uncertainty * gw[:, 0]
+            k_f = 1.0 + m.mass_flow_uncertainty * gw[:, 1]
+            t_vac, t_sl = m.thrust_vacuum * k_t, m.thrust_sea_level * k_t
+            mdot = m.mass_flow_rate * k_f
+            blk[IN["thrust_a"]] = t_vac
+            blk[IN["nozzle_area"]] = (t_vac - t_sl) / 101325.0
+            own_burn = m.propellant_mass / mdot
+        elif type(m) is SolidMotor:                                       # motor.py:95-125
+            k = 1.0 + m.thrust_uncertainty * gw[:, 0]
+            mdot = 4.26 * k
+            blk[IN["thrust_a"]] = k
+            blk[IN["nozzle_area"]] = m.nozzle_exit_area * k
+            own_burn = m.burn_time * (1.0 + m.burn_time_uncertainty * gw[:, 1])
+        else:                                                             # any duck-typed motor: ask it
+            mdot = np.empty(n); own_burn = np.empty(n)
+            for i in range(n):
+                pm = m.perturb_for_monte_carlo(np.random.RandomState(int(disp.seed[i])))
+                mdot[i] = pm.mass_flow_rate; own_burn[i] = pm.burn_time
+                blk[IN["nozzle_area"], i] = pm.nozzle_exit_area
+                if is_solid(pm):
+                    ref = np.asarray(m.thrust_curve_thrust, float)
+                    j = int(np.argmax(np.abs(ref)))
+                    blk[IN["thrust_a"], i] = np.asarray(pm.thrust_curve_thrust, float)[j] / ref[j]
+                else:
+                    blk[IN["thrust_a"], i] = pm.thrust_vacuum
+        blk[IN["dry_mass"]] = dry
+        blk[IN["prop_mass"]] = prop
+        blk[IN["mdot"]] = mdot
+        with np.errstate(divide="ignore", invalid="ignore"):
+            blk[IN["burn_time"]] = np.where(mdot > 0, prop / mdot, own_burn)  # monte_carlo.py:258-260
+        blk[IN["cd_scale"]] = 1.0
+        g3 = gw[:, :3 * n_knots].reshape(n, n_knots, 3)
+        if self.base_wind_profile is not None and self.base_altitude_profile is not None:
+            wind = self.wind_model.perturbed_profiles_batch(alts, self.base_wind_profile, g3)   # :271-275
+            wind[:, :, 0] += (disp.wind_speed * np.cos(disp.wind_direction))[:, None]            # :277-280
+            wind[:, :, 1] += (disp.wind_speed * np.sin(disp.wind_direction))[:, None]
+        else:
+            wind = self.wind_model.stochastic_profiles_batch(alts, disp.wind_speed, disp.wind_direction, g3)  # :282-288
+        return blk, np.ascontiguousarray(wind), alts
+
+    def _model_simulator(self):
+        return FlightSimulator(self.rocket, self.motor, self.atmosphere, self.wind_model, device=self.device)
+
+    # ------------------------------------------------------------------------------------------
+    # running
+    # ------------------------------------------------------------------------------------------
+    def run_batch(self, initial_conditions, disp: DispersionSet) -> BatchRun:
+        eng = get_engine(self.device)
+        alts = self._altitude_grid()
+        md = marshal.model_dict(self.rocket, self.motor, self.atmosphere, self._model_simulator(), alts)
+        eng.set_model(md)
+        n = disp.n
+        out = np.empty((_abi.OUT_COUNT, n)); iout = np.empty((_abi.IOUT_COUNT, n), np.int32)
+        scal = np.empty((_abi.IN_COUNT, n))
+        for lo in range(0, n, self.chunk_size):
+            hi = min(n, lo + self.chunk_size)
+            blk, wind, _ = self.build_inputs(initial_conditions, disp.slice(lo, hi))
+            o, io = eng.run_batch(blk, wind, opts=self.run_opts)
+            out[:, lo:hi] = o; iout[:, lo:hi] = io; scal[:, lo:hi] = blk
+        self.last_run = BatchRun(self, dict(initial_conditions), disp, out, iout, alts, scal)
+        return self.last_run
+
+    def run_monte_carlo(self, initial_conditions, n_samples=1000, n_processes=None, optimized=False):
+        """n_processes is accepted for signature compatibility; the batch runs on the GPU."""
+        if optimized:
+            return self.run_optimized_monte_carlo(initial_conditions, n_samples)
+        disp = self.draw_parameters(n_samples)
+        run = self.run_batch(initial_conditions, disp)
+        return self._analyze_run(run)
+
+    def run_optimized_monte_carlo(self, initial_conditions, n_samples=1000, chunk_size=None):
+        t0 = time.time()
+        disp = self.draw_parameters(n_samples, optimized=True)
+        run = self.run_batch(initial_conditions, disp)
+        analysis = self._analyze_run(run)
+        elapsed = time.time() - t0
+        analysis["performance"] = {"total_time": elapsed, "simulations_per_second": n_samples / elapsed,
+                                   "cores_used": self.n_cores}
+        return analysis
+
+    def resimulate(self, initial_conditions, params):
+        """The full `simulate_flight` result (time series included) of one dispersed sample."""
+        disp = DispersionSet.from_dicts([params])
+        blk, wind, alts = self.build_inputs(initial_conditions, disp)
+        sim = self._model_simulator()
+        rocket, motor = copy.copy(self.rocket), copy.copy(self.motor)     # monte_carlo.py:308-335 deep-copies and mutates
+        IN = _abi.IN
+        rocket.dry_mass, rocket.propellant_mass = blk[IN["dry_mass"], 0], blk[IN["prop_mass"], 0]
+        motor.nozzle_exit_area, motor.mass_flow_rate = blk[IN["nozzle_area"], 0], blk[IN["mdot"], 0]
+        motor.burn_time, motor.propellant_mass = blk[IN["burn_time"], 0], blk[IN["prop_mass"], 0]
+        if is_solid(self.motor):
+            motor.thrust_curve_thrust = np.asarray(self.motor.thrust_curve_thrust, float) * blk[IN["thrust_a"], 0]
+        else:
+            motor.thrust_vacuum = blk[IN["thrust_a"], 0]
+        sim.rocket, sim.motor = rocket, motor
+        ic = {"position": blk[0:3, 0].tolist(), "velocity": blk[3:6, 0].tolist(),
+              "attitude": (np.asarray(initial_conditions.get("attitude", [0.0, 0.0, 0.0]), float) + disp.att[0]).tolist(),
+              "angular_velocity": blk[10:13, 0].tolist()}
+        res = sim.simulate_flight(ic, wind[0], alts)
+        res["simulation_id"] = int(params.get("random_seed", 0)); res["parameters"] = params
+        res["trajectory"] = {"time": res["time"], "altitude": res["altitude"], "position": res["position"].T}
+        return res
+
+    # ------------------------------------------------------------------------------------------
+    # statistics (monte_carlo.py:337-473)
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def outlier_mask(apogee, range_val, flight_time):
+        """Vectorised `_filter_physics_outliers` (monte_carlo.py:348-390): True where filtered."""
+        with np.errstate(invalid="ignore"):
+            bad = ~np.isfinite(apogee) | ~np.isfinite(range_val) | ~np.isfinite(flight_time)
+            bad |= (apogee > MAX_REASONABLE_APOGEE) | (apogee < MIN_REASONABLE_APOGEE)
+            bad |= range_val > MAX_REASONABLE_RANGE
+            bad |= flight_time > MAX_REASONABLE_FLIGHT_TIME
+            bad |= apogee > THEORETICAL_MAX_ALTITUDE * 1.2
+        return bad
+
+    @staticmethod
+    def _outlier_reasons(apogee, range_val, flight_time):
+        r = []
+        if not np.isfinite(apogee) or not np.isfinite(range_val) or not np.isfinite(flight_time):
+            r.append("non-finite values")
+        if apogee > MAX_REASONABLE_APOGEE:
+            r.append(f"apogee {apogee / 1000:.1f} km > {MAX_REASONABLE_APOGEE / 1000:.1f} km")
+        elif apogee < MIN_REASONABLE_APOGEE:
+            r.append(f"apogee {apogee:.1f} m < {MIN_REASONABLE_APOGEE:.1f} m")
+        if range_val > MAX_REASONABLE_RANGE:
+            r.append(f"range {range_val / 1000:.1f} km > {MAX_REASONABLE_RANGE / 1000:.1f} km")
+        if flight_time > MAX_REASONABLE_FLIGHT_TIME:
+            r.append(f"flight time {flight_time:.1f} s > {MAX_REASONABLE_FLIGHT_TIME:.1f} s")
+        if apogee > THEORETICAL_MAX_ALTITUDE * 1.2:
+            r.append("apogee exceeds theoretical energy limit")
+        return r
+
+    def _filter_physics_outliers(self, results):
+        valid, outliers = [], []
+        for r in results:
+            reasons = self._outlier_reasons(r.get("apogee_altitude", 0), r.get("range", 0), r.get("flight_time", 0))
+            if reasons:
+                r["outlier_reasons"] = reasons
+                outliers.append(r)
+            else:
+                valid.append(r)
+        return valid, outliers
+
+    @staticmethod
+    def calc_stats(values):
+        values = np.asarray(values, float)
+        if values.size == 0:
+            nan = float("nan")
+            return {"mean": nan, "std": nan, "min": nan, "max": nan, "percentiles": [nan] * 5}
+        return {"mean": float(np.mean(values)), "std": float(np.std(values)), "min": float(np.min(values)),
+                "max": float(np.max(values)), "percentiles": np.percentile(values, [5, 25, 50, 75, 95]).tolist()}
+
+    def _analyze_results(self, results):
+        """List-of-dicts entry kept for callers of the reference's private API (monte_carlo.py:400-473)."""
+        initial = [r for r in results if r is not None]
+        if len(initial) == 0:
+            raise ValueError("No valid simulation results")
+        valid, outliers = self._filter_physics_outliers(initial)
+        if len(valid) == 0:
+            raise ValueError("No physically reasonable simulation results after outlier filtering")
+        ap = np.array([r["apogee_altitude"] for r in valid]); rg = np.array([r["range"] for r in valid])
+        ft = np.array([r["flight_time"] for r in valid])
+        ranges = {}
+        for r in valid:
+            for key, val in r.get("parameters", {}).items():
+                arr = np.array(val)
+                if key not in ranges:
+                    ranges[key] = {"min": arr.astype(float), "max": arr.astype(float)}
+                else:
+                    ranges[key]["min"] = np.minimum(ranges[key]["min"], arr)
+                    ranges[key]["max"] = np.maximum(ranges[key]["max"], arr)
+        for key in ranges:
+            ranges[key] = {"min": ranges[key]["min"].tolist(), "max": ranges[key]["max"].tolist()}
+        return {"n_samples": len(valid), "n_failed": len(results) - len(initial), "n_outliers": len(outliers),
+                "apogee_altitude": self.calc_stats(ap[np.isfinite(ap)]), "range": self.calc_stats(rg[np.isfinite(rg)]),
+                "flight_time": self.calc_stats(ft[np.isfinite(ft)]), "results": valid, "outliers": outliers,
+                "parameter_ranges_observed": ranges}
+
+    def _analyze_run(self, run: BatchRun):
+        O = _abi.OUT
+        ap, rg, ft = run.out[O["apogee_altitude"]], run.out[O["range"]], run.out[O["flight_time"]]
+        bad = self.outlier_mask(ap, rg, ft)
+        valid_ids = np.flatnonzero(~bad)
+        out_ids = np.flatnonzero(bad)
+        if run.disp.n == 0:
+            raise ValueError("No valid simulation results")
+        if valid_ids.size == 0:
+            raise ValueError("No physically reasonable simulation results after outlier filtering")
+        d = run.disp
+        ranges = {}
+        for key, arr in (("initial_position_offset", d.pos), ("initial_velocity_offset", d.vel),
+                         ("initial_attitude_offset", d.att), ("initial_angular_velocity_offset", d.omega),
+                         ("mass_multiplier", d.mass_multiplier), ("thrust_multiplier", d.thrust_multiplier),
+                         ("wind_speed", d.wind_speed), ("wind_direction", d.wind_direction),
+                         ("density_multiplier", d.density_multiplier), ("random_seed", d.seed.astype(float))):
+            sel = arr[valid_ids]
+            ranges[key] = {"min": sel.min(axis=0).tolist(), "max": sel.max(axis=0).tolist()}
+        reasons = [self._outlier_reasons(ap[i], rg[i], ft[i]) for i in out_ids] if out_ids.size <= 100000 else None
+        v_ap, v_rg, v_ft = ap[valid_ids], rg[valid_ids], ft[valid_ids]
+        return {"n_samples": int(valid_ids.size), "n_failed": 0, "n_outliers": int(out_ids.size),
+                "apogee_altitude": self.calc_stats(v_ap[np.isfinite(v_ap)]), "range": self.calc_stats(v_rg[np.isfinite(v_rg)]),
+                "flight_time": self.calc_stats(v_ft[np.isfinite(v_ft)]),
+                "results": SampleResults(run, valid_ids), "outliers": SampleResults(run, out_ids, reasons),
+                "parameter_ranges_observed": ranges}

@@ -1,0 +1,138 @@
+"""GPU (-m gpu): the drop-in Python API (FlightSimulator / MonteCarloAnalyzer) end to end through the
+C ABI, against the reference goldens.  These read like the reference's own scripts (example.py,
+test_fixes.py, README quick start) with their asserts replaced by the values the reference produces."""
+import numpy as np
+import pytest
+
+import util
+from erpl_monte_carlo_sim_b200 import (FlightSimulator, LiquidMotor, MonteCarloAnalyzer, Rocket, SolidMotor,
+                                       StandardAtmosphere, WindModel, _abi)
+from test_host_sampling import CSV_ALT, CSV_WIND
+
+pytestmark = pytest.mark.gpu
+VERTICAL = [0.0, -np.pi / 2 + 0.02, 0.0]
+
+
+def _check_single(res, z, name):
+    ref = z[name + "__out"][:, 0]
+    O = _abi.OUT
+    got = np.full(_abi.OUT_COUNT, np.nan)
+    got[O["rail_exit_time"]] = res["rail_exit_time"]
+    got[O["rail_exit_x"]:O["rail_exit_z"] + 1] = res["rail_exit_position"]
+    got[O["rail_exit_vx"]:O["rail_exit_vz"] + 1] = res["rail_exit_velocity"]
+    got[O["rail_exit_speed"]] = res["rail_exit_speed"]
+    got[O["rail_exit_roll"]:O["rail_exit_yaw"] + 1] = res["rail_exit_euler"]
+    got[O["rail_exit_aoa"]] = res["rail_exit_angle_of_attack"]; got[O["rail_exit_sideslip"]] = res["rail_exit_sideslip"]
+    got[O["wind_at_exit_u"]:O["wind_at_exit_w"] + 1] = res["wind_at_exit"]
+    got[O["apogee_altitude"]] = res["apogee_altitude"]; got[O["apogee_time"]] = res["apogee_time"]
+    got[O["range"]] = res["range"]; got[O["flight_time"]] = res["flight_time"]
+    got[O["final_x"]:O["final_z"] + 1] = res["position"][:, -1]; got[O["final_vx"]:O["final_vz"] + 1] = res["velocity"][:, -1]
+    got[O["max_mach"]] = res["max_mach"]; got[O["max_q"]] = res["max_dynamic_pressure"]
+    got[O["max_speed"]] = np.max(res["speed"]); got[O["max_abs_omega"]] = np.max(np.abs(res["angular_velocity"]))
+    got[O["min_stability"]] = res["min_stability_margin"]; got[O["max_stability"]] = res["max_stability_margin"]
+    got[O["max_abs_aoa"]] = res["max_abs_angle_of_attack"]; got[O["burnout_time"]] = res["burnout_time"]
+    got[O["chute_time"]] = res["parachute_deploy_time"]
+    util.assert_summary_close(got[:, None], ref[:, None], what=name)
+    assert res["time"].size == z[name + "__iout"][0, 0] + 1
+
+
+def test_example_single_flight():
+    """example.py:27-43: default Rocket + LiquidMotor, CSV wind, launch from z = 10 m."""
+    z = util.golden("flights_single")
+    sim = FlightSimulator(Rocket("Sounding Rocket"), LiquidMotor("Liquid Motor"), StandardAtmosphere(), WindModel())
+    ic = {"position": [0.0, 0.0, 10.0], "velocity": [0, 0, 0.0], "attitude": VERTICAL, "angular_velocity": [0.0, 0.0, 0.0]}
+    res = sim.simulate_flight(ic, CSV_WIND, CSV_ALT)
+    _check_single(res, z, "c1b_example_liquid_csv")
+    name = "c1b_example_liquid_csv"
+    idx = z[name + "__series__idx"]
+    for key in ("time", "altitude", "speed", "propellant_fraction"):
+        ref = z[name + "__series__" + key]
+        ok = np.abs(ref) < 1e15
+        np.testing.assert_allclose(res[key][idx][ok], ref[ok], rtol=1e-6, atol=1e-6, err_msg=key)
+    assert res["position"].shape[0] == 3 and res["quaternion"].shape[0] == 4 and res["euler_angles"].shape[0] == 3
+    assert "wind_profile" in res and res["thrust_curve_time"] is None and res["cp_location"] == Rocket().cp_location
+
+
+def test_readme_and_test_fixes_flights():
+    """README.md:26-31 (pitch 0.02 rad is HORIZONTAL) and test_fixes.py:54-62."""
+    z = util.golden("flights_single")
+    sim = FlightSimulator(Rocket(), LiquidMotor(), StandardAtmosphere(), WindModel())
+    res = sim.simulate_flight({"position": [0.0, 0.0, 0.0], "velocity": [0.0, 0.0, 0.0], "attitude": [0.0, 0.02, 0.0],
+                               "angular_velocity": [0.0, 0.0, 0.0]})
+    _check_single(res, z, "c1a_readme_liquid")
+    assert res["time"].size == 2 and sim.parachute_deployed            # F12: latched by the first derivative call
+    sim = FlightSimulator(Rocket("Test Rocket"), SolidMotor(), StandardAtmosphere(), WindModel())
+    res = sim.simulate_flight({"position": [0.0, 0.0, 0.0], "velocity": [0.0, 0.0, 0.0], "attitude": [0.0, 0.0, 0.0],
+                               "angular_velocity": [0.0, 0.0, 0.0]})
+    _check_single(res, z, "testfixes_solid")
+    assert res["thrust_curve_time"] is not None
+
+
+def test_planar_launch_to_landing():
+    z = util.golden("flights_single")
+    sim = FlightSimulator(Rocket(), SolidMotor(), StandardAtmosphere(), WindModel())
+    res = sim.simulate_flight({"attitude": VERTICAL})
+    _check_single(res, z, "c1c_planar_solid")
+    assert res["termination"] == "ground_impact" and 27000 < res["apogee_altitude"] < 28000
+
+
+def test_mutated_attributes_are_marshalled():
+    """Users of the reference mutate attributes between calls; every one the path reads must take effect."""
+    sim = FlightSimulator(Rocket(), LiquidMotor(), StandardAtmosphere(), WindModel())
+    base = sim.simulate_flight({"attitude": VERTICAL})
+    sim.rocket.dry_mass *= 1.05
+    heavier = sim.simulate_flight({"attitude": VERTICAL})
+    assert heavier["apogee_altitude"] < base["apogee_altitude"]
+    sim.rocket.dry_mass /= 1.05
+    sim.max_time = 30.0
+    short = sim.simulate_flight({"attitude": VERTICAL})
+    assert short["termination"] == "max_time" and abs(short["flight_time"] + short["rail_exit_time"] - 30.0) < 0.006
+
+
+def test_monte_carlo_example_config():
+    """example.py:57-64: run_monte_carlo on the CSV wind forecast; checks the per-sample values against the
+    reference's own per-sample results and the statistics against NumPy on those."""
+    z = util.golden("mc_solid_csv")
+    mc = MonteCarloAnalyzer(Rocket(), SolidMotor(), StandardAtmosphere(), WindModel())
+    mc.base_altitude_profile, mc.base_wind_profile = CSV_ALT, CSV_WIND
+    ic = {"position": [0.0, 0.0, 10.0], "velocity": [0, 0, 0.0], "attitude": VERTICAL, "angular_velocity": [0.0, 0.0, 0.0]}
+    an = mc.run_monte_carlo(ic, n_samples=64)
+    run = mc.last_run
+    np.testing.assert_array_equal(run.iout, z["iout"])
+    util.assert_summary_close(run.out, z["out"], what="mc example config")
+    ref_ap, ref_rg, ref_ft = (z["out"][_abi.OUT[k]] for k in ("apogee_altitude", "range", "flight_time"))
+    bad = mc.outlier_mask(ref_ap, ref_rg, ref_ft)
+    assert an["n_samples"] == int((~bad).sum()) and an["n_outliers"] == int(bad.sum()) and an["n_failed"] == 0
+    assert set(an) >= {"n_samples", "n_failed", "n_outliers", "apogee_altitude", "range", "flight_time", "results",
+                       "outliers", "parameter_ranges_observed"}
+    for key, ref in (("apogee_altitude", ref_ap), ("range", ref_rg), ("flight_time", ref_ft)):
+        s = mc.calc_stats(ref[~bad])
+        for f in ("mean", "std", "min", "max"):
+            assert abs(an[key][f] - s[f]) <= 1e-6 * abs(s[f])
+        np.testing.assert_allclose(an[key]["percentiles"], s["percentiles"], rtol=1e-6)
+    r0 = an["results"][0]
+    assert {"apogee_altitude", "range", "flight_time", "simulation_id", "parameters", "rail_exit_speed"} <= set(r0)
+    assert len(an["results"]) == an["n_samples"] and "outlier_reasons" in an["outliers"][0]
+    full = run.full_result(int(r0["simulation_id"]))
+    assert abs(full["apogee_altitude"] - r0["apogee_altitude"]) <= 1e-9 * abs(r0["apogee_altitude"])
+    assert "trajectory" in full and full["trajectory"]["position"].shape[1] == 3
+
+
+def test_monte_carlo_readme_literal_raises():
+    """README.md:33-39 with pitch 0.02: every sample is a one-step flight below 100 m and the reference raises
+    ValueError('No physically reasonable simulation results after outlier filtering')."""
+    mc = MonteCarloAnalyzer(Rocket(), LiquidMotor(), StandardAtmosphere(), WindModel())
+    ic = {"position": [0.0, 0.0, 0.0], "velocity": [0.0, 0.0, 0.0], "attitude": [0.0, 0.02, 0.0], "angular_velocity": [0.0, 0.0, 0.0]}
+    with pytest.raises(ValueError, match="No physically reasonable"):
+        mc.run_monte_carlo(ic, n_samples=1000)
+    z = util.golden("mc_readme_literal")
+    np.testing.assert_array_equal(mc.last_run.iout[:, :16], z["iout"])
+    util.assert_summary_close(mc.last_run.out[:, :16], z["out"], what="README literal")
+    assert np.all(mc.last_run.iout[_abi.IOUT["n_steps"]] == 1)
+
+
+def test_monte_carlo_optimized_path():
+    mc = MonteCarloAnalyzer(Rocket(), LiquidMotor(), StandardAtmosphere(), WindModel())
+    an = mc.run_monte_carlo({"attitude": VERTICAL}, n_samples=96, optimized=True)
+    assert "performance" in an and an["performance"]["simulations_per_second"] > 0
+    assert an["n_samples"] + an["n_outliers"] == 96

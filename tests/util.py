@@ -113,3 +113,33 @@ def single_case(z, name):
 
 MC_SETS = ["mc_planar_liquid", "mc_planar_solid", "mc_liquid_default", "mc_solid_csv", "mc_readme_literal"]
 DERIV_SETS = ["derivative_liquid_wind100", "derivative_solid_csv", "derivative_liquid_nowind"]
+
+
+def synth(z, n, seed):
+    """n seeded synthetic samples around a golden set: resample columns, jitter masses/thrust/attitude/wind."""
+    rng = np.random.RandomState(seed)
+    pick = rng.randint(0, z["scalars"].shape[1], n)
+    sc = z["scalars"][:, pick].copy()
+    wind = z["wind"][pick].copy()
+    IN = _abi.IN
+    k = rng.normal(1.0, 0.02, n)
+    sc[IN["dry_mass"]] *= k; sc[IN["prop_mass"]] *= k
+    sc[IN["burn_time"]] = sc[IN["prop_mass"]] / sc[IN["mdot"]]
+    q = sc[IN["q0"]:IN["q3"] + 1] + rng.normal(0, 2e-3, (4, n))
+    sc[IN["q0"]:IN["q3"] + 1] = q / np.linalg.norm(q, axis=0)
+    sc[IN["vx"]:IN["vz"] + 1] += rng.normal(0, 0.1, (3, n))
+    wind *= rng.uniform(0.5, 1.5, (n, 1, 1))
+    return np.ascontiguousarray(sc), np.ascontiguousarray(wind)
+
+
+
+
+def drop_nan_run_omega(out, ref, iref):
+    """trajectories that go NaN get category-level parity only.  For those flights the one
+    summary field that stays finite and keeps evolving in blown-up arithmetic (max |omega|, 1e100+) is not
+    compared; every other field (NaN pattern included) still is."""
+    out = out.copy(); ref = ref.copy()
+    nan_run = iref[_abi.IOUT["first_nan_step"]] >= 0
+    i = OUT["max_abs_omega"]
+    out[i, nan_run] = 0.0; ref[i, nan_run] = 0.0
+    return out, ref

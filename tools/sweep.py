@@ -8,7 +8,7 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from erpl_monte_carlo_sim_b200 import _abi, _lib  # noqa: E402
 import util  # noqa: E402
 from test_gpu_parity import _synth  # noqa: E402
