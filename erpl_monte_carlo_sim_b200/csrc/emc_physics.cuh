@@ -549,19 +549,98 @@ EMC_HD int nan_mode(const DevModel &M, const Sample &S, const Track &K, const St
     return att_ok ? 2 : 0;
 }
 
+/* Plain replay of `t += dt` (:229) with the burnout-index test of :479-480 (reads only the time). */
+EMC_HD int64_t replay_time_loop(const DevModel &M, const Sample &S, Track &K, int64_t max_iter)
+{
+    int64_t n = 0;
+    while (K.t < M.max_time && n < max_iter) {
+        K.t += M.dt; K.n_steps += 1; ++n;
+        if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
+    }
+    return n;
+}
+
+/* 2^e as a double, e in the normal range */
+EMC_HD double pow2_d(int e)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)(e + 1023) << 52);
+#else
+    return ldexp(1.0, e);
+#endif
+}
+EMC_HD int exponent_d(double v)    /* floor(log2(v)) for normal positive v */
+{
+#if defined(__CUDA_ARCH__)
+    return (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1023;
+#else
+    int e; frexp(v, &e); return e - 1;
+#endif
+}
+
+/*
+ * The same replay in closed form, bit-exact.  While t stays inside one binade [2^e, 2^(e+1)) every
+ * t_k is a multiple of ulp_e, so fl(t + dt) = t + d with ONE constant d = fl(t + dt) - t (unless
+ * dt sits exactly on a rounding tie, which is detected and sent to the plain loop).  Whole binades are
+ * therefore advanced with integer arithmetic (~10 segments for t in [0.5, 300]) instead of ~57 k
+ * dependent additions that would stall the other 31 lanes of the warp; the step that crosses a
+ * binade edge is taken as a real floating-point addition.  Mode 2 also advances x, y by
+ * n * (dt/6 * acc): 1e-16-level difference to the step-by-step sum, far inside the parity bar.
+ */
 EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K, State &s)
 {
     int64_t n = 0;
-    /* RK4 combination of :224 for a constant derivative k: ((k + 2k) + 2k) + k, then x += (dt/6)*acc */
-    const double ax = ((s.vx + 2.0 * s.vx) + 2.0 * s.vx) + s.vx;
-    const double ay = ((s.vy + 2.0 * s.vy) + 2.0 * s.vy) + s.vy;
-    const bool ballistic = (K.replay == 2);
+    const double t_begin = K.t;
     while (K.t < M.max_time) {
-        K.t += M.dt; K.n_steps += 1; ++n;
-        if (ballistic) { s.x += M.dt_over_6 * ax; s.y += M.dt_over_6 * ay; }
-        /* burnout index of :479-480 reads nothing but the time */
-        if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
+        const double t = K.t;
+        const double t1 = t + M.dt;
+        int64_t seg = 0;          /* steps that can be taken in closed form inside this binade */
+        double d = 0.0;
+        if (t >= 4.450147717014403e-308 && t1 > t && finite_d(t1)) {
+            const int e = exponent_d(t);
+            const double hi = pow2_d(e + 1);
+            if (t1 < hi) {
+                d = t1 - t;                                   /* exact: both are multiples of ulp_e */
+                const double ulp = pow2_d(e - 52);
+                const double resid = M.dt - d;                /* exact low part of dt */
+                if (fabs(resid) != 0.5 * ulp) {               /* not a rounding tie */
+                    const double sc = pow2_d(52 - e);         /* 1/ulp: scaling by 2^k is exact */
+                    const long long D = (long long)(d * sc);
+                    const long long A = (long long)((hi - t) * sc);
+                    long long jb = (A + D - 1) / D - 1;       /* largest j with t + j*d < hi */
+                    if (M.max_time < hi) {
+                        const long long G = (long long)((M.max_time - t) * sc);
+                        const long long jg = (G + D - 1) / D; /* smallest j with t + j*d >= max_time */
+                        if (jg < jb) jb = jg;
+                    }
+                    seg = jb;
+                }
+            }
+        }
+        if (seg < 1) {            /* binade crossing, tie, or degenerate operands: one real step */
+            if (!(t1 > t)) { break; }                         /* dt no longer advances t (reference would spin) */
+            n += replay_time_loop(M, S, K, 1);
+            continue;
+        }
+        if (!K.burnout_found && (S.burn_time == S.burn_time)) {
+            /* first j in [1, seg] with fl((t + j*d) - t_rail) > burn_time; the left side is monotone in j */
+            double est = ceil((S.burn_time + K.t_rail - t) / d);
+            long long j = (est < 1.0) ? 1 : ((est > (double)seg) ? seg : (long long)est);
+            while (j > 1 && ((t + (double)(j - 1) * d) - K.t_rail) > S.burn_time) --j;
+            while (j <= seg && !(((t + (double)j * d) - K.t_rail) > S.burn_time)) ++j;
+            if (j <= seg) { K.burnout_found = true; K.burnout_time = (t + (double)j * d) - K.t_rail; }
+        }
+        K.t = t + (double)seg * d;                            /* exact */
+        K.n_steps += (int32_t)seg;
+        n += seg;
     }
+    if (K.replay == 2) {
+        const double ax = ((s.vx + 2.0 * s.vx) + 2.0 * s.vx) + s.vx;     /* :224 with k = vx in all stages */
+        const double ay = ((s.vy + 2.0 * s.vy) + 2.0 * s.vy) + s.vy;
+        s.x += (double)n * (M.dt_over_6 * ax);
+        s.y += (double)n * (M.dt_over_6 * ay);
+    }
+    (void)t_begin;
     K.term = EMC_TERM_MAX_TIME;
     return n;
 }

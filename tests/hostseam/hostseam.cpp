@@ -71,4 +71,20 @@ int hs_batch(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outp
     return 0;
 }
 
+
+/* replay_time (closed form) and replay_time_loop (plain) on the same start state: out = {n, t_end, burnout_time, found} */
+__attribute__((visibility("default")))
+int hs_replay(double t0, double t_rail, double dt, double max_time, double burn_time, int closed_form, double *out)
+{
+    DevModel D; memset(&D, 0, sizeof D);
+    D.dt = dt; D.max_time = max_time; D.dt_over_6 = dt / 6.0;
+    Sample S; memset(&S, 0, sizeof S); S.burn_time = burn_time;
+    State s; memset(&s, 0, sizeof s);
+    Track K; track_init(K, s, t_rail);
+    K.t = t0; K.replay = 1;
+    int64_t n = closed_form ? replay_time(D, S, K, s) : replay_time_loop(D, S, K, (int64_t)1 << 40);
+    out[0] = (double)n; out[1] = K.t; out[2] = K.burnout_time; out[3] = K.burnout_found ? 1.0 : 0.0; out[4] = (double)K.n_steps;
+    return 0;
+}
+
 }

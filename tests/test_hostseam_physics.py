@@ -77,3 +77,31 @@ def test_seam_ballistic_nan_fast_forward():
                               what="fast-forward vs oracle")
     # max|omega| keeps its value at the fast-forward point: never above the full integration's
     assert np.all(fast[0][OUT["max_abs_omega"]] <= full[0][OUT["max_abs_omega"]] * (1 + 1e-12))
+
+
+def test_closed_form_time_replay_is_bit_exact():
+    """The NaN fast-forward advances `t += dt` binade by binade in integer arithmetic; it must land on
+    exactly the t, step count and burnout time that ~57 k floating-point additions produce."""
+    import ctypes as C
+    HS = util.hostseam_lib()
+    HS.hs_replay.argtypes = [C.c_double] * 5 + [C.c_int, C.POINTER(C.c_double)]
+    rng = np.random.RandomState(3)
+    cases = []
+    for rail_steps in (0, 1, 60, 67, 87, 94, 120):
+        t_rail = 0.0
+        for _ in range(rail_steps):
+            t_rail += 0.01
+        for k in (0, 1, 1868, 2371, 2914, 30000):
+            t0 = t_rail
+            for _ in range(k):
+                t0 += 0.005
+            for burn in (13.7, 14.906103286384978, 15.63, 0.0, 400.0, float("nan")):
+                cases.append((t0, t_rail, 0.005, 300.0, burn))
+    cases += [(0.3 + rng.rand(), 0.3, dt, mt, 14.0 + rng.rand()) for dt in (0.005, 0.0025, 0.001953125, 0.00390625, 0.0037, 1e-3)
+              for mt in (300.0, 299.9975, 17.3, 1.0, 0.2)]
+    cases += [(2.0 ** -1030, 0.0, 0.005, 1.0, 0.5), (299.999, 0.87, 0.005, 300.0, 14.9), (300.0, 0.87, 0.005, 300.0, 14.9)]
+    a = (C.c_double * 5)(); b = (C.c_double * 5)()
+    for c in cases:
+        HS.hs_replay(*c, 1, a); HS.hs_replay(*c, 0, b)
+        assert list(a)[:2] == list(b)[:2] and a[4] == b[4], (c, list(a), list(b))
+        assert a[3] == b[3] and (a[2] == b[2] or a[3] == 0.0), (c, list(a), list(b))
