@@ -72,6 +72,8 @@ def load():
     L.emc_derivative_debug.argtypes = [vp, C.POINTER(_abi.EmcInputs), i64, _dp, _dp, _ip, _dp]
     L.emc_get_counters.argtypes = [vp, C.POINTER(_abi.EmcCounters)]
     L.emc_fp64_peak.argtypes = [vp, _dp, _dp]
+    L.emc_math_debug.argtypes = [vp, C.c_int, i64, _dp, _dp, _dp]
+    L.emc_math_debug.restype = C.c_int
     for name in ("emc_create", "emc_destroy", "emc_set_model", "emc_run_batch", "emc_run_batch_device",
                  "emc_run_tape", "emc_derivative_debug", "emc_get_counters", "emc_fp64_peak"):
         getattr(L, name).restype = C.c_int
@@ -204,6 +206,15 @@ class Engine:
                                                    state.ctypes.data_as(_dp), ch.ctypes.data_as(_ip),
                                                    sd.ctypes.data_as(_dp)), "emc_derivative_debug")
         return sd, ch
+
+    def math_debug(self, op, x, y=None):
+        x = np.ascontiguousarray(x, np.float64)
+        yy = np.ascontiguousarray(y, np.float64) if y is not None else None
+        out = np.empty_like(x)
+        self._check(self._lib.emc_math_debug(self._ctx, int(op), x.size, x.ctypes.data_as(_dp),
+                                             yy.ctypes.data_as(_dp) if yy is not None else None,
+                                             out.ctypes.data_as(_dp)), "emc_math_debug")
+        return out
 
     def counters(self) -> dict:
         c = _abi.EmcCounters()

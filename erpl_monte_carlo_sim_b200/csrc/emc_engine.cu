@@ -188,6 +188,19 @@ __global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+__global__ void emc_math_kernel(int op, int64_t n, const double *x, const double *y, double *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double r;
+    if (op == 0) r = fast_rcp(x[i]);
+    else if (op == 1) r = fast_rsqrt(x[i]);
+    else if (op == 2) r = fast_atan2(y[i], x[i]);
+    else r = fast_sqrt(x[i]);
+    out[i] = r;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* 8 independent DFMA chains per thread, all in registers: 2*8*iters flop per thread */
 __global__ void __launch_bounds__(256) emc_dfma_kernel(double *sink, int iters, double a, double b)
 {
@@ -530,6 +543,26 @@ EMC_EXPORT int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_t); cudaFree(d_s); cudaFree(d_k); cudaFree(d_c);
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("emc_derivative_debug: ") + cudaGetErrorString(e));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_math_debug(emc_ctx *ctx, int op, int64_t n, const double *x, const double *y, double *out)
+{
+    if (!ctx || !x || !out || n < 0 || op < 0 || op > 3 || (op == 2 && !y)) return fail(ctx, EMC_ERR_INVALID, "emc_math_debug: bad argument");
+    if (n == 0) return EMC_OK;
+    CK(cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double) * 3 * n));
+    cudaError_t e = cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && y) e = cudaMemcpyAsync(d + n, y, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        emc_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(op, n, d, d + n, d + 2 * n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * n, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("emc_math_debug: ") + cudaGetErrorString(e));
     return EMC_OK;
 }
 

@@ -61,9 +61,9 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
     const double fin_area = 0.5 * (cr + ct) * s;                                      /* rocket.py:176 */
     const double AR = (fin_area > 0) ? 2 * (s * s) / fin_area : 0.0;                  /* rocket.py:177 */
     const double cs = cos(m.fin_sweep_angle);
-    D.cos_sweep = cs;
-    D.AR_over_cos = AR / ((1e-6 > cs) ? 1e-6 : cs);                                   /* rocket.py:179 */
-    D.two_pi_AR = 2 * M_PI * AR;                                                      /* rocket.py:180 */
+    const double aoc = AR / ((1e-6 > cs) ? 1e-6 : cs);                                /* rocket.py:179 */
+    D.AR_over_cos2 = aoc * aoc;
+    D.two_pi_AR_cos = (2 * M_PI * AR) * cs;                                           /* rocket.py:180 */
     D.power_off_factor = m.power_off_drag_factor;
     D.stall_angle = 15.0 * (M_PI / 180.0);                                            /* rocket.py:167 */
     D.inv_stall_span = 1.0 / (45.0 * (M_PI / 180.0) - 15.0 * (M_PI / 180.0));         /* rocket.py:168,185 */
@@ -84,15 +84,18 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
         for (int i = 0; i < m.n_wind && uni; ++i) if (fabs(a[i] - (a[0] + i * dz)) > 1e-6 * dz) uni = false;
         D.wind_uniform = uni ? 1 : 0; D.wind_alt0 = a[0]; D.wind_inv_dz = uni ? 1.0 / dz : 0.0;
     }
-    for (int i = 0; i < m.n_cd; ++i) { T.cd_mach[i] = m.cd_mach[i]; T.cd0[i] = m.cd0[i]; T.cda[i] = m.cda[i]; }
-    for (int i = 0; i + 1 < m.n_cd; ++i) {        /* np.interp slope, compiled_base.c */
-        T.cd0_s[i] = (m.cd0[i + 1] - m.cd0[i]) / (m.cd_mach[i + 1] - m.cd_mach[i]);
-        T.cda_s[i] = (m.cda[i + 1] - m.cda[i]) / (m.cd_mach[i + 1] - m.cd_mach[i]);
-    }
-    for (int i = 0; i < m.n_cp; ++i) { T.cp_mach[i] = m.cp_mach[i]; T.cp_shift[i] = m.cp_shift[i]; }
-    for (int i = 0; i + 1 < m.n_cp; ++i) T.cp_s[i] = (m.cp_shift[i + 1] - m.cp_shift[i]) / (m.cp_mach[i + 1] - m.cp_mach[i]);
-    for (int i = 0; i < D.n_thrust; ++i) { T.th_t[i] = m.thrust_time[i]; T.th_f[i] = m.thrust_curve[i]; }
-    for (int i = 0; i + 1 < D.n_thrust; ++i) T.th_s[i] = (m.thrust_curve[i + 1] - m.thrust_curve[i]) / (m.thrust_time[i + 1] - m.thrust_time[i]);
+    /* bracket tables (see DevTables): np.interp slope expression, compiled_base.c */
+    auto fill = [](int n, const double *x, const double *f, double *lo, double *hi, double *x0, double *f0, double *sl) {
+        for (int b = 0; b <= n; ++b) {
+            if (b == 0) { lo[b] = -INFINITY; hi[b] = x[0]; x0[b] = x[0]; f0[b] = f[0]; sl[b] = 0.0; }
+            else if (b == n) { lo[b] = x[n - 1]; hi[b] = INFINITY; x0[b] = x[n - 1]; f0[b] = f[n - 1]; sl[b] = 0.0; }
+            else { lo[b] = x[b - 1]; hi[b] = x[b]; x0[b] = x[b - 1]; f0[b] = f[b - 1]; sl[b] = (f[b] - f[b - 1]) / (x[b] - x[b - 1]); }
+        }
+    };
+    fill(m.n_cd, m.cd_mach, m.cd0, T.cd_lo, T.cd_hi, T.cd_x0, T.cd0_f, T.cd0_s);
+    fill(m.n_cd, m.cd_mach, m.cda, T.cd_lo, T.cd_hi, T.cd_x0, T.cda_f, T.cda_s);
+    fill(m.n_cp, m.cp_mach, m.cp_shift, T.cp_lo, T.cp_hi, T.cp_x0, T.cp_f, T.cp_s);
+    if (D.n_thrust > 0) fill(D.n_thrust, m.thrust_time, m.thrust_curve, T.th_lo, T.th_hi, T.th_x0, T.th_f, T.th_s);
 }
 
 }  // namespace emc

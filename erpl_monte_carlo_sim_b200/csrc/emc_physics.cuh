@@ -51,7 +51,7 @@ struct DevModel {
     double cg_dry, prop_cg, d4sq, len2_12, Ixx_dry, Iyy_dry;
     /* aerodynamics, rocket.py:138-218 */
     double ref_area, ref_diam, inv_ref_diam, area_diam, cp_location;
-    double AR_over_cos, two_pi_AR, cos_sweep, power_off_factor;
+    double AR_over_cos2, two_pi_AR_cos, power_off_factor;   /* (AR/max(cos,1e-6))^2, 2*pi*AR*cos(sweep) */
     double stall_angle, inv_stall_span;
     double chute_cd, chute_area, chute_alt;
     /* simulator knobs, simulator.py:19-37,42,209 */
@@ -61,13 +61,21 @@ struct DevModel {
     int32_t motor_kind, n_cd, n_cp, n_thrust, has_wind, n_wind, wind_uniform, pad_;
 };
 
-/* Tables staged into shared memory by the kernels (host seam: plain struct). Slopes are computed on
- * the host with the same (f1-f0)/(x1-x0) expression np.interp uses, so they are bit-identical. */
+/* Tables staged into shared memory by the kernels (host seam: plain struct), stored as BRACKETS so
+ * that np.interp's clamping needs no special case: a table with n knots has n+1 brackets
+ *   b = 0      (-inf, x[0])       value f[0],    slope 0
+ *   b = 1..n-1 [x[b-1], x[b])     value f[b-1] + s*(x - x[b-1]),  s = (f[b]-f[b-1])/(x[b]-x[b-1])
+ *   b = n      [x[n-1], +inf)     value f[n-1],  slope 0
+ * Slopes are computed on the host with the expression np.interp uses (bit-identical).  Each lane
+ * remembers its bracket (Mach and burn time move slowly), so a lookup is two compares and an FMA. */
+#define EMC_BRK_CD (EMC_MAX_CD_KNOTS + 2)
+#define EMC_BRK_CP (EMC_MAX_CP_KNOTS + 2)
+#define EMC_BRK_TH (EMC_MAX_THRUST_KNOTS + 2)
 struct DevTables {
-    double cd_mach[EMC_MAX_CD_KNOTS], cd0[EMC_MAX_CD_KNOTS], cda[EMC_MAX_CD_KNOTS];
-    double cd0_s[EMC_MAX_CD_KNOTS], cda_s[EMC_MAX_CD_KNOTS];
-    double cp_mach[EMC_MAX_CP_KNOTS], cp_shift[EMC_MAX_CP_KNOTS], cp_s[EMC_MAX_CP_KNOTS];
-    double th_t[EMC_MAX_THRUST_KNOTS], th_f[EMC_MAX_THRUST_KNOTS], th_s[EMC_MAX_THRUST_KNOTS];
+    double cd_lo[EMC_BRK_CD], cd_hi[EMC_BRK_CD], cd_x0[EMC_BRK_CD];
+    double cd0_f[EMC_BRK_CD], cd0_s[EMC_BRK_CD], cda_f[EMC_BRK_CD], cda_s[EMC_BRK_CD];
+    double cp_lo[EMC_BRK_CP], cp_hi[EMC_BRK_CP], cp_x0[EMC_BRK_CP], cp_f[EMC_BRK_CP], cp_s[EMC_BRK_CP];
+    double th_lo[EMC_BRK_TH], th_hi[EMC_BRK_TH], th_x0[EMC_BRK_TH], th_f[EMC_BRK_TH], th_s[EMC_BRK_TH];
 };
 
 /* Per-sample parameters (registers) */
@@ -84,6 +92,7 @@ struct Sample {
 struct WindBracket {
     double lo, hi, x0;
     double f0[3], s[3];
+    int32_t j_cd, j_cp, j_th;      /* remembered brackets of the Cd/CP-vs-Mach and thrust-vs-time tables */
 };
 
 struct State {
@@ -102,26 +111,86 @@ EMC_HD double py_min(double a, double b) { return (b < a) ? b : a; }   /* Python
 EMC_HD void np_max_acc(double &m, double v) { m = (v > m || v != v) ? ((m != m) ? m : v) : m; }
 EMC_HD void np_min_acc(double &m, double v) { m = (v < m || v != v) ? ((m != m) ? m : v) : m; }
 
-/* index of the bracket: number of interior knots <= x, i.e. largest j in [0, n-2] with xp[j] <= x
- * (x already known to be inside [xp[0], xp[n-1]]) */
-EMC_HD int bracket_small(const double *xp, int n, double x)
+/* ---------------- cheap reciprocal / reciprocal square root / atan2 ----------------
+ * Device: MUFU seed + Newton steps in DFMA, no slow-path branches (operands here are positive, normal
+ * numbers: masses, inertias, R*T, squared speeds).  ~1 ulp; tests/test_gpu_parity.py measures it.
+ * Host (test seam): plain IEEE division / sqrt. */
+EMC_HD double fast_rcp(double x)
 {
-    int j = 0;
 #if defined(__CUDA_ARCH__)
-#pragma unroll 1
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+#else
+    return 1.0 / x;
 #endif
-    for (int k = 1; k < n - 1; ++k) j += (xp[k] <= x) ? 1 : 0;
-    return j;
 }
 
-/* np.interp with precomputed slopes (utils.py:147-149): clamps outside, NaN -> NaN */
-EMC_HD double interp_tab(const double *xp, const double *fp, const double *sl, int n, double x)
+EMC_HD double fast_rsqrt(double x)
 {
-    if (x != x) return x;
-    if (x >= xp[n - 1]) return fp[n - 1];
-    if (x <= xp[0]) return fp[0];
-    int j = bracket_small(xp, n, x);
-    return sl[j] * (x - xp[j]) + fp[j];
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double h = 0.5 * y;
+    double e = fma(-x * y, y, 1.0);          /* 1 - x*y^2 */
+    y = fma(h, e, y);
+    h = 0.5 * y;
+    e = fma(-x * y, y, 1.0);
+    y = fma(h, e, y);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+
+/* sqrt(x) for x >= 0 via x*rsqrt(x); 0 -> 0, NaN -> NaN */
+EMC_HD double fast_sqrt(double x)
+{
+    const double r = x * fast_rsqrt(x);
+    return (x > 0.0) ? r : ((x == 0.0) ? 0.0 : NAN);
+}
+
+/* atan2 with one division and a degree-18 minimax polynomial in t^2 (tools/fit_atan.py, relative error
+ * 2.8e-17 before rounding): atan(t) = t + t*u*Q(u), u = t^2, t = min(|x|,|y|)/max(|x|,|y|) in [0,1]. */
+EMC_HD double fast_atan2(double y, double x)
+{
+    const double ax = fabs(x), ay = fabs(y);
+    const bool swap = ay > ax;
+    const double num = swap ? ax : ay, den = swap ? ay : ax;
+    double t = num * fast_rcp(den);
+    t = (den > 0.0) ? t : ((den == 0.0) ? 0.0 : t);      /* atan2(0, 0) = 0; NaN stays NaN */
+    const double u = t * t, u2 = u * u;
+    /* two interleaved Horner chains (even / odd coefficients) for instruction-level parallelism */
+    double pe = -2.025853092076122e-05, po = 0.00022302218576995646;
+    pe = fma(pe, u2, -0.0011640707910558462);  po = fma(po, u2, 0.0038559722045492582);
+    pe = fma(pe, u2, -0.009184554046120928);   po = fma(po, u2, 0.01697802875462528);
+    pe = fma(pe, u2, -0.02582678957209261);    po = fma(po, u2, 0.03406780544224133);
+    pe = fma(pe, u2, -0.04092637904494918);    po = fma(po, u2, 0.04673949464358622);
+    pe = fma(pe, u2, -0.05239232950492257);    po = fma(po, u2, 0.058773077574447684);
+    pe = fma(pe, u2, -0.0666586036040998);     po = fma(po, u2, 0.07692212930161942);
+    pe = fma(pe, u2, -0.0909090123535805);     po = fma(po, u2, 0.11111110678746688);
+    pe = fma(pe, u2, -0.14285714271334715);    po = fma(po, u2, 0.19999999999755017);
+    pe = fma(pe, u2, -0.3333333333333186);
+    const double q = fma(po, u, pe);
+    double r = fma(t * u, q, t);
+    if (swap) r = (1.5707963267948966 - r) + 6.123233995736766e-17;
+    if (x < 0.0) r = (3.141592653589793 - r) + 1.2246467991473532e-16;
+    return (y < 0.0 || (y == 0.0 && signbit(y))) ? -r : r;
+}
+
+/* remembered-bracket lookup: j stays valid while lo[j] <= x < hi[j]; NaN leaves j alone (the FMA that
+ * follows then yields NaN, which is np.interp's answer) */
+EMC_HD int brk_find(const double *lo, const double *hi, int nb, int j, double x)
+{
+    if (!(x >= lo[j] && x < hi[j]) && (x == x)) {
+        while (j < nb - 1 && x >= hi[j]) ++j;
+        while (j > 0 && x < lo[j]) --j;
+    }
+    return j;
 }
 
 /* ---------------- atmosphere: T and 1/(R*T), p  (environment.py:26-103) ---------------- */
@@ -146,7 +215,7 @@ EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, d
         T = py_max(T, 180.0);
         base = 868.02; arg = 0.0;     /* filled below once 1/(R*T) is known */
     }
-    inv_RT = 1.0 / (M.R_gas * T);
+    inv_RT = fast_rcp(M.R_gas * T);
     if (use_log) arg = le * log(lx);
     if (z > 32000.0 || z != z) arg = -(z - 32000.0) * (M.g0 * inv_RT);   /* -(z-32000)/(R*T/g) */
     p = base * exp(arg);
@@ -156,7 +225,7 @@ EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, d
 EMC_HD double gravity(const DevModel &M, double z)
 {
     const double Re = 6.371e6;
-    double r = Re / (Re + z);
+    const double r = Re * fast_rcp(Re + z);
     return M.g0 * (r * r);
 }
 
@@ -204,11 +273,13 @@ EMC_HD void wind_at(const DevModel &M, const double *alt, const Sample &S, doubl
 }
 
 /* ---------------- thrust (motor.py:54-76, 152-156), caller has checked pf>0 && t<=burn ---------- */
-EMC_HD double thrust_at(const DevModel &M, const DevTables &Tb, const Sample &S, double t, double p)
+EMC_HD double thrust_at(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, double p)
 {
     if (t < 0.0 || t > S.burn_time) return 0.0;
     if (M.motor_kind == EMC_MOTOR_SOLID) {
-        double f = interp_tab(Tb.th_t, Tb.th_f, Tb.th_s, M.n_thrust, t) * S.thrust_a;
+        const int j = brk_find(Tb.th_lo, Tb.th_hi, M.n_thrust + 1, C.j_th, t);
+        C.j_th = j;
+        const double f = fma(Tb.th_s[j], t - Tb.th_x0[j], Tb.th_f[j]) * S.thrust_a;
         return f + S.nozzle_area * (101325.0 - p);
     }
     return S.thrust_a - S.nozzle_area * p;
@@ -228,16 +299,17 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const bool burning = (pf > 0.0) && (t <= S.burn_time);
 
     /* :308  normalise the quaternion (identity if |q| <= 1e-12 or NaN), utils.py:76-82 */
-    double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
-    double qw, qx, qy, qz;
-    if (n2 > 1e-24) { double rn = 1.0 / sqrt(n2); qw = s.q0 * rn; qx = s.q1 * rn; qy = s.q2 * rn; qz = s.q3 * rn; }
-    else { qw = 1.0; qx = 0.0; qy = 0.0; qz = 0.0; }
+    const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
+    const bool q_ok = n2 > 1e-24;
+    const double rn = fast_rsqrt(q_ok ? n2 : 1.0);
+    const double qw = q_ok ? s.q0 * rn : 1.0, qx = q_ok ? s.q1 * rn : 0.0;
+    const double qy = q_ok ? s.q2 * rn : 0.0, qz = q_ok ? s.q3 * rn : 0.0;
 
     /* :311-321  mass properties, rocket.py:110-136 */
     double mp = S.prop_mass * pf;
     double mass = S.dry_mass + mp;
     if (mass < S.dry_mass) { mass = S.dry_mass; mp = S.prop_mass * 0.0; }      /* :315-318 */
-    const double inv_m = 1.0 / mass;
+    const double inv_m = fast_rcp(mass);
     const double cg = (S.dry_cg + mp * M.prop_cg) * inv_m;
     const double dcg = M.prop_cg - cg;
     const double Ixx = M.Ixx_dry + mp * M.d4sq;
@@ -262,57 +334,53 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double vbz = r02 * ux + r12 * uy + r22 * uz;
     const double v2 = ux * ux + uy * uy + uz * uz;
     const double mach2 = v2 * (inv_RT * (1.0 / 1.4));       /* (|v|/sqrt(1.4*R*T))^2, utils.py:152-157 */
-    const double mach = sqrt(mach2);
     const double qdyn = 0.5 * rho * v2;
 
     /* :359-363 thrust along body x */
-    double fbx = burning ? thrust_at(M, Tb, S, t, p) : 0.0;
+    double fbx = burning ? thrust_at(M, Tb, S, WB, t, p) : 0.0;
     double fby = 0.0, fbz = 0.0;
-    double my = 0.0, mz = 0.0;
-    /* :394-399: croll = 0.0 but q*0.0 keeps the reference's NaN/Inf propagation into roll */
-    double mx = 0.0;
+    double mx = 0.0, my = 0.0, mz = 0.0;
 
     /* :366-369 sticky parachute latch */
     if (!chute && s.z <= M.chute_alt && s.vz < 0.0) { chute = true; chute_time = t; }
 
     const bool aero = (!chute) && (qdyn > 0.0);
-    double alpha = 0.0, beta = 0.0;
     const double vxz2 = vbx * vbx + vbz * vbz;
     const double vb2 = vxz2 + vby * vby;
     if (aero || want_diag) {
-        /* utils.py:160-172 */
+        /* Mach-table brackets (rocket.py:105-108,156-157): shared by Cd0/Cda, separate knots for CP */
+        const double mach = fast_sqrt(mach2);
+        const int jc = brk_find(Tb.cp_lo, Tb.cp_hi, M.n_cp + 1, WB.j_cp, mach);
+        WB.j_cp = jc;
+        const double cp = M.cp_location + fma(Tb.cp_s[jc], mach - Tb.cp_x0[jc], Tb.cp_f[jc]);
+        const double sm = cp - cg;
+        /* utils.py:160-164 */
         const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
-        alpha = a_dead ? 0.0 : atan2(vbz, vbx);
+        const double alpha = a_dead ? 0.0 : fast_atan2(vbz, vbx);
+        if (want_diag) { dg.mach2 = mach2; dg.qdyn = qdyn; dg.abs_aoa = fabs(alpha); dg.stab = sm * M.inv_ref_diam; }
         if (aero) {
-            const double vxz = sqrt(vxz2);
+            /* utils.py:167-172 and the sin/cos of utils.py:194-197 from the velocity ratios */
+            const double rvxz = fast_rsqrt(vxz2);
+            const double vxz = (vxz2 > 0.0) ? vxz2 * rvxz : vxz2;
             const bool b_dead = vxz < 1e-6;
-            beta = b_dead ? 0.0 : atan2(vby, vxz);
-            /* sin/cos of alpha, beta from the velocity ratios (== sin/cos(atan2(...)) to rounding) */
-            double ca, sa, cb, sb;
-            if (a_dead) { ca = 1.0; sa = 0.0; } else { double iv = 1.0 / vxz; ca = vbx * iv; sa = vbz * iv; }
-            if (b_dead) { cb = 1.0; sb = 0.0; } else { double iv = 1.0 / sqrt(vb2); cb = vxz * iv; sb = vby * iv; }
+            double beta = b_dead ? 0.0 : vby;               /* planar flights: atan2(+-0, vxz) = +-0, no polynomial */
+            if (!b_dead && vby != 0.0) beta = fast_atan2(vby, vxz);
+            const double rvb = fast_rsqrt(vb2);
+            const double ca = a_dead ? 1.0 : vbx * rvxz, sa = a_dead ? 0.0 : vbz * rvxz;
+            const double cb = b_dead ? 1.0 : vxz * rvb, sb = b_dead ? 0.0 : vby * rvb;
 
             /* rocket.py:138-218 */
-            double cd0, cda;
-            {
-                const int n = M.n_cd;
-                if (mach != mach) { cd0 = mach; cda = mach; }
-                else if (mach >= Tb.cd_mach[n - 1]) { cd0 = Tb.cd0[n - 1]; cda = Tb.cda[n - 1]; }
-                else if (mach <= Tb.cd_mach[0]) { cd0 = Tb.cd0[0]; cda = Tb.cda[0]; }
-                else {
-                    int j = bracket_small(Tb.cd_mach, n, mach);
-                    double dm = mach - Tb.cd_mach[j];
-                    cd0 = Tb.cd0_s[j] * dm + Tb.cd0[j];
-                    cda = Tb.cda_s[j] * dm + Tb.cda[j];
-                }
-            }
-            cd0 *= S.cd_scale;
+            const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, WB.j_cd, mach);
+            WB.j_cd = jd;
+            const double dm = mach - Tb.cd_x0[jd];
+            const double cd0 = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * S.cd_scale;
+            const double cda = fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]);
             double cd = cd0 + cda * (alpha * alpha);
             if (!(pf > 0.0)) cd *= M.power_off_factor;
             const double abs_alpha = fabs(alpha);
-            const double beta_m = sqrt(fabs(1.0 - mach2));
-            const double tt = M.AR_over_cos * beta_m;
-            const double cl_alpha = (M.two_pi_AR / (2.0 + sqrt(4.0 + tt * tt))) * M.cos_sweep;
+            /* cl_alpha = 2*pi*AR / (2 + sqrt(4 + (AR*beta_M/cos)^2)) * cos,  beta_M^2 = |1 - M^2|  (:178-180) */
+            const double rad = 4.0 + M.AR_over_cos2 * fabs(1.0 - mach2);
+            const double cl_alpha = M.two_pi_AR_cos * fast_rcp(2.0 + rad * fast_rsqrt(rad));
             double cl = cl_alpha * alpha;
             double cy = cl_alpha * beta;
             if (abs_alpha > M.stall_angle) {
@@ -324,11 +392,8 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
                 cd *= 1.0 + 0.5 * over;
                 cy *= sf;
             }
-            const double cp = M.cp_location + interp_tab(Tb.cp_mach, Tb.cp_shift, Tb.cp_s, M.n_cp, mach);
-            const double sm = cp - cg;
             const double cm = -cl_alpha * sm * alpha;
             const double cyaw = -cl_alpha * sm * beta;
-            dg.stab = sm * M.inv_ref_diam;
 
             /* :385-391  F_b += W2B(alpha,beta) @ [-D,-S,-L], utils.py:199-205 */
             const double qa = qdyn * M.ref_area;
@@ -336,7 +401,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
             fbx += (ca * cb) * (-D) + (-sb) * (-Sd) + (sa * cb) * (-L);
             fby += (ca * sb) * (-D) + cb * (-Sd) + (sa * sb) * (-L);
             fbz += (-sa) * (-D) + ca * (-L);
-            /* :394-411 */
+            /* :394-411; croll = 0.0 but q*0.0 keeps the reference's NaN/Inf propagation into roll */
             const double qad = qdyn * M.area_diam;
             mx = qdyn * 0.0;
             my = qad * cm;
@@ -345,18 +410,12 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     }
     if (chute) {
         /* :372-377 */
-        const double rel = sqrt(vb2);
-        if (rel > 0.0) {
+        const double rrel = fast_rsqrt(vb2);
+        if (vb2 > 0.0) {                                   /* rel_speed > 0 (False for NaN) */
             const double drag = (0.5 * rho * vb2 * M.chute_cd) * M.chute_area;
-            const double f = -drag / rel;
+            const double f = -drag * rrel;
             fbx += f * vbx; fby += f * vby; fbz += f * vbz;
         }
-    }
-    if (want_diag) {
-        dg.mach2 = mach2;
-        dg.qdyn = qdyn;
-        dg.abs_aoa = fabs(alpha);
-        if (!aero) dg.stab = (M.cp_location + interp_tab(Tb.cp_mach, Tb.cp_shift, Tb.cp_s, M.n_cp, mach) - cg) * M.inv_ref_diam;
     }
 
     /* :414-415 damping */
@@ -372,7 +431,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     k.vx = fix * inv_m; k.vy = fiy * inv_m; k.vz = fiz * inv_m;
 
     /* :431-436  Euler equations with Izz == Iyy (rocket.py:127); Ixx, Iyy > 0 */
-    const double inv_Iyy = 1.0 / Iyy;
+    const double inv_Iyy = fast_rcp(Iyy);
     /* roll: (mx - (Izz-Iyy)*wy*wz)/Ixx with Izz-Iyy == 0 and mx in {0, NaN}: no division needed */
     k.wx = (Ixx > 0.0) ? (mx - 0.0 * (s.wy * s.wz)) : 0.0;
     k.wy = (Iyy > 0.0) ? (my - (Ixx - Iyy) * s.wz * s.wx) * inv_Iyy : 0.0;
@@ -391,7 +450,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     double pfr = 0.0;
     if (burning) {
         pfr = S.pf_rate;
-        if (pfr != 0.0 && pf < 0.01 * fabs(pfr)) pfr = -pf / 0.01;
+        if (pfr != 0.0 && pf < 0.01 * fabs(pfr)) pfr = -pf * 100.0;
     }
     k.pf = pfr;
 }
@@ -513,7 +572,7 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
     s.pf += h * acc.pf;
     /* :227 renormalise */
     const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
-    if (n2 > 1e-24) { const double rn = 1.0 / sqrt(n2); s.q0 *= rn; s.q1 *= rn; s.q2 *= rn; s.q3 *= rn; }
+    if (n2 > 1e-24) { const double rn = fast_rsqrt(n2); s.q0 *= rn; s.q1 *= rn; s.q2 *= rn; s.q3 *= rn; }
     else { s.q0 = 1.0; s.q1 = 0.0; s.q2 = 0.0; s.q3 = 0.0; }
     K.t += M.dt;
     return true;
@@ -706,6 +765,7 @@ EMC_HD void wind_bracket_reset(WindBracket &B)
 {
     B.lo = 1.0; B.hi = 0.0; B.x0 = 0.0;     /* empty interval: first use loads */
     B.f0[0] = B.f0[1] = B.f0[2] = 0.0; B.s[0] = B.s[1] = B.s[2] = 0.0;
+    B.j_cd = 1; B.j_cp = 1; B.j_th = 1;
 }
 
 /* motor.py:86-93 */
@@ -750,11 +810,14 @@ EMC_HD int rail_phase(const DevModel &M, const DevTables &Tb, const double *wind
         double speed = vx * dx + vy * dy + vz * dz;            /* :75 */
         const double rx = dx * speed - w[0], ry = dy * speed - w[1], rz = dz * speed - w[2];
         const double rel_speed = rx * dx + ry * dy + rz * dz;  /* :80 */
-        const double mach = sqrt((rx * rx + ry * ry + rz * rz) * (inv_RT * (1.0 / 1.4)));
-        double cd = interp_tab(Tb.cd_mach, Tb.cd0, Tb.cd0_s, M.n_cd, mach) * S.cd_scale
-                    + interp_tab(Tb.cd_mach, Tb.cda, Tb.cda_s, M.n_cd, mach) * 0.0;   /* alpha = 0, :82-83 */
+        const double mach = fast_sqrt((rx * rx + ry * ry + rz * rz) * (inv_RT * (1.0 / 1.4)));
+        const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, WB.j_cd, mach);
+        WB.j_cd = jd;
+        const double dm = mach - Tb.cd_x0[jd];
+        const double cd = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * S.cd_scale
+                          + fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]) * 0.0;                 /* alpha = 0, :82-83 */
         const double drag = 0.5 * rho * (rel_speed * rel_speed) * cd * M.ref_area;     /* :84 */
-        const double thrust = thrust_at(M, Tb, S, t, p);       /* :86 */
+        const double thrust = thrust_at(M, Tb, S, WB, t, p);   /* :86 */
         const double g = gravity(M, pz);
         const double accel = (thrust - mass * g - drag) / mass; /* :88 */
         speed += accel * dt;

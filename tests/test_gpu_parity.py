@@ -115,7 +115,9 @@ def test_gpu_vs_oracle_seeded_batch(engine, name, n):
     # a step count may differ only where an event test sits within rounding of its threshold
     same = np.all(iout == iref, axis=0)
     assert same.mean() >= 0.99, f"{(~same).sum()} of {n} samples differ in step count/termination"
-    util.assert_summary_close(*util.drop_nan_run_omega(out[:, same], ref[:, same], iref[:, same]), what=name)
+    sens = util.oracle_sensitivity(md, sc, wind)
+    assert np.mean(np.isinf(sens).any(axis=0)) < 0.02
+    util.assert_summary_close(*util.drop_nan_run_omega(out[:, same], ref[:, same], iref[:, same]), what=name, sens=sens[:, same])
 
 
 def test_gpu_full_size_properties(engine):
@@ -149,7 +151,9 @@ def test_gpu_full_size_properties(engine):
     ref, iref = O.batch(md, sc[:, pick].copy(), wind[pick].copy())
     same = np.all(iout[:, pick] == iref, axis=0)
     assert same.mean() >= 0.99
-    util.assert_summary_close(*util.drop_nan_run_omega(out[:, pick][:, same], ref[:, same], iref[:, same]), what="100k spot check")
+    sens = util.oracle_sensitivity(md, sc[:, pick].copy(), wind[pick].copy())
+    util.assert_summary_close(*util.drop_nan_run_omega(out[:, pick][:, same], ref[:, same], iref[:, same]), what="100k spot check",
+                              sens=sens[:, same])
 
 
 def test_gpu_edge_cases(engine):
@@ -190,3 +194,28 @@ def test_gpu_errors(engine):
     e2.close()
     with pytest.raises(_lib.EmcError, match="out of range"):
         _lib.Engine(99)
+
+
+def test_gpu_math_helpers(engine):
+    """The derivative kernel's reciprocal / rsqrt / sqrt (MUFU seed + Newton) and atan2 (minimax
+    polynomial): accuracy in ulp against NumPy over the operand ranges the path produces."""
+    rng = np.random.RandomState(0)
+    x = np.concatenate([10.0 ** rng.uniform(-8, 12, 200000), rng.uniform(100.0, 200.0, 50000), [1.0, 4.0, 6.371e6, 1e-300, 1e300]])
+
+    def ulps(got, ref):
+        return np.abs(got - ref) / np.spacing(np.abs(ref))
+    assert ulps(engine.math_debug(0, x), 1.0 / x).max() <= 1.5
+    assert ulps(engine.math_debug(1, x), 1.0 / np.sqrt(x)).max() <= 2.0
+    assert ulps(engine.math_debug(3, x), np.sqrt(x)).max() <= 2.0
+    assert engine.math_debug(3, np.array([0.0]))[0] == 0.0 and np.isnan(engine.math_debug(3, np.array([np.nan]))[0])
+    ang = rng.uniform(-np.pi, np.pi, 400000)
+    r = 10.0 ** rng.uniform(-6, 6, ang.size)
+    yy, xx = r * np.sin(ang), r * np.cos(ang)
+    yy[:1000] = rng.normal(0, 1e-9, 1000) * xx[:1000]                       # small angles
+    got, ref = engine.math_debug(2, xx, yy), np.arctan2(yy, xx)
+    assert ulps(got, ref).max() <= 2.5, ulps(got, ref).max()
+    sp_y = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, 1.0, -1.0, np.nan])
+    sp_x = np.array([1.0, 1.0, -1.0, -1.0, 0.0, 0.0, 0.0, 1.0, -1.0, 1.0])
+    got, ref = engine.math_debug(2, sp_x, sp_y), np.arctan2(sp_y, sp_x)
+    np.testing.assert_allclose(got, ref, rtol=3e-16, atol=0, equal_nan=True)
+    assert np.array_equal(np.signbit(got[:4]), np.signbit(ref[:4]))

@@ -58,12 +58,35 @@ def summary_errors(out, ref):
     return err
 
 
-def assert_summary_close(out, ref, rtol=RTOL, what=""):
+def assert_summary_close(out, ref, rtol=RTOL, what="", sens=None):
+    """Every field of every sample within rtol (scaled as in summary_errors).  `sens` (optional, from
+    oracle_sensitivity) widens the bar on ILL-CONDITIONED flights only: where a 1-ulp change of one input
+    moves the reference algorithm's own output by s > rtol/10, the bar for that field is 10*s."""
     err = summary_errors(out, ref)
-    worst = np.unravel_index(np.argmax(err), err.shape)
-    assert err[worst] <= rtol, (f"{what}: field {_abi.OUT_FIELDS[worst[0]]} sample {worst[1]}: "
-                                f"{out[worst]!r} vs {ref[worst]!r} (scaled err {err[worst]:.3e} > {rtol})")
+    tol = np.full(err.shape, rtol)
+    if sens is not None:
+        tol = np.maximum(tol, 10.0 * sens)
+    excess = np.where(err <= tol, 0.0, err / tol)
+    worst = np.unravel_index(np.argmax(excess), excess.shape)
+    assert excess[worst] == 0.0, (f"{what}: field {_abi.OUT_FIELDS[worst[0]]} sample {worst[1]}: "
+                                  f"{out[worst]!r} vs {ref[worst]!r} (scaled err {err[worst]:.3e} > {tol[worst]:.3e})")
     return float(err.max())
+
+
+def oracle_sensitivity(md, scalars, wind):
+    """Self-conditioning of the reference algorithm, measured with the C oracle: scaled change of every
+    output field when ONE input (dry mass) moves by one ulp.  Well-conditioned flights give ~1e-13 (SURVEY
+    App. C); the reference's super-exponentially diverging flights (F6/F7) give up to 1e-5 and beyond.
+    Samples whose step count itself flips get +inf (nothing can be asserted beyond the category)."""
+    import oracle_lib as O
+    sc1 = np.array(scalars, dtype=np.float64, copy=True)
+    i = _abi.IN["dry_mass"]
+    sc1[i] = np.nextafter(sc1[i], np.inf)
+    o0, i0 = O.batch(md, scalars, wind)
+    o1, i1 = O.batch(md, sc1, wind)
+    s = summary_errors(o1, o0)
+    s[:, np.any(i0 != i1, axis=0)] = np.inf
+    return s
 
 
 def hostseam_lib():
