@@ -95,40 +95,45 @@ __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
     const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
 
     for (;;) {
-        /* ---- retire/refill: ballot the idle lanes, one atomic per warp, ranks by popc ---- */
-        const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle != 0u && !drained) {
-            const int nidle = __popc(idle);
-            if (nidle >= thr) {
-                const int leader = __ffs(idle) - 1;
-                unsigned long long base = 0;
-                if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)nidle);
-                base = __shfl_sync(FULL, base, leader);
-                if (base + (unsigned long long)nidle >= (unsigned long long)a.n) drained = true;
-                if (!active) {
-                    const int64_t my = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
-                    if (my < a.n) {
-                        idx = my;
-                        load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
-                        double t_rail;
-                        load_flight_state(S, a.scalars + idx, a.ld, a.out + idx, a.old, s, t_rail);
-                        track_init(K, s, t_rail);
-                        wind_bracket_reset(WB);
-                        if (!(K.t < c_model.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
-                        if (a.tape && a.tape_cap > 0) {
-                            a.tape[0] = K.t;
-                            const double *sp = reinterpret_cast<const double *>(&s);
-                            for (int c = 0; c < 14; ++c) a.tape[1 + c] = sp[c];
+        /* ---- retire/refill: ONE ballot per iteration in the steady state; idle lanes are ranked with
+         * popc and fetch their sample indices with one atomic per warp ---- */
+        unsigned act = __ballot_sync(FULL, active);
+        if (act != FULL) {
+            if (!drained) {
+                const unsigned idle = ~act;
+                const int nidle = __popc(idle);
+                if (nidle >= thr) {
+                    const int leader = __ffs(idle) - 1;
+                    unsigned long long base = 0;
+                    if ((int)lane == leader) base = atomicAdd(a.queue, (unsigned long long)nidle);
+                    base = __shfl_sync(FULL, base, leader);
+                    if (base + (unsigned long long)nidle >= (unsigned long long)a.n) drained = true;
+                    if (!active) {
+                        const int64_t my = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
+                        if (my < a.n) {
+                            idx = my;
+                            load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
+                            double t_rail;
+                            load_flight_state(S, a.scalars + idx, a.ld, a.out + idx, a.old, s, t_rail);
+                            track_init(K, s, t_rail);
+                            wind_bracket_reset(WB);
+                            if (!(K.t < c_model.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
+                            if (a.tape && a.tape_cap > 0) {
+                                a.tape[0] = K.t;
+                                const double *sp = reinterpret_cast<const double *>(&s);
+                                for (int c = 0; c < 14; ++c) a.tape[1 + c] = sp[c];
+                            }
+                            active = true;
+                            ++n_refill;
                         }
-                        active = true;
-                        ++n_refill;
                     }
+                    act = __ballot_sync(FULL, active);
                 }
             }
-        }
-        if (__ballot_sync(FULL, active) == 0u) {
-            if (drained) break;
-            continue;
+            if (act == 0u) {
+                if (drained) break;
+                continue;
+            }
         }
         if (active) {
             bool stepped; int64_t rep = 0;
@@ -196,7 +201,9 @@ __global__ void emc_math_kernel(int op, int64_t n, const double *x, const double
     if (op == 0) r = fast_rcp(x[i]);
     else if (op == 1) r = fast_rsqrt(x[i]);
     else if (op == 2) r = fast_atan2(y[i], x[i]);
-    else r = fast_sqrt(x[i]);
+    else if (op == 3) r = fast_sqrt(x[i]);
+    else if (op == 4) r = fast_exp(x[i]);
+    else r = fast_log(x[i]);
     out[i] = r;
 }
 
@@ -548,7 +555,7 @@ EMC_EXPORT int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t 
 
 EMC_EXPORT int emc_math_debug(emc_ctx *ctx, int op, int64_t n, const double *x, const double *y, double *out)
 {
-    if (!ctx || !x || !out || n < 0 || op < 0 || op > 3 || (op == 2 && !y)) return fail(ctx, EMC_ERR_INVALID, "emc_math_debug: bad argument");
+    if (!ctx || !x || !out || n < 0 || op < 0 || op > 5 || (op == 2 && !y)) return fail(ctx, EMC_ERR_INVALID, "emc_math_debug: bad argument");
     if (n == 0) return EMC_OK;
     CK(cudaSetDevice(ctx->device));
     double *d = nullptr;

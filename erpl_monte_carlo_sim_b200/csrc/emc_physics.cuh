@@ -24,6 +24,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/emc.h"
 
@@ -108,8 +109,8 @@ struct Diag {
 EMC_HD double py_max(double a, double b) { return (b > a) ? b : a; }   /* Python max(a, b) */
 EMC_HD double py_min(double a, double b) { return (b < a) ? b : a; }   /* Python min(a, b) */
 /* running np.max / np.min over a series: NaN propagates and sticks */
-EMC_HD void np_max_acc(double &m, double v) { m = (v > m || v != v) ? ((m != m) ? m : v) : m; }
-EMC_HD void np_min_acc(double &m, double v) { m = (v < m || v != v) ? ((m != m) ? m : v) : m; }
+EMC_HD void np_max_acc(double &m, double v) { m = (v > m || v != v) ? v : m; }   /* a NaN m stays: both tests are False */
+EMC_HD void np_min_acc(double &m, double v) { m = (v < m || v != v) ? v : m; }
 
 /* ---------------- cheap reciprocal / reciprocal square root / atan2 ----------------
  * Device: MUFU seed + Newton steps in DFMA, no slow-path branches (operands here are positive, normal
@@ -151,7 +152,75 @@ EMC_HD double fast_rsqrt(double x)
 EMC_HD double fast_sqrt(double x)
 {
     const double r = x * fast_rsqrt(x);
-    return (x > 0.0) ? r : ((x == 0.0) ? 0.0 : NAN);
+    return (x > 0.0) ? ((x <= 1.7976931348623157e308) ? r : x) : ((x == 0.0) ? 0.0 : NAN);
+}
+
+EMC_HD long long d2ll(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(v);
+#else
+    long long b; memcpy(&b, &v, sizeof b); return b;
+#endif
+}
+EMC_HD double ll2d(long long b)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(b);
+#else
+    double v; memcpy(&v, &b, sizeof v); return v;
+#endif
+}
+
+/* exp(x) = 2^k * (1 + r + r^2 Q(r)), k = rint(x/ln2), |r| <= ln2/2; Q: degree-10 minimax
+ * (tools/fit_minimax.py exp 10, 6e-20).  Straight-line code: the atmosphere calls it once per
+ * derivative for every layer (environment.py:42-45,59-62,66-69,90). */
+EMC_HD double fast_exp(double x)
+{
+    const double magic = 6755399441055744.0;                    /* 1.5 * 2^52 */
+    const double kd = fma(x, 1.4426950408889634, magic) - magic;
+    double r = fma(kd, -0.6931471805599453, x);
+    r = fma(kd, -2.3190468138462996e-17, r);
+    const double r2 = r * r;
+    double qe = 2.0825635355315893e-09, qo = 2.5113226396698607e-08;
+    qe = fma(qe, r2, 2.755759237788011e-07);   qo = fma(qo, r2, 2.755723148198774e-06);
+    qe = fma(qe, r2, 2.4801586903844624e-05);  qo = fma(qo, r2, 0.0001984126989972697);
+    qe = fma(qe, r2, 0.001388888888913419);    qo = fma(qo, r2, 0.008333333333315703);
+    qe = fma(qe, r2, 0.04166666666666603);     qo = fma(qo, r2, 0.16666666666666685);
+    qe = fma(qe, r2, 0.5);
+    const double q = fma(qo, r, qe);
+    const double p = fma(r2, q, r) + 1.0;
+    const long long k = (long long)kd;
+    const double scale = ll2d((k + 1023) << 52);
+    const double y = p * scale;
+    return (x > 709.0) ? INFINITY : ((x < -708.0) ? 0.0 : y);   /* NaN falls through as NaN */
+}
+
+/* log(x) = k ln2 + 2 atanh(s), s = (m-1)/(m+1), m in [sqrt(1/2), sqrt(2)); atanh(s) = s + s w Q(w), w = s^2,
+ * Q: degree-6 minimax (tools/fit_minimax.py log 6, 1.4e-18).  Used for the two pow() layers of the
+ * atmosphere (environment.py:31-33,79-81) where x = T/T_base stays within [0.7, 1.4], i.e. k = 0. */
+EMC_HD double fast_log(double x)
+{
+    if (!(x >= 2.2250738585072014e-308 && x <= 1.7976931348623157e308)) return log(x);   /* 0, <0, denormal, inf, NaN */
+    const long long b = d2ll(x);
+    unsigned int hx = (unsigned int)(b >> 32);
+    hx += 0x3ff00000u - 0x3fe6a09eu;
+    const int k = (int)(hx >> 20) - 0x3ff;
+    hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+    const double m = ll2d(((long long)hx << 32) | (b & 0xffffffffLL));
+    const double f = m - 1.0;
+    const double s = f * fast_rcp(2.0 + f);
+    const double w = s * s;
+    double q = 0.07413327838146679;
+    q = fma(q, w, 0.0765556191960003);
+    q = fma(q, w, 0.09091836369173024);
+    q = fma(q, w, 0.11111098305913143);
+    q = fma(q, w, 0.1428571438008729);
+    q = fma(q, w, 0.19999999999670642);
+    q = fma(q, w, 0.3333333333333372);
+    const double at = fma(s * w, q, s);
+    const double kd = (double)k;
+    return fma(kd, 0.6931471805599453, fma(2.0, at, kd * 2.3190468138462996e-17));
 }
 
 /* atan2 with one division and a degree-18 minimax polynomial in t^2 (tools/fit_atan.py, relative error
@@ -177,9 +246,12 @@ EMC_HD double fast_atan2(double y, double x)
     pe = fma(pe, u2, -0.3333333333333186);
     const double q = fma(po, u, pe);
     double r = fma(t * u, q, t);
-    if (swap) r = (1.5707963267948966 - r) + 6.123233995736766e-17;
-    if (x < 0.0) r = (3.141592653589793 - r) + 1.2246467991473532e-16;
-    return (y < 0.0 || (y == 0.0 && signbit(y))) ? -r : r;
+    /* octant fix-ups as straight-line selects: r <- c_hi - r + c_lo */
+    const double r1 = (1.5707963267948966 - r) + 6.123233995736766e-17;
+    r = swap ? r1 : r;
+    const double r2 = (3.141592653589793 - r) + 1.2246467991473532e-16;
+    r = (x < 0.0) ? r2 : r;
+    return copysign(r, y);
 }
 
 /* remembered-bracket lookup: j stays valid while lo[j] <= x < hi[j]; NaN leaves j alone (the FMA that
@@ -216,9 +288,9 @@ EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, d
         base = 868.02; arg = 0.0;     /* filled below once 1/(R*T) is known */
     }
     inv_RT = fast_rcp(M.R_gas * T);
-    if (use_log) arg = le * log(lx);
+    if (use_log) arg = le * fast_log(lx);
     if (z > 32000.0 || z != z) arg = -(z - 32000.0) * (M.g0 * inv_RT);   /* -(z-32000)/(R*T/g) */
-    p = base * exp(arg);
+    p = base * fast_exp(arg);
 }
 
 /* environment.py:105-108 */
@@ -349,7 +421,8 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double vb2 = vxz2 + vby * vby;
     if (aero || want_diag) {
         /* Mach-table brackets (rocket.py:105-108,156-157): shared by Cd0/Cda, separate knots for CP */
-        const double mach = fast_sqrt(mach2);
+        double mach = fast_sqrt(mach2);
+        mach = (mach > 1e300) ? 1e300 : mach;     /* +inf clamps like np.interp (right value), NaN stays NaN */
         const int jc = brk_find(Tb.cp_lo, Tb.cp_hi, M.n_cp + 1, WB.j_cp, mach);
         WB.j_cp = jc;
         const double cp = M.cp_location + fma(Tb.cp_s[jc], mach - Tb.cp_x0[jc], Tb.cp_f[jc]);

@@ -200,7 +200,7 @@ int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t n, const do
 int emc_get_counters(const emc_ctx *ctx, emc_counters *c);
 
 /* Test seam: the engine's device math helpers on arrays.  op 0: 1/x, 1: 1/sqrt(x), 2: atan2(y, x),
- * 3: sqrt(x) (as used by the derivative kernel: MUFU seed + Newton / minimax polynomial). */
+ * 3: sqrt(x), 4: exp(x), 5: log(x) (as used by the derivative kernel: MUFU seed + Newton / minimax polynomials). */
 int emc_math_debug(emc_ctx *ctx, int op, int64_t n, const double *x, const double *y, double *out);
 
 /* Register-resident DFMA chain: measures this GPU's FP64 FMA peak (the roofline denominator). */

@@ -208,6 +208,16 @@ def test_gpu_math_helpers(engine):
     assert ulps(engine.math_debug(1, x), 1.0 / np.sqrt(x)).max() <= 2.0
     assert ulps(engine.math_debug(3, x), np.sqrt(x)).max() <= 2.0
     assert engine.math_debug(3, np.array([0.0]))[0] == 0.0 and np.isnan(engine.math_debug(3, np.array([np.nan]))[0])
+    xe = np.concatenate([rng.uniform(-20, 2, 300000), rng.uniform(-700, 700, 20000), [0.0, -0.0, 1e-300, -745.0, 710.0]])
+    got, ref = engine.math_debug(4, xe), np.exp(xe)
+    ok = (xe > -700) & (xe < 700)
+    assert ulps(got[ok], ref[ok]).max() <= 1.5
+    assert got[-2] == 0.0 and np.isinf(got[-1]) and np.isnan(engine.math_debug(4, np.array([np.nan]))[0])
+    xl = np.concatenate([rng.uniform(0.5, 2.0, 300000), 10.0 ** rng.uniform(-300, 300, 20000), [1.0, 0.75, 1.0551]])
+    got, ref = engine.math_debug(5, xl), np.log(xl)
+    err = np.abs(got - ref) / np.maximum(np.spacing(np.abs(ref)), 2.3e-17)         # near x = 1 log -> 0: absolute floor
+    assert err.max() <= 4.0, err.max()
+    assert got[-3] == 0.0 and np.isnan(engine.math_debug(5, np.array([-1.0]))[0]) and np.isinf(engine.math_debug(5, np.array([0.0]))[0])
     ang = rng.uniform(-np.pi, np.pi, 400000)
     r = 10.0 ** rng.uniform(-6, 6, ang.size)
     yy, xx = r * np.sin(ang), r * np.cos(ang)

@@ -53,8 +53,11 @@ def main():
         sc, w = tile(z, okp, 8192)
         run(eng, "D planar solid x8192", sc, w)
     if which == "ncu":
-        sc, w = tile(z, ok, 128)
-        run(eng, "ncu A x128", sc, w)
+        sc, w = tile(z, ok, 1024)
+        run(eng, "ncu A x1024", sc, w)
+    if which == "ncu3":
+        sc, w = tile(z, ok, 1024)
+        run(eng, "ncu A x1024 (128,3)", sc, w, block_threads=128, blocks_per_sm=3)
 
 if __name__ == "__main__":
     main()
