@@ -74,19 +74,23 @@ def assert_summary_close(out, ref, rtol=RTOL, what="", sens=None):
 
 
 def oracle_sensitivity(md, scalars, wind):
-    """Self-conditioning of the reference algorithm, measured with the C oracle: scaled change of every
-    output field when ONE input (dry mass) moves by one ulp.  Well-conditioned flights give ~1e-13 (SURVEY
-    App. C); the reference's super-exponentially diverging flights (F6/F7) give up to 1e-5 and beyond.
-    Samples whose step count itself flips get +inf (nothing can be asserted beyond the category)."""
+    """Self-conditioning of the reference algorithm, measured with the C oracle: the largest scaled change
+    of every output field when ONE input (dry mass, attitude q0, thrust) moves by one ulp.  Well-conditioned
+    flights give ~1e-13; the reference's super-exponentially diverging flights (F6/F7)
+    give up to 1e-5 and beyond.  Samples whose step count itself flips get +inf (nothing can be asserted
+    beyond the category)."""
     import oracle_lib as O
-    sc1 = np.array(scalars, dtype=np.float64, copy=True)
-    i = _abi.IN["dry_mass"]
-    sc1[i] = np.nextafter(sc1[i], np.inf)
     o0, i0 = O.batch(md, scalars, wind)
-    o1, i1 = O.batch(md, sc1, wind)
-    s = summary_errors(o1, o0)
-    s[:, np.any(i0 != i1, axis=0)] = np.inf
-    return s
+    worst = np.zeros_like(o0)
+    for field in ("dry_mass", "q0", "thrust_a"):
+        sc1 = np.array(scalars, dtype=np.float64, copy=True)
+        i = _abi.IN[field]
+        sc1[i] = np.nextafter(sc1[i], np.inf)
+        o1, i1 = O.batch(md, sc1, wind)
+        s = summary_errors(o1, o0)
+        s[:, np.any(i0 != i1, axis=0)] = np.inf
+        worst = np.maximum(worst, s)
+    return worst
 
 
 def hostseam_lib():
