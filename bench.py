@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--refill-threshold", type=int, default=0)
+    ap.add_argument("--cold-smem", type=int, default=0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     if a.impl == "reference":
@@ -160,7 +161,8 @@ def main():
     md, blk, wind, desc = make_workload(a.workload, n, rank * n)
     eng = _lib.Engine(local)
     eng.set_model(md)
-    opts = _lib.run_opts(refill_threshold=a.refill_threshold, block_threads=a.block_threads, blocks_per_sm=a.blocks_per_sm)
+    opts = _lib.run_opts(refill_threshold=a.refill_threshold, block_threads=a.block_threads, blocks_per_sm=a.blocks_per_sm,
+                         cold_state_in_smem=bool(a.cold_smem))
     peak_tf, _ = eng.fp64_peak()
 
     # ---- device-resident inputs/outputs (torch owns the HBM; the engine gets raw device pointers) ----
@@ -235,7 +237,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "samples_per_gpu": n, "global_batch": n_total, "seeds": "host-seeded numpy streams, seed = sample index",
                        "l2": "256 MB buffer written between timed iterations", "parallelism": f"sample-sharded x{world}",
-                       "launch": {"block_threads": a.block_threads, "blocks_per_sm": a.blocks_per_sm, "refill_threshold": a.refill_threshold}},
+                       "launch": {"block_threads": a.block_threads, "blocks_per_sm": a.blocks_per_sm, "refill_threshold": a.refill_threshold, "cold_smem": a.cold_smem}},
             "rk4_steps_per_s": steps_per_s, "mean_rk4_steps_per_trajectory": rk4_all / a.steps / n_total,
             "replayed_steps_per_trajectory": replay_all / a.steps / n_total,
             "kernel_ms_per_step": {"flight": flight_ms / a.steps, "rail": rail_ms / a.steps},

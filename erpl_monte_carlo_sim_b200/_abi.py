@@ -82,7 +82,7 @@ class EmcOutputs(C.Structure):
 
 class EmcRunOpts(C.Structure):
     _fields_ = [("refill_threshold", C.c_int32), ("block_threads", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("nan_fast_forward", C.c_int32)]
+                ("blocks_per_sm", C.c_int32), ("nan_fast_forward", C.c_int32), ("cold_state_in_smem", C.c_int32)]
 
 
 class EmcCounters(C.Structure):

@@ -57,6 +57,7 @@ __device__ __forceinline__ void stage_tables(double *smem, const KernelArgs &a)
 }
 
 static size_t smem_bytes(int n_wind) { return sizeof(DevTables) + sizeof(double) * (size_t)(n_wind > 0 ? n_wind : 0); }
+static size_t smem_bytes_cold(int n_wind, int block);
 
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) emc_rail_kernel(KernelArgs a)
@@ -78,7 +79,18 @@ __global__ void __launch_bounds__(128) emc_rail_kernel(KernelArgs a)
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-template <int BLOCK, int MINB>
+/* Per-lane state that is touched once per step or per derivative (event bookkeeping, sample constants,
+ * the remembered table brackets) can live in shared memory instead of registers (COLD = 1): the
+ * derivative then fits in fewer registers and more warps are resident to hide the FP64 latency.
+ * The structs are padded to an odd number of 8-byte words, so lane-strided access is conflict-free. */
+struct ColdLaneRaw { Track K; Sample S; WindBracket WB; };
+struct alignas(8) ColdLane {
+    Track K; Sample S; WindBracket WB;
+    double pad_[((sizeof(ColdLaneRaw) / 8) % 2 == 1) ? 2 : 1];
+};
+static_assert(sizeof(ColdLane) % 8 == 0 && (sizeof(ColdLane) / 8) % 2 == 1, "ColdLane must span an odd number of 8-byte words");
+
+template <int BLOCK, int MINB, int COLD>
 __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
 {
     extern __shared__ double smem[];
@@ -90,7 +102,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
 
     bool active = false, drained = false;
     int64_t idx = -1;
-    Sample S; State s; Track K; WindBracket WB;
+    State s;
+    ColdLane reg_lane;                     /* COLD = 0: plain registers */
+    ColdLane *cold = COLD ? reinterpret_cast<ColdLane *>(smem + sizeof(DevTables) / sizeof(double) + ((c_model.n_wind + 1) & ~1)) + threadIdx.x
+                          : &reg_lane;
+    Track &K = cold->K; Sample &S = cold->S; WindBracket &WB = cold->WB;
     unsigned long long n_steps = 0, n_replay = 0, n_refill = 0;
     const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
 
@@ -358,12 +374,21 @@ static int check_run_args(emc_ctx *ctx, const emc_inputs *in, int64_t n, const e
     return EMC_OK;
 }
 
-template <int BLOCK, int MINB>
+static size_t smem_bytes_cold(int n_wind, int block)
+{
+    const size_t words = sizeof(DevTables) / sizeof(double) + (size_t)(((n_wind > 0 ? n_wind : 0) + 1) & ~1);
+    return words * sizeof(double) + sizeof(ColdLane) * (size_t)block;
+}
+
+template <int BLOCK, int MINB, int COLD>
 static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
 {
-    auto kern = emc_flight_kernel<BLOCK, MINB>;
+    auto kern = emc_flight_kernel<BLOCK, MINB, COLD>;
+    if (COLD) smem = smem_bytes_cold(ctx->dmodel.n_wind, BLOCK);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     if (blocks_per_sm_req > 0 && blocks_per_sm_req < occ) occ = blocks_per_sm_req;
@@ -378,7 +403,7 @@ static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem,
 /* all pointers in `a` are device pointers */
 static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
 {
-    emc_run_opts o = { 0, 0, 0, 1 };
+    emc_run_opts o = { 0, 0, 0, 1, 0 };
     if (opts) o = *opts;
     a.refill_threshold = o.refill_threshold > 0 ? o.refill_threshold : 1;
     a.nan_ff = o.nan_fast_forward;
@@ -402,11 +427,12 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     const int bt = o.block_threads > 0 ? o.block_threads : 128;
     const int bps = o.blocks_per_sm;
     cudaError_t e;
-    if (bt == 64) e = launch_flight<64, 1>(ctx, a, smem, bps);
-    else if (bt == 256) e = launch_flight<256, 1>(ctx, a, smem, bps);
-    else if (bt == 128 && bps == 3) e = launch_flight<128, 3>(ctx, a, smem, bps);
-    else if (bt == 128 && bps >= 4) e = launch_flight<128, 4>(ctx, a, smem, bps);
-    else if (bt == 128) e = launch_flight<128, 1>(ctx, a, smem, bps);
+    const bool cold = o.cold_state_in_smem != 0;
+    if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
+    else if (bt == 256) e = launch_flight<256, 1, 0>(ctx, a, smem, bps);
+    else if (bt == 128 && bps == 3) e = cold ? launch_flight<128, 3, 1>(ctx, a, smem, bps) : launch_flight<128, 3, 0>(ctx, a, smem, bps);
+    else if (bt == 128 && bps >= 4) e = cold ? launch_flight<128, 4, 1>(ctx, a, smem, bps) : launch_flight<128, 4, 0>(ctx, a, smem, bps);
+    else if (bt == 128) e = cold ? launch_flight<128, 1, 1>(ctx, a, smem, bps) : launch_flight<128, 1, 0>(ctx, a, smem, bps);
     else return fail(ctx, EMC_ERR_INVALID, "block_threads must be 64, 128 or 256");
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("flight kernel launch: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
@@ -506,7 +532,7 @@ EMC_EXPORT int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_output
     if (int rc = upload_inputs(ctx, in, 1, a)) return rc;
     CK(grow(&ctx->d_tape, &ctx->cap_tape, (size_t)cap * EMC_TAPE_WIDTH));
     a.tape = ctx->d_tape; a.tape_cap = cap;
-    emc_run_opts o = { 1, 64, 1, 0 };       /* every state is integrated: no fast-forward on the tape path */
+    emc_run_opts o = { 1, 64, 1, 0, 0 };    /* every state is integrated: no fast-forward on the tape path */
     if (int rc = run_device(ctx, a, &o)) return rc;
     if (int rc = download_outputs(ctx, out, 1)) return rc;
     if (int rc = finish_counters(ctx)) return rc;

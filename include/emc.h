@@ -157,7 +157,8 @@ typedef struct emc_run_opts {
     int32_t refill_threshold; /* idle lanes per warp before the warp refills from the work queue; 0 = default */
     int32_t block_threads;    /* 0 = default */
     int32_t blocks_per_sm;    /* 0 = default */
-    int32_t nan_fast_forward; /* 1 (default when opts==NULL): replay t += dt only once the state is all-NaN */
+    int32_t nan_fast_forward; /* 1 (default when opts==NULL): replay t += dt only once the altitude is NaN for good */
+    int32_t cold_state_in_smem; /* 1: per-lane bookkeeping lives in shared memory (fewer registers, more resident warps) */
 } emc_run_opts;
 
 typedef struct emc_ctx emc_ctx;

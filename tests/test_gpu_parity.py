@@ -88,7 +88,8 @@ def test_gpu_scheduling_invariance(engine):
         np.testing.assert_array_equal(got[0], base[0], err_msg=str(kw))
         np.testing.assert_array_equal(got[1], base[1], err_msg=str(kw))
     for kw in (dict(block_threads=64), dict(block_threads=256), dict(block_threads=128, blocks_per_sm=3),
-               dict(block_threads=128, blocks_per_sm=4)):
+               dict(block_threads=128, blocks_per_sm=4), dict(block_threads=128, blocks_per_sm=3, cold_state_in_smem=True),
+               dict(block_threads=128, blocks_per_sm=4, cold_state_in_smem=True), dict(block_threads=128, cold_state_in_smem=True)):
         got = engine.run_batch(z["scalars"], z["wind"], opts=_lib.run_opts(**kw))
         np.testing.assert_array_equal(got[1], base[1], err_msg=str(kw))
         util.assert_summary_close(got[0], base[0], what=str(kw))
