@@ -138,7 +138,7 @@ def main():
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--refill-threshold", type=int, default=0)
-    ap.add_argument("--cold-smem", type=int, default=0)
+    ap.add_argument("--cold-smem", type=int, default=1)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     if a.impl == "reference":

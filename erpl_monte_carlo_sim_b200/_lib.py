@@ -83,13 +83,13 @@ def load():
     return L
 
 
-def run_opts(refill_threshold=0, block_threads=0, blocks_per_sm=0, nan_fast_forward=True, cold_state_in_smem=False):
+def run_opts(refill_threshold=0, block_threads=0, blocks_per_sm=0, nan_fast_forward=True, cold_state_in_smem=True):
     o = _abi.EmcRunOpts()
     o.refill_threshold = int(refill_threshold)
     o.block_threads = int(block_threads)
     o.blocks_per_sm = int(blocks_per_sm)
     o.nan_fast_forward = 1 if nan_fast_forward else 0
-    o.cold_state_in_smem = 1 if cold_state_in_smem else 0
+    o.cold_state_in_smem = 1 if cold_state_in_smem else -1
     return o
 
 

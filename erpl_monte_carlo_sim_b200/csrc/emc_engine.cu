@@ -424,10 +424,11 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    /* default launch: 128 threads, 3 blocks/SM (168 registers, 12 warps/SM), cold lane state in shared memory */
     const int bt = o.block_threads > 0 ? o.block_threads : 128;
-    const int bps = o.blocks_per_sm;
+    const int bps = (o.block_threads > 0 || o.blocks_per_sm > 0) ? o.blocks_per_sm : 3;
     cudaError_t e;
-    const bool cold = o.cold_state_in_smem != 0;
+    const bool cold = o.cold_state_in_smem >= 0;
     if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
     else if (bt == 256) e = launch_flight<256, 1, 0>(ctx, a, smem, bps);
     else if (bt == 128 && bps == 3) e = cold ? launch_flight<128, 3, 1>(ctx, a, smem, bps) : launch_flight<128, 3, 0>(ctx, a, smem, bps);

@@ -29,12 +29,37 @@
 #include "../../include/emc.h"
 
 #if defined(__CUDACC__)
-#define EMC_HD __host__ __device__ __forceinline__
+#define EMC_HD __device__ __forceinline__          /* libemc.so never runs the physics on the host */
+#define EMC_KDECL static __constant__ double       /* constant bank: used as instruction operands, no register */
 #else
 #define EMC_HD inline
+#define EMC_KDECL static const double
 #endif
 
 namespace emc {
+
+/* Minimax coefficients (tools/fit_minimax.py).  On the device they sit in the constant bank so that
+ * every DFMA reads its coefficient as an operand instead of materialising a 64-bit immediate with two
+ * moves (which cost 13 % of all issued instructions in the first version, profiles/). */
+EMC_KDECL K_ATAN[19] = {   /* atan(t) = t + t*u*Q(u), u = t^2 in [0,1]; degree 18, 2.8e-17 */
+    -0.3333333333333186, 0.19999999999755017, -0.14285714271334715, 0.11111110678746688, -0.0909090123535805,
+    0.07692212930161942, -0.0666586036040998, 0.058773077574447684, -0.05239232950492257, 0.04673949464358622,
+    -0.04092637904494918, 0.03406780544224133, -0.02582678957209261, 0.01697802875462528, -0.009184554046120928,
+    0.0038559722045492582, -0.0011640707910558462, 0.00022302218576995646, -2.025853092076122e-05 };
+EMC_KDECL K_EXP[11] = {    /* exp(r) = 1 + r + r^2 Q(r), |r| <= ln2/2; degree 10, 6e-20 */
+    0.5, 0.16666666666666685, 0.04166666666666603, 0.008333333333315703, 0.001388888888913419, 0.0001984126989972697,
+    2.4801586903844624e-05, 2.755723148198774e-06, 2.755759237788011e-07, 2.5113226396698607e-08, 2.0825635355315893e-09 };
+EMC_KDECL K_LOG[7] = {     /* atanh(s) = s + s*w*Q(w), w = s^2 <= 0.0295; degree 6, 1.4e-18 */
+    0.3333333333333372, 0.19999999999670642, 0.1428571438008729, 0.11111098305913143, 0.09091836369173024,
+    0.0765556191960003, 0.07413327838146679 };
+EMC_KDECL K_MISC[10] = {
+    1.5707963267948966, 6.123233995736766e-17,     /* 0,1: pi/2 hi, lo */
+    3.141592653589793, 1.2246467991473532e-16,     /* 2,3: pi hi, lo */
+    1.4426950408889634,                            /* 4: log2(e) */
+    0.6931471805599453, 2.3190468138462996e-17,    /* 5,6: ln2 hi, lo */
+    0.7142857142857143,                            /* 7: 1/1.4 (utils.py:154) */
+    6.371e6,                                       /* 8: earth radius (environment.py:107) */
+    1.7976931348623157e308 };                      /* 9: DBL_MAX */
 
 /* ------------------------------------------------------------------------------------------------
  * Run constants (device: __constant__ memory, so they are instruction operands, not registers)
@@ -178,16 +203,16 @@ EMC_HD double ll2d(long long b)
 EMC_HD double fast_exp(double x)
 {
     const double magic = 6755399441055744.0;                    /* 1.5 * 2^52 */
-    const double kd = fma(x, 1.4426950408889634, magic) - magic;
-    double r = fma(kd, -0.6931471805599453, x);
-    r = fma(kd, -2.3190468138462996e-17, r);
+    const double kd = fma(x, K_MISC[4], magic) - magic;
+    double r = fma(kd, -K_MISC[5], x);
+    r = fma(kd, -K_MISC[6], r);
     const double r2 = r * r;
-    double qe = 2.0825635355315893e-09, qo = 2.5113226396698607e-08;
-    qe = fma(qe, r2, 2.755759237788011e-07);   qo = fma(qo, r2, 2.755723148198774e-06);
-    qe = fma(qe, r2, 2.4801586903844624e-05);  qo = fma(qo, r2, 0.0001984126989972697);
-    qe = fma(qe, r2, 0.001388888888913419);    qo = fma(qo, r2, 0.008333333333315703);
-    qe = fma(qe, r2, 0.04166666666666603);     qo = fma(qo, r2, 0.16666666666666685);
-    qe = fma(qe, r2, 0.5);
+    double qe = K_EXP[10], qo = K_EXP[9];
+    qe = fma(qe, r2, K_EXP[8]);  qo = fma(qo, r2, K_EXP[7]);
+    qe = fma(qe, r2, K_EXP[6]);  qo = fma(qo, r2, K_EXP[5]);
+    qe = fma(qe, r2, K_EXP[4]);  qo = fma(qo, r2, K_EXP[3]);
+    qe = fma(qe, r2, K_EXP[2]);  qo = fma(qo, r2, K_EXP[1]);
+    qe = fma(qe, r2, K_EXP[0]);
     const double q = fma(qo, r, qe);
     const double p = fma(r2, q, r) + 1.0;
     const long long k = (long long)kd;
@@ -211,16 +236,16 @@ EMC_HD double fast_log(double x)
     const double f = m - 1.0;
     const double s = f * fast_rcp(2.0 + f);
     const double w = s * s;
-    double q = 0.07413327838146679;
-    q = fma(q, w, 0.0765556191960003);
-    q = fma(q, w, 0.09091836369173024);
-    q = fma(q, w, 0.11111098305913143);
-    q = fma(q, w, 0.1428571438008729);
-    q = fma(q, w, 0.19999999999670642);
-    q = fma(q, w, 0.3333333333333372);
+    double q = K_LOG[6];
+    q = fma(q, w, K_LOG[5]);
+    q = fma(q, w, K_LOG[4]);
+    q = fma(q, w, K_LOG[3]);
+    q = fma(q, w, K_LOG[2]);
+    q = fma(q, w, K_LOG[1]);
+    q = fma(q, w, K_LOG[0]);
     const double at = fma(s * w, q, s);
     const double kd = (double)k;
-    return fma(kd, 0.6931471805599453, fma(2.0, at, kd * 2.3190468138462996e-17));
+    return fma(kd, K_MISC[5], fma(2.0, at, kd * K_MISC[6]));
 }
 
 /* atan2 with one division and a degree-18 minimax polynomial in t^2 (tools/fit_atan.py, relative error
@@ -234,22 +259,22 @@ EMC_HD double fast_atan2(double y, double x)
     t = (den > 0.0) ? t : ((den == 0.0) ? 0.0 : t);      /* atan2(0, 0) = 0; NaN stays NaN */
     const double u = t * t, u2 = u * u;
     /* two interleaved Horner chains (even / odd coefficients) for instruction-level parallelism */
-    double pe = -2.025853092076122e-05, po = 0.00022302218576995646;
-    pe = fma(pe, u2, -0.0011640707910558462);  po = fma(po, u2, 0.0038559722045492582);
-    pe = fma(pe, u2, -0.009184554046120928);   po = fma(po, u2, 0.01697802875462528);
-    pe = fma(pe, u2, -0.02582678957209261);    po = fma(po, u2, 0.03406780544224133);
-    pe = fma(pe, u2, -0.04092637904494918);    po = fma(po, u2, 0.04673949464358622);
-    pe = fma(pe, u2, -0.05239232950492257);    po = fma(po, u2, 0.058773077574447684);
-    pe = fma(pe, u2, -0.0666586036040998);     po = fma(po, u2, 0.07692212930161942);
-    pe = fma(pe, u2, -0.0909090123535805);     po = fma(po, u2, 0.11111110678746688);
-    pe = fma(pe, u2, -0.14285714271334715);    po = fma(po, u2, 0.19999999999755017);
-    pe = fma(pe, u2, -0.3333333333333186);
+    double pe = K_ATAN[18], po = K_ATAN[17];
+    pe = fma(pe, u2, K_ATAN[16]);  po = fma(po, u2, K_ATAN[15]);
+    pe = fma(pe, u2, K_ATAN[14]);  po = fma(po, u2, K_ATAN[13]);
+    pe = fma(pe, u2, K_ATAN[12]);  po = fma(po, u2, K_ATAN[11]);
+    pe = fma(pe, u2, K_ATAN[10]);  po = fma(po, u2, K_ATAN[9]);
+    pe = fma(pe, u2, K_ATAN[8]);   po = fma(po, u2, K_ATAN[7]);
+    pe = fma(pe, u2, K_ATAN[6]);   po = fma(po, u2, K_ATAN[5]);
+    pe = fma(pe, u2, K_ATAN[4]);   po = fma(po, u2, K_ATAN[3]);
+    pe = fma(pe, u2, K_ATAN[2]);   po = fma(po, u2, K_ATAN[1]);
+    pe = fma(pe, u2, K_ATAN[0]);
     const double q = fma(po, u, pe);
     double r = fma(t * u, q, t);
     /* octant fix-ups as straight-line selects: r <- c_hi - r + c_lo */
-    const double r1 = (1.5707963267948966 - r) + 6.123233995736766e-17;
+    const double r1 = (K_MISC[0] - r) + K_MISC[1];
     r = swap ? r1 : r;
-    const double r2 = (3.141592653589793 - r) + 1.2246467991473532e-16;
+    const double r2 = (K_MISC[2] - r) + K_MISC[3];
     r = (x < 0.0) ? r2 : r;
     return copysign(r, y);
 }
@@ -296,7 +321,7 @@ EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, d
 /* environment.py:105-108 */
 EMC_HD double gravity(const DevModel &M, double z)
 {
-    const double Re = 6.371e6;
+    const double Re = K_MISC[8];
     const double r = Re * fast_rcp(Re + z);
     return M.g0 * (r * r);
 }
@@ -405,7 +430,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double vby = r01 * ux + r11 * uy + r21 * uz;
     const double vbz = r02 * ux + r12 * uy + r22 * uz;
     const double v2 = ux * ux + uy * uy + uz * uz;
-    const double mach2 = v2 * (inv_RT * (1.0 / 1.4));       /* (|v|/sqrt(1.4*R*T))^2, utils.py:152-157 */
+    const double mach2 = v2 * (inv_RT * K_MISC[7]);         /* (|v|/sqrt(1.4*R*T))^2, utils.py:152-157 */
     const double qdyn = 0.5 * rho * v2;
 
     /* :359-363 thrust along body x */

@@ -155,10 +155,10 @@ typedef struct emc_outputs {
 
 typedef struct emc_run_opts {
     int32_t refill_threshold; /* idle lanes per warp before the warp refills from the work queue; 0 = default */
-    int32_t block_threads;    /* 0 = default */
-    int32_t blocks_per_sm;    /* 0 = default */
+    int32_t block_threads;    /* 0 = default (128) */
+    int32_t blocks_per_sm;    /* 0 = default (3 when block_threads is 0, else the occupancy limit) */
     int32_t nan_fast_forward; /* 1 (default when opts==NULL): replay t += dt only once the altitude is NaN for good */
-    int32_t cold_state_in_smem; /* 1: per-lane bookkeeping lives in shared memory (fewer registers, more resident warps) */
+    int32_t cold_state_in_smem; /* >= 0 (default): per-lane bookkeeping lives in shared memory (fewer registers, more resident warps); -1: registers */
 } emc_run_opts;
 
 typedef struct emc_ctx emc_ctx;
