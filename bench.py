@@ -26,6 +26,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+STATS_LAUNCHES = 4 + 2 + 3 * 6     # moments1 (+3 finish), moments2 (+1 finish), 3 metrics x 6 radix-select passes
 FLOP_PER_STEP = 1600.0          # 4*348 + 203 ~ 1.6 kflop per accepted RK4 step
 CSV_ALT = np.array([0.0, 5000.0, 10000.0, 15000.0, 20000.0, 25000.0])                # sample_wind.csv:2-7
 CSV_WIND = np.array([[2.0, 0, 0], [5, 1, 0], [8, 2, 0], [10, 2, 0], [12, 3, 0], [15, 3, 0]], float)
@@ -146,7 +147,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from erpl_monte_carlo_sim_b200 import _abi, _lib
+    from erpl_monte_carlo_sim_b200 import _abi, _lib, stats as emc_stats
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -170,7 +171,7 @@ def main():
     d_out = torch.empty((_abi.OUT_COUNT, n), dtype=torch.float64, device=dev)
     d_iout = torch.empty((_abi.IOUT_COUNT, n), dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    stats = torch.zeros(8, dtype=torch.float64, device=dev)
+    last_stats = [None]
     torch.cuda.synchronize()
 
     def barrier():
@@ -184,9 +185,9 @@ def main():
         eng.run_batch_device(d_blk.data_ptr(), n, d_wind.data_ptr(), wind.shape[1] * 3, d_out.data_ptr(),
                              d_iout.data_ptr(), n, n, opts)
         c = eng.counters()
-        if world > 1:       # the one collective of the path: all-reduce of the per-rank statistics block
-            stats[0] = float(n); stats[1] = float(c["rk4_steps"]); stats[2] = float(c["replay_steps"])
-            dist.all_reduce(stats)
+        # statistics of the batch reduced on the device; for N > 1 the small result blocks are all-reduced over NCCL
+        # between the passes (the only collective of the path)
+        last_stats[0] = emc_stats.device_statistics(eng, n, out_dev=d_out.data_ptr(), ld=n, distributed=(world > 1))
         return c
 
     for _ in range(a.warmup):
@@ -247,8 +248,9 @@ def main():
                                  "peak = in-run DFMA-chain microbenchmark (emc_fp64_peak), per GPU x n_gpus"},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
                     "h2d_bytes_per_step": int(blk.nbytes + wind.nbytes), "d2h_bytes_per_step": int(h_out.nbytes + h_iout.nbytes)},
-            "gpu_launches": 2 * a.steps * world,
+            "gpu_launches": (2 + STATS_LAUNCHES) * a.steps * world,
             "clocks": sampler.summary(),
+            "statistics": {k: last_stats[0][k] for k in ("n_total", "n_samples", "n_outliers", "apogee_altitude", "range", "flight_time", "landing_ellipse")},
             "e2e_equals_resident": parity_hint,
         }
         if not a.no_cpu_baseline:

@@ -74,6 +74,18 @@ def load():
     L.emc_fp64_peak.argtypes = [vp, _dp, _dp]
     L.emc_math_debug.argtypes = [vp, C.c_int, i64, _dp, _dp, _dp]
     L.emc_math_debug.restype = C.c_int
+    L.emc_scratch.argtypes = [vp, i64, C.POINTER(vp)]
+    L.emc_copy_to_host.argtypes = [vp, vp, vp, i64]
+    L.emc_copy_to_device.argtypes = [vp, vp, vp, i64]
+    L.emc_stats_moments1.argtypes = [vp, vp, i64, i64, vp, vp, vp]
+    L.emc_stats_moments2.argtypes = [vp, vp, i64, i64, vp, vp]
+    L.emc_stats_select_hist.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int, vp]
+    L.emc_stats_linear_hist.argtypes = [vp, vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_int, vp]
+    L.emc_upload_outputs.argtypes = [vp, vp, i64, i64]
+    L.emc_upload_outputs.restype = C.c_int
+    for name in ("emc_scratch", "emc_copy_to_host", "emc_copy_to_device", "emc_stats_moments1", "emc_stats_moments2",
+                 "emc_stats_select_hist", "emc_stats_linear_hist"):
+        getattr(L, name).restype = C.c_int
     for name in ("emc_create", "emc_destroy", "emc_set_model", "emc_run_batch", "emc_run_batch_device",
                  "emc_run_tape", "emc_derivative_debug", "emc_get_counters", "emc_fp64_peak"):
         getattr(L, name).restype = C.c_int
@@ -216,6 +228,11 @@ class Engine:
                                              yy.ctypes.data_as(_dp) if yy is not None else None,
                                              out.ctypes.data_as(_dp)), "emc_math_debug")
         return out
+
+    def upload_outputs(self, out):
+        out = np.ascontiguousarray(out, np.float64)
+        assert out.shape[0] == _abi.OUT_COUNT
+        self._check(self._lib.emc_upload_outputs(self._ctx, out.ctypes.data, out.shape[1], out.shape[1]), "emc_upload_outputs")
 
     def counters(self) -> dict:
         c = _abi.EmcCounters()

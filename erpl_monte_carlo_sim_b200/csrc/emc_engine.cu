@@ -24,6 +24,7 @@
 #include <string>
 
 #include "emc_model_build.h"
+#include "emc_stats.cuh"
 
 using namespace emc;
 
@@ -257,6 +258,9 @@ struct emc_ctx {
     double *d_out = nullptr; size_t cap_out = 0;
     int32_t *d_iout = nullptr; size_t cap_iout = 0;
     double *d_tape = nullptr; size_t cap_tape = 0;
+    unsigned char *d_scratch = nullptr; size_t cap_scratch = 0;
+    double *d_partial = nullptr; size_t cap_partial = 0;
+    int64_t last_n = 0;                       /* samples held by d_out/d_iout after the last host-buffer run */
     emc_counters counters;
     std::string err;
 };
@@ -322,7 +326,7 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
-    cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -519,6 +523,7 @@ EMC_EXPORT int emc_run_batch(emc_ctx *ctx, const emc_inputs *in, int64_t n, cons
     if (int rc = upload_inputs(ctx, in, n, a)) return rc;
     if (int rc = run_device(ctx, a, opts)) return rc;
     if (int rc = download_outputs(ctx, out, n)) return rc;
+    ctx->last_n = n;
     return finish_counters(ctx);
 }
 
@@ -577,6 +582,134 @@ EMC_EXPORT int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_t); cudaFree(d_s); cudaFree(d_k); cudaFree(d_c);
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("emc_derivative_debug: ") + cudaGetErrorString(e));
+    return EMC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ *  device statistics
+ * ------------------------------------------------------------------------------------------------- */
+EMC_EXPORT int emc_scratch(emc_ctx *ctx, int64_t bytes, void **dev_ptr)
+{
+    if (!ctx || !dev_ptr || bytes < 0) return fail(ctx, EMC_ERR_INVALID, "emc_scratch: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(grow(&ctx->d_scratch, &ctx->cap_scratch, (size_t)bytes));
+    *dev_ptr = ctx->d_scratch;
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_copy_to_host(emc_ctx *ctx, void *host, const void *dev, int64_t bytes)
+{
+    if (!ctx || !host || !dev || bytes < 0) return fail(ctx, EMC_ERR_INVALID, "emc_copy_to_host: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(host, dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_copy_to_device(emc_ctx *ctx, void *dev, const void *host, int64_t bytes)
+{
+    if (!ctx || !host || !dev || bytes < 0) return fail(ctx, EMC_ERR_INVALID, "emc_copy_to_device: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_upload_outputs(emc_ctx *ctx, const double *out_host, int64_t ld, int64_t n)
+{
+    if (!ctx || !out_host || n < 0 || ld < n) return fail(ctx, EMC_ERR_INVALID, "emc_upload_outputs: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(grow(&ctx->d_out, &ctx->cap_out, (size_t)EMC_OUT_COUNT * (size_t)(n > 0 ? n : 1)));
+    if (n > 0)
+        CK(cudaMemcpy2DAsync(ctx->d_out, sizeof(double) * n, out_host, sizeof(double) * ld, sizeof(double) * n, EMC_OUT_COUNT,
+                             cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->last_n = n;
+    return EMC_OK;
+}
+
+static int stats_source(emc_ctx *ctx, const double *&out_dev, int64_t &ld, int64_t n)
+{
+    if (!ctx || n < 0) return fail(ctx, EMC_ERR_INVALID, "emc_stats: bad argument");
+    if (!out_dev) {
+        if (!ctx->d_out || ctx->last_n < n || ctx->last_n == 0) return fail(ctx, EMC_ERR_INVALID, "emc_stats: no resident outputs of a previous emc_run_batch");
+        out_dev = ctx->d_out; ld = ctx->last_n;
+    }
+    if (ld < n) return fail(ctx, EMC_ERR_INVALID, "emc_stats: ld < n");
+    return EMC_OK;
+}
+
+static int stats_grid(emc_ctx *ctx, int64_t n)
+{
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)ctx->sm_count * 4;
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+
+EMC_EXPORT int emc_stats_moments1(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, double *sum_dev,
+                                  double *min_dev, double *max_dev)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!sum_dev || !min_dev || !max_dev) return fail(ctx, EMC_ERR_INVALID, "emc_stats_moments1: NULL result block");
+    CK(cudaSetDevice(ctx->device));
+    const int g = stats_grid(ctx, n);
+    const size_t need = (size_t)g * (ST_SUM_COUNT + 2 * ST_MM_COUNT);
+    CK(grow(&ctx->d_partial, &ctx->cap_partial, need));
+    double *ps = ctx->d_partial, *pmin = ps + (size_t)g * ST_SUM_COUNT, *pmax = pmin + (size_t)g * ST_MM_COUNT;
+    emc_stats_moments1_kernel<<<g, 256, 0, ctx->stream>>>(out_dev, ld, n, ps, pmin, pmax);
+    emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(ps, g, ST_SUM_COUNT, 0, sum_dev);
+    emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(pmin, g, ST_MM_COUNT, 1, min_dev);
+    emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(pmax, g, ST_MM_COUNT, 2, max_dev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_stats_moments2(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *center_dev,
+                                  double *sum_dev)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!center_dev || !sum_dev) return fail(ctx, EMC_ERR_INVALID, "emc_stats_moments2: NULL block");
+    CK(cudaSetDevice(ctx->device));
+    const int g = stats_grid(ctx, n);
+    CK(grow(&ctx->d_partial, &ctx->cap_partial, (size_t)g * ST2_COUNT));
+    emc_stats_moments2_kernel<<<g, 256, 0, ctx->stream>>>(out_dev, ld, n, center_dev, ctx->d_partial);
+    emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, g, ST2_COUNT, 0, sum_dev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_stats_select_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, int shift,
+                                     int prefix_shift, const uint64_t *prefixes, int n_prefix, uint64_t *hist_dev)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!hist_dev || !prefixes || n_prefix < 1 || n_prefix > EMC_SELECT_MAX_PREFIX || field < 0 || field > 2 || shift < 0 || shift > 63)
+        return fail(ctx, EMC_ERR_INVALID, "emc_stats_select_hist: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    SelectArgs a;
+    memset(&a, 0, sizeof a);
+    for (int u = 0; u < n_prefix; ++u) a.prefix[u] = prefixes[u];
+    a.n_prefix = n_prefix; a.field = field; a.shift = shift; a.prefix_shift = prefix_shift;
+    CK(cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * (size_t)n_prefix * EMC_SELECT_BINS, ctx->stream));
+    emc_stats_select_kernel<<<stats_grid(ctx, n), 256, 0, ctx->stream>>>(out_dev, ld, n, a, reinterpret_cast<unsigned long long *>(hist_dev));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, double lo, double hi,
+                                     int nbins, uint64_t *hist_dev)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!hist_dev || nbins < 1 || field < 0 || field > 4) return fail(ctx, EMC_ERR_INVALID, "emc_stats_linear_hist: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * (size_t)nbins, ctx->stream));
+    emc_stats_linear_hist_kernel<<<stats_grid(ctx, n), 256, 0, ctx->stream>>>(out_dev, ld, n, field, lo, hi, nbins,
+                                                                             reinterpret_cast<unsigned long long *>(hist_dev));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
     return EMC_OK;
 }
 

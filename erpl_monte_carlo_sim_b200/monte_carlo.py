@@ -18,7 +18,7 @@ from collections.abc import Sequence
 
 import numpy as np
 
-from . import _abi, marshal
+from . import _abi, marshal, stats
 from .motor import LiquidMotor, SolidMotor, is_solid
 from .simulator import FlightSimulator, get_engine, summary_extras
 
@@ -93,9 +93,10 @@ class SampleResults(Sequence):
 class BatchRun:
     """Everything one Monte Carlo batch produced: dispersions, inputs summary and the SoA outputs."""
 
-    def __init__(self, analyzer, base_ic, disp, out, iout, altitude_profile, scalars):
+    def __init__(self, analyzer, base_ic, disp, out, iout, altitude_profile, scalars, outputs_resident=False):
         self.analyzer, self.base_ic, self.disp = analyzer, base_ic, disp
         self.out, self.iout, self.altitude_profile, self.scalars = out, iout, altitude_profile, scalars
+        self.outputs_resident = outputs_resident      # the engine still holds these outputs in HBM (single chunk)
 
     def sample_result(self, i):
         O = _abi.OUT
@@ -143,6 +144,7 @@ class MonteCarloAnalyzer:
         self.device = device
         self.chunk_size = 1 << 16
         self.run_opts = None
+        self.histogram_bins = 0
         self.last_run = None
 
     # ------------------------------------------------------------------------------------------
@@ -285,7 +287,7 @@ class MonteCarloAnalyzer:
             blk, wind, _ = self.build_inputs(initial_conditions, disp.slice(lo, hi))
             o, io = eng.run_batch(blk, wind, opts=self.run_opts)
             out[:, lo:hi] = o; iout[:, lo:hi] = io; scal[:, lo:hi] = blk
-        self.last_run = BatchRun(self, dict(initial_conditions), disp, out, iout, alts, scal)
+        self.last_run = BatchRun(self, dict(initial_conditions), disp, out, iout, alts, scal, outputs_resident=(n <= self.chunk_size))
         return self.last_run
 
     def run_monte_carlo(self, initial_conditions, n_samples=1000, n_processes=None, optimized=False):
@@ -407,15 +409,20 @@ class MonteCarloAnalyzer:
                 "parameter_ranges_observed": ranges}
 
     def _analyze_run(self, run: BatchRun):
+        """Statistics of a batch: outlier classification, moments, landing ellipse and exact percentiles are reduced
+        on the GPU (stats.device_statistics; NCCL all-reduce between the passes in a multi-GPU job)."""
         O = _abi.OUT
-        ap, rg, ft = run.out[O["apogee_altitude"]], run.out[O["range"]], run.out[O["flight_time"]]
-        bad = self.outlier_mask(ap, rg, ft)
-        valid_ids = np.flatnonzero(~bad)
-        out_ids = np.flatnonzero(bad)
         if run.disp.n == 0:
             raise ValueError("No valid simulation results")
-        if valid_ids.size == 0:
+        eng = get_engine(self.device)
+        if not run.outputs_resident:
+            eng.upload_outputs(run.out)
+        st = stats.device_statistics(eng, run.disp.n, histogram_bins=self.histogram_bins)
+        if st["n_samples"] == 0:
             raise ValueError("No physically reasonable simulation results after outlier filtering")
+        ap, rg, ft = run.out[O["apogee_altitude"]], run.out[O["range"]], run.out[O["flight_time"]]
+        bad = self.outlier_mask(ap, rg, ft)                       # per-sample membership for the lazy result lists
+        valid_ids, out_ids = np.flatnonzero(~bad), np.flatnonzero(bad)
         d = run.disp
         ranges = {}
         for key, arr in (("initial_position_offset", d.pos), ("initial_velocity_offset", d.vel),
@@ -426,9 +433,12 @@ class MonteCarloAnalyzer:
             sel = arr[valid_ids]
             ranges[key] = {"min": sel.min(axis=0).tolist(), "max": sel.max(axis=0).tolist()}
         reasons = [self._outlier_reasons(ap[i], rg[i], ft[i]) for i in out_ids] if out_ids.size <= 100000 else None
-        v_ap, v_rg, v_ft = ap[valid_ids], rg[valid_ids], ft[valid_ids]
-        return {"n_samples": int(valid_ids.size), "n_failed": 0, "n_outliers": int(out_ids.size),
-                "apogee_altitude": self.calc_stats(v_ap[np.isfinite(v_ap)]), "range": self.calc_stats(v_rg[np.isfinite(v_rg)]),
-                "flight_time": self.calc_stats(v_ft[np.isfinite(v_ft)]),
-                "results": SampleResults(run, valid_ids), "outliers": SampleResults(run, out_ids, reasons),
-                "parameter_ranges_observed": ranges}
+        analysis = {"n_samples": st["n_samples"], "n_failed": 0, "n_outliers": st["n_outliers"],
+                    "apogee_altitude": st["apogee_altitude"], "range": st["range"], "flight_time": st["flight_time"],
+                    "results": SampleResults(run, valid_ids), "outliers": SampleResults(run, out_ids, reasons),
+                    "parameter_ranges_observed": ranges,
+                    # engine extras (not in the reference's dict): device-reduced landing ellipse, reasons, histograms
+                    "landing_ellipse": st["landing_ellipse"], "outlier_reason_counts": st["outlier_reasons"]}
+        if "histograms" in st:
+            analysis["histograms"] = st["histograms"]
+        return analysis

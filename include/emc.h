@@ -200,6 +200,42 @@ int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t n, const do
 
 int emc_get_counters(const emc_ctx *ctx, emc_counters *c);
 
+/* ---- device-side Monte Carlo statistics (reference monte_carlo.py:337-473) --------------------------------
+ * All buffers below are DEVICE pointers (HBM).  `out_dev` is a field-major [EMC_OUT_COUNT][ld] block; NULL means
+ * "the outputs of this context's last emc_run_batch, still resident".  The SUM/MIN/MAX blocks are what a
+ * multi-GPU job all-reduces (NCCL) between the passes; see erpl_monte_carlo_sim_b200/stats.py. */
+enum { EMC_ST_N = 0, EMC_ST_VALID, EMC_ST_OUTLIER, EMC_ST_NONFINITE, EMC_ST_AP_HIGH, EMC_ST_AP_LOW, EMC_ST_RANGE,
+       EMC_ST_TIME, EMC_ST_ENERGY, EMC_ST_SUM_AP, EMC_ST_SUM_RG, EMC_ST_SUM_FT, EMC_ST_SUM_X, EMC_ST_SUM_Y, EMC_ST_SUM_COUNT };
+#define EMC_ST_MM_COUNT 3     /* apogee, range, flight_time */
+#define EMC_ST2_COUNT 6       /* centred: apogee^2, range^2, time^2, xx, xy, yy (landing ellipse) */
+#define EMC_SELECT_BINS 2048
+#define EMC_SELECT_MAX_PREFIX 16
+
+/* context-owned device scratch (valid until the next emc_scratch call with a larger size or emc_destroy) */
+int emc_scratch(emc_ctx *ctx, int64_t bytes, void **dev_ptr);
+int emc_copy_to_host(emc_ctx *ctx, void *host, const void *dev, int64_t bytes);
+int emc_copy_to_device(emc_ctx *ctx, void *dev, const void *host, int64_t bytes);
+
+/* make a host [EMC_OUT_COUNT][ld] block the context's resident outputs (for statistics over a run that was
+ * executed in several chunks) */
+int emc_upload_outputs(emc_ctx *ctx, const double *out_host, int64_t ld, int64_t n);
+
+/* outlier classification (monte_carlo.py:348-390) + counts, sums, min, max over the valid samples */
+int emc_stats_moments1(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n,
+                       double *sum_dev /*[EMC_ST_SUM_COUNT]*/, double *min_dev /*[3]*/, double *max_dev /*[3]*/);
+/* centred second moments about center_dev[5] = mean apogee, range, flight_time, landing x, y (np.std two-pass) */
+int emc_stats_moments2(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *center_dev,
+                       double *sum_dev /*[EMC_ST2_COUNT]*/);
+/* one digit pass of the exact radix select behind np.percentile: field 0 apogee, 1 range, 2 flight_time;
+ * hist_dev[u][digit] += 1 for every valid sample whose key >> prefix_shift == prefixes[u] (prefix_shift 64: all) */
+int emc_stats_select_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, int shift,
+                          int prefix_shift, const uint64_t *prefixes /*host, [n_prefix]*/, int n_prefix,
+                          uint64_t *hist_dev /*[n_prefix][EMC_SELECT_BINS], zeroed by the call*/);
+
+/* fixed-bin histogram over the valid samples; field 0 apogee, 1 range, 2 flight_time, 3 landing x, 4 landing y */
+int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, double lo, double hi,
+                          int nbins, uint64_t *hist_dev /*[nbins], zeroed by the call*/);
+
 /* Test seam: the engine's device math helpers on arrays.  op 0: 1/x, 1: 1/sqrt(x), 2: atan2(y, x),
  * 3: sqrt(x), 4: exp(x), 5: log(x) (as used by the derivative kernel: MUFU seed + Newton / minimax polynomials). */
 int emc_math_debug(emc_ctx *ctx, int op, int64_t n, const double *x, const double *y, double *out);

@@ -136,3 +136,34 @@ def test_monte_carlo_optimized_path():
     an = mc.run_monte_carlo({"attitude": VERTICAL}, n_samples=96, optimized=True)
     assert "performance" in an and an["performance"]["simulations_per_second"] > 0
     assert an["n_samples"] + an["n_outliers"] == 96
+
+
+def test_device_statistics_match_numpy_backend():
+    """csrc/emc_stats.cuh against the NumPy stand-in on the same per-sample outputs (incl. injected outliers)."""
+    from erpl_monte_carlo_sim_b200 import stats as S
+    from erpl_monte_carlo_sim_b200.simulator import get_engine
+    from stats_numpy_backend import NumpyBackend
+    rng = np.random.RandomState(5)
+    n = 20011
+    out = np.zeros((_abi.OUT_COUNT, n))
+    O = _abi.OUT
+    out[O["apogee_altitude"]] = rng.normal(26000, 2500, n); out[O["range"]] = np.abs(rng.normal(5000, 1500, n))
+    out[O["flight_time"]] = rng.normal(205, 9, n); out[O["final_x"]] = rng.normal(4000, 1200, n); out[O["final_y"]] = rng.normal(0, 800, n)
+    out[O["apogee_altitude"], ::17] = rng.choice([np.nan, 4e8, 50.0, 90000.0, -np.inf], out[O["apogee_altitude"], ::17].size)
+    out[O["range"], 5::91] = 3e5; out[O["flight_time"], 7::113] = 900.0
+    eng = get_engine(0)
+    eng.upload_outputs(out)
+    got = S.device_statistics(eng, n, histogram_bins=24)
+    ref = S.compute_statistics(NumpyBackend(out[O["apogee_altitude"]], out[O["range"]], out[O["flight_time"]], out[O["final_x"]],
+                                            out[O["final_y"]]), histogram_bins=24)
+    assert (got["n_total"], got["n_samples"], got["n_outliers"], got["outlier_reasons"]) == \
+           (ref["n_total"], ref["n_samples"], ref["n_outliers"], ref["outlier_reasons"])
+    for key in ("apogee_altitude", "range", "flight_time"):
+        for f in ("mean", "std"):
+            assert abs(got[key][f] - ref[key][f]) <= 1e-12 * abs(ref[key][f])
+        assert got[key]["min"] == ref[key]["min"] and got[key]["max"] == ref[key]["max"]
+        assert got[key]["percentiles"] == ref[key]["percentiles"]          # exact order statistics
+        np.testing.assert_array_equal(got["histograms"][key]["counts"], ref["histograms"][key]["counts"])
+    np.testing.assert_allclose(got["landing_ellipse"]["covariance"], ref["landing_ellipse"]["covariance"], rtol=1e-11)
+    np.testing.assert_allclose(got[key]["percentiles"], np.percentile(out[O["flight_time"]][~MonteCarloAnalyzer.outlier_mask(
+        out[O["apogee_altitude"]], out[O["range"]], out[O["flight_time"]])], [5, 25, 50, 75, 95]), rtol=1e-15)

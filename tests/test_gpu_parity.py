@@ -83,7 +83,7 @@ def test_gpu_scheduling_invariance(engine):
     z = util.golden("mc_liquid_default")
     engine.set_model(_abi.model_from_npz(z))
     base = engine.run_batch(z["scalars"], z["wind"])
-    for kw in (dict(refill_threshold=32), dict(refill_threshold=8), dict(blocks_per_sm=1)):
+    for kw in (dict(refill_threshold=32), dict(refill_threshold=8), dict(refill_threshold=2)):
         got = engine.run_batch(z["scalars"], z["wind"], opts=_lib.run_opts(**kw))
         np.testing.assert_array_equal(got[0], base[0], err_msg=str(kw))
         np.testing.assert_array_equal(got[1], base[1], err_msg=str(kw))
