@@ -156,6 +156,8 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     n = a.samples_per_gpu
@@ -242,10 +244,10 @@ def main():
             "rk4_steps_per_s": steps_per_s, "mean_rk4_steps_per_trajectory": rk4_all / a.steps / n_total,
             "replayed_steps_per_trajectory": replay_all / a.steps / n_total,
             "kernel_ms_per_step": {"flight": flight_ms / a.steps, "rail": rail_ms / a.steps},
-            "roofline": {"bound": "fp64", "achieved": achieved_tf * world, "peak": peak_tf * world, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
-                         "note": "achieved = RK4 steps/s x 1600 flop (SURVEY 8d) over the flight kernel's CUDA-event time; "
-                                 "peak = in-run DFMA-chain microbenchmark (emc_fp64_peak), per GPU x n_gpus"},
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf * world, "unit": "TFLOP/s",
+                         "frac": achieved_tf / (peak_tf * world), "traffic": None,
+                         "note": "achieved = whole-job RK4 steps/s x 1600 flop (SURVEY 8d) over the flight kernel's CUDA-event time "
+                                 "(max over ranks); peak = in-run DFMA-chain microbenchmark (emc_fp64_peak) x n_gpus"},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
                     "h2d_bytes_per_step": int(blk.nbytes + wind.nbytes), "d2h_bytes_per_step": int(h_out.nbytes + h_iout.nbytes)},
             "gpu_launches": (2 + STATS_LAUNCHES) * a.steps * world,
