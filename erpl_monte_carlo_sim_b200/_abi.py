@@ -31,6 +31,11 @@ OUT = {k: i for i, k in enumerate(OUT_FIELDS)}
 IOUT = {k: i for i, k in enumerate(IOUT_FIELDS)}
 IN_COUNT, OUT_COUNT, IOUT_COUNT = len(IN_FIELDS), len(OUT_FIELDS), len(IOUT_FIELDS)
 TAPE_WIDTH = 15
+SERIES_FIELDS = ["mass", "Ixx", "Iyy", "Izz", "center_of_mass", "euler_roll", "euler_pitch", "euler_yaw", "thrust", "drag",
+                 "cd", "cl", "cm", "cp_location_dynamic", "stability_margin", "angle_of_attack", "sideslip_angle", "speed",
+                 "mach", "dynamic_pressure"]
+SER = {k: i for i, k in enumerate(SERIES_FIELDS)}
+SERIES_COUNT = len(SERIES_FIELDS)
 
 TERMINATION = {0: "none", 1: "ground_impact", 2: "excessive_altitude", 3: "coast_cap", 4: "max_time"}
 

@@ -81,6 +81,8 @@ def load():
     L.emc_stats_moments2.argtypes = [vp, vp, i64, i64, vp, vp]
     L.emc_stats_select_hist.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int, vp]
     L.emc_stats_linear_hist.argtypes = [vp, vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_int, vp]
+    L.emc_extract_series.argtypes = [vp, C.POINTER(_abi.EmcInputs), _dp, i64, _dp]
+    L.emc_extract_series.restype = C.c_int
     L.emc_upload_outputs.argtypes = [vp, vp, i64, i64]
     L.emc_upload_outputs.restype = C.c_int
     for name in ("emc_scratch", "emc_copy_to_host", "emc_copy_to_device", "emc_stats_moments1", "emc_stats_moments2",
@@ -205,6 +207,18 @@ class Engine:
         self._check(self._lib.emc_run_tape(self._ctx, C.byref(ins), C.byref(outs), tape.ctypes.data_as(_dp), cap,
                                            C.byref(ns)), "emc_run_tape")
         return out, iout, tape[:ns.value]
+
+    def extract_series(self, scalars, wind, tape):
+        """Derived per-state series of one flight (simulator.py:496-552) from its tape -> [SERIES_COUNT][n_states]."""
+        scalars = np.ascontiguousarray(scalars, np.float64).reshape(_abi.IN_COUNT, 1)
+        w = np.ascontiguousarray(wind, np.float64) if (self.has_wind and wind is not None) else None
+        ins = _abi.inputs_struct(scalars, w, wind_shared=True)
+        tape = np.ascontiguousarray(tape, np.float64)
+        n = tape.shape[0]
+        series = np.empty((_abi.SERIES_COUNT, n), np.float64)
+        self._check(self._lib.emc_extract_series(self._ctx, C.byref(ins), tape.ctypes.data_as(_dp), n, series.ctypes.data_as(_dp)),
+                    "emc_extract_series")
+        return series
 
     def derivative_debug(self, scalars, wind, t, state, chute):
         scalars = np.ascontiguousarray(scalars, np.float64)

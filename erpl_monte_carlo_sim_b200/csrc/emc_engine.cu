@@ -210,6 +210,23 @@ __global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* one thread per stored state of ONE flight: the derived series of _extract_results (simulator.py:511-552) */
+__global__ void __launch_bounds__(128) emc_series_kernel(KernelArgs a, const double *tape, int64_t n_states, double *series)
+{
+    extern __shared__ double smem[];
+    stage_tables(smem, a);
+    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
+    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_states) return;
+    Sample S;
+    load_sample(c_model, a.scalars, a.ld, a.wind, S);
+    const double t_rail = tape[0];
+    const double *row = tape + i * EMC_TAPE_WIDTH;
+    series_state(c_model, Tb, alt, S, row, row[0] - t_rail, series + i, n_states);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 __global__ void emc_math_kernel(int op, int64_t n, const double *x, const double *y, double *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -549,6 +566,29 @@ EMC_EXPORT int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_output
     const int64_t rows = ns < cap ? ns : cap;
     CK(cudaMemcpy(tape, ctx->d_tape, sizeof(double) * (size_t)rows * EMC_TAPE_WIDTH, cudaMemcpyDeviceToHost));
     if (ns > cap) return fail(ctx, EMC_ERR_CAPACITY, "emc_run_tape: tape capacity too small; n_states holds the required rows");
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_extract_series(emc_ctx *ctx, const emc_inputs *in, const double *tape, int64_t n_states, double *series)
+{
+    emc_outputs dummy = { (double *)1, (int32_t *)1, 1 };
+    if (int rc = check_run_args(ctx, in, 1, &dummy)) return rc;
+    if (!tape || !series || n_states < 1) return fail(ctx, EMC_ERR_INVALID, "emc_extract_series: tape/series/n_states");
+    CK(cudaSetDevice(ctx->device));
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    if (int rc = upload_inputs(ctx, in, 1, a)) return rc;
+    a.wind_alt = ctx->d_wind_alt;
+    if (!ctx->dmodel.has_wind) { a.wind = nullptr; a.wind_stride = 0; }
+    CK(grow(&ctx->d_tape, &ctx->cap_tape, (size_t)n_states * EMC_TAPE_WIDTH));
+    const size_t ns = (size_t)EMC_SERIES_COUNT * (size_t)n_states;
+    CK(grow(&ctx->d_scratch, &ctx->cap_scratch, ns * sizeof(double)));
+    double *d_series = reinterpret_cast<double *>(ctx->d_scratch);
+    CK(cudaMemcpyAsync(ctx->d_tape, tape, sizeof(double) * (size_t)n_states * EMC_TAPE_WIDTH, cudaMemcpyHostToDevice, ctx->stream));
+    emc_series_kernel<<<(unsigned)((n_states + 127) / 128), 128, smem_bytes(ctx->dmodel.n_wind), ctx->stream>>>(a, ctx->d_tape, n_states, d_series);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(series, d_series, ns * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return EMC_OK;
 }
 

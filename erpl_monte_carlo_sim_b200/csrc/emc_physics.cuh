@@ -963,4 +963,90 @@ EMC_HD void load_flight_state(const Sample &S, const double *col, int64_t ld, co
     s.pf = propellant_remaining(S, t_rail);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-stored-state result series, simulator.py:511-552 (_extract_results): one call per stored state.
+ * `t_shift` is time[i] = t - t_rail: the reference evaluates the thrust history at the SHIFTED time (:543).
+ * ---------------------------------------------------------------------------------------------- */
+EMC_HD void series_state(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
+                         const double *row /*t, state[14]*/, double t_shift, double *out, int64_t ld)
+{
+    State s;
+    s.x = row[1]; s.y = row[2]; s.z = row[3]; s.vx = row[4]; s.vy = row[5]; s.vz = row[6];
+    s.q0 = row[7]; s.q1 = row[8]; s.q2 = row[9]; s.q3 = row[10]; s.wx = row[11]; s.wy = row[12]; s.wz = row[13]; s.pf = row[14];
+    /* :512 euler angles of the stored quaternion, utils.py:139-144,46-69 */
+    {
+        const double x = s.q1, y = s.q2, z = s.q3, w = s.q0;
+        out[EMC_SER_EULER_ROLL * ld] = fast_atan2(2.0 * (w * x + y * z), 1.0 - 2.0 * (x * x + y * y));
+        const double sinp = 2.0 * (w * y - z * x);
+        out[EMC_SER_EULER_PITCH * ld] = (fabs(sinp) >= 1.0) ? copysign(K_MISC[0], sinp) : asin(sinp);
+        out[EMC_SER_EULER_YAW * ld] = fast_atan2(2.0 * (w * z + x * y), 1.0 - 2.0 * (y * y + z * z));
+    }
+    /* :515-520 mass properties at the UNCLAMPED propellant fraction, rocket.py:110-136 */
+    const double mp = S.prop_mass * s.pf;
+    const double mass = S.dry_mass + mp;
+    const double cg = (S.dry_cg + mp * M.prop_cg) / mass;
+    const double dcg = M.prop_cg - cg;
+    const double Ixx = M.Ixx_dry + mp * M.d4sq;
+    const double Iyy = M.Iyy_dry + mp * (M.len2_12 + dcg * dcg);
+    out[EMC_SER_MASS * ld] = mass; out[EMC_SER_CENTER_OF_MASS * ld] = cg;
+    out[EMC_SER_IXX * ld] = Ixx; out[EMC_SER_IYY * ld] = Iyy; out[EMC_SER_IZZ * ld] = Iyy;
+    /* :522-534 */
+    double T, inv_RT, p;
+    atmosphere(M, s.z, T, inv_RT, p);
+    const double rho = p * inv_RT;
+    WindBracket WB; wind_bracket_reset(WB);
+    double w[3];
+    wind_at(M, wind_alt, S, s.z, WB, w);
+    const double ux = s.vx - w[0], uy = s.vy - w[1], uz = s.vz - w[2];
+    const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
+    const bool q_ok = n2 > 1e-24;
+    const double rn = fast_rsqrt(q_ok ? n2 : 1.0);
+    const double qw = q_ok ? s.q0 * rn : 1.0, qx = q_ok ? s.q1 * rn : 0.0, qy = q_ok ? s.q2 * rn : 0.0, qz = q_ok ? s.q3 * rn : 0.0;
+    const double r00 = 1.0 - 2.0 * (qy * qy + qz * qz), r01 = 2.0 * (qx * qy - qw * qz), r02 = 2.0 * (qx * qz + qw * qy);
+    const double r10 = 2.0 * (qx * qy + qw * qz), r11 = 1.0 - 2.0 * (qx * qx + qz * qz), r12 = 2.0 * (qy * qz - qw * qx);
+    const double r20 = 2.0 * (qx * qz - qw * qy), r21 = 2.0 * (qy * qz + qw * qx), r22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+    const double vbx = r00 * ux + r10 * uy + r20 * uz, vby = r01 * ux + r11 * uy + r21 * uz, vbz = r02 * ux + r12 * uy + r22 * uz;
+    const double v2 = ux * ux + uy * uy + uz * uz;
+    const double mach2 = v2 * (inv_RT * K_MISC[7]);
+    double mach = fast_sqrt(mach2);
+    const double mach_c = (mach > 1e300) ? 1e300 : mach;
+    const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
+    const double alpha = a_dead ? 0.0 : fast_atan2(vbz, vbx);
+    const double vxz = fast_sqrt(vbx * vbx + vbz * vbz);
+    const double beta = (vxz < 1e-6) ? 0.0 : fast_atan2(vby, vxz);
+    /* :535-539 rocket.py:105-108,138-218 */
+    const int jc = brk_find(Tb.cp_lo, Tb.cp_hi, M.n_cp + 1, 1, mach_c);
+    const double cp = M.cp_location + fma(Tb.cp_s[jc], mach_c - Tb.cp_x0[jc], Tb.cp_f[jc]);
+    const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, 1, mach_c);
+    const double dm = mach_c - Tb.cd_x0[jd];
+    const double cd0 = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * S.cd_scale;
+    const double cda = fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]);
+    double cd = cd0 + cda * (alpha * alpha);
+    if (!(s.pf > 0.0)) cd *= M.power_off_factor;
+    const double rad = 4.0 + M.AR_over_cos2 * fabs(1.0 - mach2);
+    const double cl_alpha = M.two_pi_AR_cos / (2.0 + fast_sqrt(rad));
+    double cl = cl_alpha * alpha;
+    const double abs_alpha = fabs(alpha);
+    if (abs_alpha > M.stall_angle) {
+        const double over = (abs_alpha - M.stall_angle) * M.inv_stall_span;
+        double sf = 1.0 - over;
+        sf = (sf > 0.0) ? sf : 0.0;
+        const double sgn = (alpha > 0.0) ? 1.0 : ((alpha < 0.0) ? -1.0 : alpha);
+        cl = cl_alpha * M.stall_angle * sf * sgn;
+        cd *= 1.0 + 0.5 * over;
+    }
+    const double sm = cp - cg;
+    const double cm = -cl_alpha * sm * alpha;
+    const double qdyn = 0.5 * rho * v2;                                   /* :541 */
+    out[EMC_SER_DRAG * ld] = qdyn * cd * M.ref_area;                      /* :542 */
+    WindBracket TB; wind_bracket_reset(TB);
+    out[EMC_SER_THRUST * ld] = thrust_at(M, Tb, S, TB, t_shift, p);       /* :543 */
+    out[EMC_SER_CD * ld] = cd; out[EMC_SER_CL * ld] = cl; out[EMC_SER_CM * ld] = cm;
+    out[EMC_SER_CP_DYNAMIC * ld] = cp;
+    out[EMC_SER_STABILITY_MARGIN * ld] = sm / M.ref_diam;                 /* :549 */
+    out[EMC_SER_AOA * ld] = alpha; out[EMC_SER_SIDESLIP * ld] = beta;
+    out[EMC_SER_SPEED * ld] = sqrt(s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);
+    out[EMC_SER_MACH * ld] = mach; out[EMC_SER_QDYN * ld] = qdyn;
+}
+
 }  // namespace emc

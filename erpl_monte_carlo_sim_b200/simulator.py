@@ -9,7 +9,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _abi, _lib, marshal
-from .utils import object_to_serializable_dict, quaternion_to_euler
+from .utils import object_to_serializable_dict
 
 _ENGINES = {}
 
@@ -55,6 +55,8 @@ class FlightSimulator:
         wind = np.ascontiguousarray(wind_profile, np.float64) if use_wind else None
         cap = int(np.ceil(max(self.max_time, 0.0) / min(self.dt_initial, 0.005))) + 16
         out, iout, tape = eng.run_tape(blk, wind, cap=cap)
+        ser = eng.extract_series(blk, wind, tape)                # simulator.py:496-552 on the device
+        SR = _abi.SER
         o = out[:, 0]
         O = _abi.OUT
         rail_time = o[O["rail_exit_time"]]
@@ -64,8 +66,14 @@ class FlightSimulator:
             "time": tape[:, 0] - rail_time,
             "position": states[0:3], "velocity": states[3:6], "quaternion": quat,
             "angular_velocity": states[10:13], "propellant_fraction": states[13],
-            "altitude": states[2], "speed": np.linalg.norm(states[3:6], axis=0),
-            "euler_angles": quaternion_to_euler(quat.T).T,
+            "mass": ser[SR["mass"]], "moments_of_inertia": ser[SR["Ixx"]:SR["Izz"] + 1],
+            "altitude": states[2], "speed": ser[SR["speed"]],
+            "euler_angles": ser[SR["euler_roll"]:SR["euler_yaw"] + 1],
+            "center_of_mass": ser[SR["center_of_mass"]], "thrust": ser[SR["thrust"]], "drag": ser[SR["drag"]],
+            "cd": ser[SR["cd"]], "cl": ser[SR["cl"]], "cm": ser[SR["cm"]],
+            "cp_location_dynamic": ser[SR["cp_location_dynamic"]], "stability_margin": ser[SR["stability_margin"]],
+            "angle_of_attack": ser[SR["angle_of_attack"]], "sideslip_angle": ser[SR["sideslip_angle"]],
+            "mach": ser[SR["mach"]], "dynamic_pressure": ser[SR["dynamic_pressure"]],
             "cp_location": self.rocket.cp_location,
             "thrust_curve_time": getattr(self.motor, "thrust_curve_time", None),
             "thrust_curve_thrust": getattr(self.motor, "thrust_curve_thrust", None),

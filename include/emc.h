@@ -192,6 +192,24 @@ int emc_run_batch_device(emc_ctx *ctx, const emc_inputs *in_dev, int64_t n, cons
 int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_outputs *out,
                  double *tape, int64_t cap, int64_t *n_states);
 
+/* ---- per-state result series of one flight (reference simulator.py:496-552, _extract_results) ----------
+ * series[EMC_SERIES_COUNT][n_states], field-major, from the tape of emc_run_tape (tape[i] = t, state[14]). */
+enum emc_series_field {
+    EMC_SER_MASS = 0, EMC_SER_IXX, EMC_SER_IYY, EMC_SER_IZZ,        /* simulator.py:515-520 */
+    EMC_SER_CENTER_OF_MASS,                                         /* :516 */
+    EMC_SER_EULER_ROLL, EMC_SER_EULER_PITCH, EMC_SER_EULER_YAW,     /* :512 */
+    EMC_SER_THRUST,                                                 /* :543 (evaluated at the SHIFTED time, as the reference does) */
+    EMC_SER_DRAG,                                                   /* :542 */
+    EMC_SER_CD, EMC_SER_CL, EMC_SER_CM,                             /* :544-546 */
+    EMC_SER_CP_DYNAMIC, EMC_SER_STABILITY_MARGIN,                   /* :548-549 */
+    EMC_SER_AOA, EMC_SER_SIDESLIP,                                  /* :551-552 */
+    EMC_SER_SPEED,                                                  /* :476 */
+    EMC_SER_MACH, EMC_SER_QDYN,                                     /* :532, :541 (not result keys; used for max Mach / max Q) */
+    EMC_SERIES_COUNT
+};
+int emc_extract_series(emc_ctx *ctx, const emc_inputs *in /*one sample*/, const double *tape /*[n_states][EMC_TAPE_WIDTH], host*/,
+                       int64_t n_states, double *series /*[EMC_SERIES_COUNT][n_states], host*/);
+
 /* Test seam: out[i][14] = _rocket_dynamics(t[i], state[i]) (simulator.py:295-460) for sample i.
  * chute[i] is the sticky parachute flag, read and written back (simulator.py:366-369). */
 int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t n, const double *t,

@@ -646,6 +646,52 @@ static void *batch_worker(void *arg)
     return NULL;
 }
 
+/* simulator.py:496-552 (_extract_results): derived series of ONE flight from its stored states.
+ * series[EMC_SERIES_COUNT][n]; tape[i] = t (since ignition), state[14].  time[i] = t_i - t_0 (:464). */
+ORC_API int emc_oracle_series(const emc_model *m, const emc_inputs *in, const double *tape, int64_t n, double *series)
+{
+    orc_sample s;
+    sample_init(m, in->scalars, in->ld, in->wind, &s);
+    const double rail_time = tape[0];
+    for (int64_t i = 0; i < n; ++i) {
+        const double *st = tape + i * EMC_TAPE_WIDTH + 1;
+        double *o = series + i;
+        double time_i = tape[i * EMC_TAPE_WIDTH] - rail_time;                           /* :464 */
+        double e[3];
+        quaternion_to_euler(st + 6, e);                                                 /* :512 */
+        o[EMC_SER_EULER_ROLL * n] = e[0]; o[EMC_SER_EULER_PITCH * n] = e[1]; o[EMC_SER_EULER_YAW * n] = e[2];
+        double mp[4];
+        orc_mass_properties(m, s.dry_mass, s.propellant_mass, st[13], mp);              /* :515 */
+        o[EMC_SER_MASS * n] = mp[0]; o[EMC_SER_CENTER_OF_MASS * n] = mp[1];
+        o[EMC_SER_IXX * n] = mp[2]; o[EMC_SER_IYY * n] = mp[3]; o[EMC_SER_IZZ * n] = mp[3];
+        double alt = st[2], T, p, rho;
+        orc_atmosphere(m, alt, &T, &p, &rho);                                           /* :523 */
+        double w[3];
+        wind_at_altitude(m, &s, alt, w);                                                /* :525-528 */
+        double vel_rel[3] = { st[3] - w[0], st[4] - w[1], st[5] - w[2] };              /* :530 */
+        double R[3][3];
+        quaternion_to_rotation_matrix(st + 6, R);
+        double vb[3];
+        for (int k = 0; k < 3; ++k) vb[k] = R[0][k] * vel_rel[0] + R[1][k] * vel_rel[1] + R[2][k] * vel_rel[2]; /* :531 */
+        double mach = mach_number(vel_rel, T);                                          /* :532 */
+        double aoa = angle_of_attack(vb), beta = sideslip_angle(vb);                    /* :533-534 */
+        double cp_val = dynamic_cp(m, mach);                                            /* :535 */
+        double c[6];
+        orc_aero_coefficients(m, mach, aoa, beta, mp[1], st[13] > 0, s.cd_scale, c);    /* :536-539 */
+        double vn = norm3(vel_rel);
+        double q_dyn = 0.5 * rho * (vn * vn);                                           /* :541 */
+        o[EMC_SER_DRAG * n] = q_dyn * c[0] * m->reference_area;                         /* :542 */
+        o[EMC_SER_THRUST * n] = orc_thrust_raw(m, &s, time_i, p);                       /* :543 (shifted time) */
+        o[EMC_SER_CD * n] = c[0]; o[EMC_SER_CL * n] = c[1]; o[EMC_SER_CM * n] = c[2];   /* :544-546 */
+        o[EMC_SER_CP_DYNAMIC * n] = cp_val;                                             /* :548 */
+        o[EMC_SER_STABILITY_MARGIN * n] = (cp_val - mp[1]) / m->reference_diameter;     /* :549 */
+        o[EMC_SER_AOA * n] = aoa; o[EMC_SER_SIDESLIP * n] = beta;                       /* :551-552 */
+        o[EMC_SER_SPEED * n] = sqrt(st[3] * st[3] + st[4] * st[4] + st[5] * st[5]);     /* :476 */
+        o[EMC_SER_MACH * n] = mach; o[EMC_SER_QDYN * n] = q_dyn;
+    }
+    return 0;
+}
+
 ORC_API int emc_oracle_max_threads(void)
 {
     long c = sysconf(_SC_NPROCESSORS_ONLN);

@@ -113,5 +113,19 @@ def tape(md, scalars, wind, cap=70000):
     return out, iout, tp[:min(ns.value, cap)]
 
 
+def series(md, scalars, wind, tape_rows):
+    L = lib()
+    m, keep = _abi.pack_model(md)
+    scalars, wind = _prep(scalars, wind)
+    ins = _abi.inputs_struct(scalars, wind, wind_shared=True)
+    tape_rows = np.ascontiguousarray(tape_rows, np.float64)
+    n = tape_rows.shape[0]
+    out = np.empty((_abi.SERIES_COUNT, n))
+    L.emc_oracle_series.restype = C.c_int
+    rc = L.emc_oracle_series(C.byref(m), C.byref(ins), tape_rows.ctypes.data_as(_dp), C.c_int64(n), out.ctypes.data_as(_dp))
+    assert rc == 0
+    return out
+
+
 def max_threads():
     return lib().emc_oracle_max_threads()

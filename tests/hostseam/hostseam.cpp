@@ -87,4 +87,18 @@ int hs_replay(double t0, double t_rail, double dt, double max_time, double burn_
     return 0;
 }
 
+
+__attribute__((visibility("default")))
+int hs_series(const emc_model *m, const emc_inputs *in, const double *tape, int64_t n_states, double *series)
+{
+    if (validate_model(*m)) return -1;
+    DevModel D; DevTables T;
+    build_dev_model(*m, D, T);
+    Sample S;
+    load_sample(D, in->scalars, in->ld, in->wind, S);
+    for (int64_t i = 0; i < n_states; ++i)
+        series_state(D, T, m->wind_altitudes, S, tape + i * EMC_TAPE_WIDTH, tape[i * EMC_TAPE_WIDTH] - tape[0], series + i, n_states);
+    return 0;
+}
+
 }

@@ -105,3 +105,13 @@ def test_closed_form_time_replay_is_bit_exact():
         HS.hs_replay(*c, 1, a); HS.hs_replay(*c, 0, b)
         assert list(a)[:2] == list(b)[:2] and a[4] == b[4], (c, list(a), list(b))
         assert a[3] == b[3] and (a[2] == b[2] or a[3] == 0.0), (c, list(a), list(b))
+
+
+def test_seam_series_match_reference():
+    z = util.golden("flights_single")
+    for name in z["names"]:
+        name = str(name)
+        md, sc, wind, ref, iref = util.single_case(z, name)
+        idx, rows, sref = util.series_reference(z, name)
+        got = util.hostseam_series(md, sc, wind, rows.copy())
+        util.assert_series_close(got, sref, name)

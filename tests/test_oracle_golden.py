@@ -110,3 +110,18 @@ def test_oracle_threads_agree():
     b = O.batch(md, z["scalars"][:, :16], z["wind"][:16], n_threads=4)
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_oracle_series_match_reference():
+    """_extract_results (simulator.py:496-552) restated in the oracle vs the reference's own series, evaluated on the
+    reference's stored states (rows of the golden tape), incl. the shifted-time thrust quirk (:543)."""
+    z = util.golden("flights_single")
+    for name in z["names"]:
+        name = str(name)
+        md, sc, wind, ref, iref = util.single_case(z, name)
+        idx, rows, sref = util.series_reference(z, name)
+        rows = rows.copy()
+        # row 0 of the selection is state 0 (idx[0] == 0): the oracle takes t_rail from the first row
+        assert idx[0] == 0
+        got = O.series(md, sc, wind, rows)
+        util.assert_series_close(got, sref, name, rtol=1e-9)

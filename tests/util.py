@@ -179,3 +179,52 @@ def drop_nan_run_omega(out, ref, iref):
     i = OUT["max_abs_omega"]
     out[i, nan_run] = 0.0; ref[i, nan_run] = 0.0
     return out, ref
+
+
+# golden series keys (oracle/make_golden.py SERIES_KEYS) -> rows of the engine's series block
+SERIES_MAP = {"mass": "mass", "center_of_mass": "center_of_mass", "thrust": "thrust", "drag": "drag", "cd": "cd", "cl": "cl",
+              "cm": "cm", "cp_location_dynamic": "cp_location_dynamic", "stability_margin": "stability_margin",
+              "angle_of_attack": "angle_of_attack", "sideslip_angle": "sideslip_angle", "speed": "speed"}
+
+
+def series_reference(z, name):
+    """(row indices, tape rows, {engine series field: reference values}) of one golden single flight."""
+    idx = z[name + "__series__idx"]
+    rows = z[name + "__series__tape"]
+    ref = {v: z[name + "__series__" + k] for k, v in SERIES_MAP.items()}
+    moi = z[name + "__series__moments_of_inertia"]; eul = z[name + "__series__euler_angles"]
+    ref.update({"Ixx": moi[0], "Iyy": moi[1], "Izz": moi[2], "euler_roll": eul[0], "euler_pitch": eul[1], "euler_yaw": eul[2]})
+    return idx, rows, ref
+
+
+def assert_series_close(series, ref, what, rtol=RTOL):
+    """Every derived series within rtol of the reference; angles get a 1e-9 rad floor, forces/coefficients are
+    scaled by the series' own magnitude (they pass through zero); the blown-up tail (> 1e15) is skipped."""
+    for field, rv in ref.items():
+        got = series[_abi.SER[field]]
+        ok = np.isfinite(rv) & (np.abs(rv) < 1e15)
+        if not ok.any():
+            continue
+        scale = np.maximum(np.abs(rv[ok]), max(1e-9, 1e-6 * float(np.max(np.abs(rv[ok])))))
+        if field in ("angle_of_attack", "sideslip_angle", "euler_roll", "euler_pitch", "euler_yaw"):
+            # +pi and -pi are the same attitude
+            d = np.abs(np.angle(np.exp(1j * (got[ok] - rv[ok]))))
+            scale = np.maximum(np.abs(rv[ok]), 1e-3)
+        else:
+            d = np.abs(got[ok] - rv[ok])
+        worst = int(np.argmax(d / scale))
+        assert (d / scale)[worst] <= rtol, f"{what}: series {field} row {worst}: {got[ok][worst]!r} vs {rv[ok][worst]!r}"
+
+
+def hostseam_series(md, scalars, wind, tape_rows):
+    HS = hostseam_lib()
+    m, keep = _abi.pack_model(md)
+    scalars = np.ascontiguousarray(scalars, np.float64)
+    wind = np.ascontiguousarray(wind, np.float64) if wind is not None and np.size(wind) else None
+    ins = _abi.inputs_struct(scalars, wind, wind_shared=True)
+    tape_rows = np.ascontiguousarray(tape_rows, np.float64)
+    n = tape_rows.shape[0]
+    out = np.empty((_abi.SERIES_COUNT, n))
+    rc = HS.hs_series(C.byref(m), C.byref(ins), tape_rows.ctypes.data_as(_dp), C.c_int64(n), out.ctypes.data_as(_dp))
+    assert rc == 0
+    return out
