@@ -90,6 +90,19 @@ class EmcRunOpts(C.Structure):
                 ("blocks_per_sm", C.c_int32), ("nan_fast_forward", C.c_int32), ("cold_state_in_smem", C.c_int32)]
 
 
+class EmcDispersion(C.Structure):
+    _fields_ = [("base_pos", C.c_double * 3), ("base_vel", C.c_double * 3), ("base_att", C.c_double * 3), ("base_omega", C.c_double * 3),
+                ("sigma_pos", C.c_double * 3), ("sigma_vel", C.c_double * 3), ("sigma_att", C.c_double * 3), ("sigma_omega", C.c_double * 3),
+                ("mass_sigma", C.c_double), ("wind_speed_lo", C.c_double), ("wind_speed_hi", C.c_double),
+                ("wind_dir_lo", C.c_double), ("wind_dir_hi", C.c_double),
+                ("dry_mass", C.c_double), ("propellant_mass", C.c_double),
+                ("thrust_vacuum", C.c_double), ("thrust_sea_level", C.c_double), ("mass_flow_rate", C.c_double),
+                ("nozzle_exit_area", C.c_double), ("motor_propellant_mass", C.c_double), ("motor_burn_time", C.c_double),
+                ("thrust_sigma", C.c_double), ("flow_sigma", C.c_double), ("burn_sigma", C.c_double),
+                ("motor_kind", C.c_int32), ("wind_mode", C.c_int32), ("n_knots", C.c_int32), ("pad_", C.c_int32),
+                ("shear", _dp), ("base_wind", _dp), ("rho", _dp), ("innov", _dp)]
+
+
 class EmcCounters(C.Structure):
     _fields_ = [("rk4_steps", C.c_int64), ("replay_steps", C.c_int64), ("rail_steps", C.c_int64),
                 ("refills", C.c_int64), ("kernel_launches", C.c_int64),

@@ -81,6 +81,12 @@ def load():
     L.emc_stats_moments2.argtypes = [vp, vp, i64, i64, vp, vp]
     L.emc_stats_select_hist.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.c_int, vp]
     L.emc_stats_linear_hist.argtypes = [vp, vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_int, vp]
+    L.emc_generate_inputs.argtypes = [vp, C.POINTER(_abi.EmcDispersion), C.c_uint64, i64, i64, _dp, i64, _dp, vp, i64, vp]
+    L.emc_run_batch_staged.argtypes = [vp, i64, C.POINTER(_abi.EmcOutputs), C.POINTER(_abi.EmcRunOpts)]
+    L.emc_staged_inputs.argtypes = [vp, i64, _dp, _dp]
+    L.emc_philox_draws.argtypes = [vp, C.c_uint64, i64, i64, i64, _dp, _dp]
+    for name in ("emc_generate_inputs", "emc_run_batch_staged", "emc_staged_inputs", "emc_philox_draws"):
+        getattr(L, name).restype = C.c_int
     L.emc_extract_series.argtypes = [vp, C.POINTER(_abi.EmcInputs), _dp, i64, _dp]
     L.emc_extract_series.restype = C.c_int
     L.emc_upload_outputs.argtypes = [vp, vp, i64, i64]
@@ -207,6 +213,40 @@ class Engine:
         self._check(self._lib.emc_run_tape(self._ctx, C.byref(ins), C.byref(outs), tape.ctypes.data_as(_dp), cap,
                                            C.byref(ns)), "emc_run_tape")
         return out, iout, tape[:ns.value]
+
+    # -- device-side dispersions -----------------------------------------------------------------
+    def generate_inputs(self, disp, seed, first_index, n, gauss=None, unif=None, scalars_ptr=None, ld=0, wind_ptr=None):
+        """disp = (EmcDispersion, keepalive).  Philox draws unless gauss [n][G] / unif [n][2] are supplied.
+        Without device pointers the inputs are staged inside the context (fly them with run_batch_staged)."""
+        d, _keep = disp
+        g = np.ascontiguousarray(gauss, np.float64) if gauss is not None else None
+        u = np.ascontiguousarray(unif, np.float64) if unif is not None else None
+        self._check(self._lib.emc_generate_inputs(self._ctx, C.byref(d), C.c_uint64(seed), first_index, n,
+                                                  g.ctypes.data_as(_dp) if g is not None else None, g.shape[1] if g is not None else 0,
+                                                  u.ctypes.data_as(_dp) if u is not None else None,
+                                                  C.c_void_p(scalars_ptr) if scalars_ptr else None, ld,
+                                                  C.c_void_p(wind_ptr) if wind_ptr else None), "emc_generate_inputs")
+        self._staged_knots = int(d.n_knots)
+
+    def run_batch_staged(self, n, opts=None):
+        outs, out, iout = _abi.outputs_alloc(n)
+        self._check(self._lib.emc_run_batch_staged(self._ctx, n, C.byref(outs), C.byref(opts) if opts is not None else None),
+                    "emc_run_batch_staged")
+        return out, iout
+
+    def staged_inputs(self, n, want_wind=True):
+        sc = np.empty((_abi.IN_COUNT, n), np.float64)
+        k = getattr(self, "_staged_knots", 0)
+        w = np.empty((n, k, 3), np.float64) if (want_wind and k > 0) else None
+        self._check(self._lib.emc_staged_inputs(self._ctx, n, sc.ctypes.data_as(_dp), w.ctypes.data_as(_dp) if w is not None else None),
+                    "emc_staged_inputs")
+        return sc, w
+
+    def philox_draws(self, seed, first_index, n, n_gauss):
+        g = np.empty((n, n_gauss), np.float64); u = np.empty((n, 2), np.float64)
+        self._check(self._lib.emc_philox_draws(self._ctx, C.c_uint64(seed), first_index, n, n_gauss, g.ctypes.data_as(_dp),
+                                               u.ctypes.data_as(_dp)), "emc_philox_draws")
+        return g, u
 
     def extract_series(self, scalars, wind, tape):
         """Derived per-state series of one flight (simulator.py:496-552) from its tape -> [SERIES_COUNT][n_states]."""

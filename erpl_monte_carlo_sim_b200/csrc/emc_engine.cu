@@ -25,6 +25,7 @@
 
 #include "emc_model_build.h"
 #include "emc_stats.cuh"
+#include "emc_philox.cuh"
 
 using namespace emc;
 
@@ -277,6 +278,9 @@ struct emc_ctx {
     double *d_tape = nullptr; size_t cap_tape = 0;
     unsigned char *d_scratch = nullptr; size_t cap_scratch = 0;
     double *d_partial = nullptr; size_t cap_partial = 0;
+    double *d_disp = nullptr; size_t cap_disp = 0;    /* dispersion tables (shear/base wind/rho/innov) */
+    double *d_draws = nullptr; size_t cap_draws = 0;  /* caller-supplied draws */
+    int64_t staged_n = 0; int staged_knots = 0;
     int64_t last_n = 0;                       /* samples held by d_out/d_iout after the last host-buffer run */
     emc_counters counters;
     std::string err;
@@ -343,7 +347,7 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
-    cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -622,6 +626,114 @@ EMC_EXPORT int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(d_t); cudaFree(d_s); cudaFree(d_k); cudaFree(d_c);
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("emc_derivative_debug: ") + cudaGetErrorString(e));
+    return EMC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ *  device-side dispersions
+ * ------------------------------------------------------------------------------------------------- */
+EMC_EXPORT int emc_generate_inputs(emc_ctx *ctx, const emc_dispersion *d, uint64_t seed, int64_t first_index, int64_t n,
+                                   const double *gauss, int64_t n_gauss, const double *unif,
+                                   double *scalars_dev, int64_t ld, double *wind_dev)
+{
+    if (!ctx || !d || n < 0) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: bad argument");
+    if (d->n_knots < 0 || d->n_knots > EMC_MAX_WIND_KNOTS) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: n_knots");
+    if (d->n_knots > 0 && (!d->rho || !d->innov || (d->wind_mode == 0 ? !d->shear : !d->base_wind)))
+        return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: missing wind tables");
+    const int64_t need_g = (3 * (int64_t)d->n_knots > 15) ? 3 * (int64_t)d->n_knots : 15;
+    if (gauss && n_gauss < need_g) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: n_gauss too small (max(15, 3*n_knots))");
+    if (scalars_dev && d->n_knots > 0 && !wind_dev)
+        return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: wind_dev is NULL but the dispersion has wind knots");
+    if (n == 0) { if (!scalars_dev) { ctx->staged_n = 0; } return EMC_OK; }
+    CK(cudaSetDevice(ctx->device));
+    const int K = d->n_knots;
+    CK(grow(&ctx->d_disp, &ctx->cap_disp, (size_t)(6 * (K > 0 ? K : 1))));
+    DevDispersion D;
+    memset(&D, 0, sizeof D);
+    memcpy(D.base_pos, d->base_pos, sizeof(double) * 3 * 8);        /* base_* and sigma_* are contiguous in both structs */
+    D.mass_sigma = d->mass_sigma; D.wind_speed_lo = d->wind_speed_lo; D.wind_speed_hi = d->wind_speed_hi;
+    D.wind_dir_lo = d->wind_dir_lo; D.wind_dir_hi = d->wind_dir_hi; D.dry_mass = d->dry_mass; D.propellant_mass = d->propellant_mass;
+    D.thrust_vacuum = d->thrust_vacuum; D.thrust_sea_level = d->thrust_sea_level; D.mass_flow_rate = d->mass_flow_rate;
+    D.nozzle_exit_area = d->nozzle_exit_area; D.motor_propellant_mass = d->motor_propellant_mass; D.motor_burn_time = d->motor_burn_time;
+    D.thrust_sigma = d->thrust_sigma; D.flow_sigma = d->flow_sigma; D.burn_sigma = d->burn_sigma;
+    D.motor_kind = d->motor_kind; D.wind_mode = d->wind_mode; D.n_knots = K;
+    if (K > 0) {
+        double *t = ctx->d_disp;
+        D.shear = t; D.base_wind = t + K; D.rho = t + 4 * K; D.innov = t + 5 * K;
+        if (d->shear) CK(cudaMemcpyAsync(t, d->shear, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+        if (d->base_wind) CK(cudaMemcpyAsync(t + K, d->base_wind, sizeof(double) * 3 * K, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(t + 4 * K, d->rho, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(t + 5 * K, d->innov, sizeof(double) * K, cudaMemcpyHostToDevice, ctx->stream));
+        D.scale0 = d->innov[0];
+    }
+    const double *g_dev = nullptr, *u_dev = nullptr;
+    if (gauss || unif) {
+        if (!gauss || !unif) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: gauss and unif must be given together");
+        CK(grow(&ctx->d_draws, &ctx->cap_draws, (size_t)n * (size_t)(n_gauss + 2)));
+        CK(cudaMemcpyAsync(ctx->d_draws, gauss, sizeof(double) * (size_t)n * n_gauss, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_draws + (size_t)n * n_gauss, unif, sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        g_dev = ctx->d_draws; u_dev = ctx->d_draws + (size_t)n * n_gauss;
+    }
+    if (!scalars_dev) {
+        CK(grow(&ctx->d_scalars, &ctx->cap_scalars, (size_t)EMC_IN_COUNT * (size_t)n));
+        if (K > 0) CK(grow(&ctx->d_wind, &ctx->cap_wind, (size_t)n * (size_t)K * 3));
+        scalars_dev = ctx->d_scalars; ld = n; wind_dev = K > 0 ? ctx->d_wind : nullptr;
+        ctx->staged_n = n; ctx->staged_knots = K;
+    }
+    if (ld < n) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: ld < n");
+    emc_generate_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(D, seed, first_index, n, g_dev, n_gauss, u_dev, scalars_dev, ld, wind_dev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_run_batch_staged(emc_ctx *ctx, int64_t n, const emc_outputs *out, const emc_run_opts *opts)
+{
+    if (!ctx || !out) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: NULL argument");
+    if (!ctx->has_model) return fail(ctx, EMC_ERR_NO_MODEL, "emc_set_model has not been called");
+    if (n < 0 || n > ctx->staged_n) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: n exceeds the staged samples");
+    if (ctx->dmodel.has_wind && ctx->staged_knots != ctx->dmodel.n_wind) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: staged wind tables do not match the model's altitude grid");
+    if (n == 0) return EMC_OK;
+    if (!out->out || !out->iout || out->ld < n) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: output buffers");
+    CK(cudaSetDevice(ctx->device));
+    KernelArgs a;
+    memset(&a, 0, sizeof a);
+    a.scalars = ctx->d_scalars; a.ld = ctx->staged_n;
+    a.wind = ctx->dmodel.has_wind ? ctx->d_wind : nullptr; a.wind_stride = (int64_t)ctx->staged_knots * 3;
+    CK(grow(&ctx->d_out, &ctx->cap_out, (size_t)EMC_OUT_COUNT * (size_t)n));
+    CK(grow(&ctx->d_iout, &ctx->cap_iout, (size_t)EMC_IOUT_COUNT * (size_t)n));
+    a.out = ctx->d_out; a.iout = ctx->d_iout; a.old = n; a.n = n;
+    if (int rc = run_device(ctx, a, opts)) return rc;
+    if (int rc = download_outputs(ctx, out, n)) return rc;
+    ctx->last_n = n;
+    return finish_counters(ctx);
+}
+
+EMC_EXPORT int emc_staged_inputs(emc_ctx *ctx, int64_t n, double *scalars_host, double *wind_host)
+{
+    if (!ctx || n < 0 || n > ctx->staged_n) return fail(ctx, EMC_ERR_INVALID, "emc_staged_inputs: bad argument");
+    CK(cudaSetDevice(ctx->device));
+    if (scalars_host && n > 0)
+        CK(cudaMemcpy2DAsync(scalars_host, sizeof(double) * n, ctx->d_scalars, sizeof(double) * ctx->staged_n, sizeof(double) * n,
+                             EMC_IN_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    if (wind_host && n > 0 && ctx->staged_knots > 0)
+        CK(cudaMemcpyAsync(wind_host, ctx->d_wind, sizeof(double) * (size_t)n * ctx->staged_knots * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_philox_draws(emc_ctx *ctx, uint64_t seed, int64_t first_index, int64_t n, int64_t n_gauss, double *gauss, double *unif)
+{
+    if (!ctx || !gauss || !unif || n < 0 || n_gauss < 1) return fail(ctx, EMC_ERR_INVALID, "emc_philox_draws: bad argument");
+    if (n == 0) return EMC_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(grow(&ctx->d_draws, &ctx->cap_draws, (size_t)n * (size_t)(n_gauss + 2)));
+    double *g = ctx->d_draws, *u = g + (size_t)n * n_gauss;
+    emc_philox_draws_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(seed, first_index, n, n_gauss, g, u);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(gauss, g, sizeof(double) * (size_t)n * n_gauss, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(unif, u, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return EMC_OK;
 }
 

@@ -145,6 +145,8 @@ class MonteCarloAnalyzer:
         self.chunk_size = 1 << 16
         self.run_opts = None
         self.histogram_bins = 0
+        self.rng = "numpy"          # "numpy": the reference's own MT19937 streams (bit-matched inputs); "philox": drawn on the GPU
+        self.philox_seed = 0
         self.last_run = None
 
     # ------------------------------------------------------------------------------------------
@@ -268,6 +270,78 @@ class MonteCarloAnalyzer:
             wind = self.wind_model.stochastic_profiles_batch(alts, disp.wind_speed, disp.wind_direction, g3)  # :282-288
         return blk, np.ascontiguousarray(wind), alts
 
+    # ------------------------------------------------------------------------------------------
+    # device-side dispersions (Philox): same perturbation, draws generated on the GPU
+    # ------------------------------------------------------------------------------------------
+    def dispersion_struct(self, initial_conditions):
+        """(EmcDispersion, keepalive) describing uncertainty_params, the base initial conditions, the nominal rocket and
+        motor and the wind generator's per-knot coefficients (environment.py:161-185)."""
+        from .environment import _ar1_coefficients
+        up, ic, mtr = self.uncertainty_params, initial_conditions, self.motor
+        d = _abi.EmcDispersion()
+        for name, key in (("base_pos", "position"), ("base_vel", "velocity"), ("base_att", "attitude"), ("base_omega", "angular_velocity")):
+            for k, v in enumerate(np.asarray(ic.get(key, [0.0, 0.0, 0.0]), float)):
+                getattr(d, name)[k] = v
+        for name, key in (("sigma_pos", "initial_position"), ("sigma_vel", "initial_velocity"), ("sigma_att", "initial_attitude"),
+                          ("sigma_omega", "initial_angular_velocity")):
+            for k, v in enumerate(np.asarray(up[key], float)):
+                getattr(d, name)[k] = v
+        d.mass_sigma = up["mass_uncertainty"]
+        d.wind_speed_lo, d.wind_speed_hi = up["wind_speed_range"]
+        d.wind_dir_lo, d.wind_dir_hi = up["wind_direction_range"]
+        d.dry_mass, d.propellant_mass = self.rocket.dry_mass, self.rocket.propellant_mass
+        d.thrust_vacuum, d.thrust_sea_level, d.mass_flow_rate = mtr.thrust_vacuum, mtr.thrust_sea_level, mtr.mass_flow_rate
+        d.nozzle_exit_area, d.motor_propellant_mass, d.motor_burn_time = mtr.nozzle_exit_area, mtr.propellant_mass, mtr.burn_time
+        d.thrust_sigma = mtr.thrust_uncertainty
+        d.flow_sigma = getattr(mtr, "mass_flow_uncertainty", 0.0)
+        d.burn_sigma = getattr(mtr, "burn_time_uncertainty", 0.0)
+        d.motor_kind = _abi.MOTOR_SOLID if is_solid(mtr) else _abi.MOTOR_LIQUID
+        alts = self._altitude_grid()
+        scale, rho, innov = _ar1_coefficients(self.wind_model, alts)
+        csv = self.base_wind_profile is not None and self.base_altitude_profile is not None
+        d.wind_mode = 1 if csv else 0
+        d.n_knots = len(alts)
+        shear = np.array([(alts[i] / 10.0) ** self.wind_model.power_law_exponent for i in range(len(alts))])
+        base = np.ascontiguousarray(self.base_wind_profile, np.float64) if csv else np.zeros((len(alts), 3))
+        rho, innov = np.ascontiguousarray(rho), np.ascontiguousarray(innov)
+        dp = _abi._dp
+        d.shear, d.base_wind, d.rho, d.innov = (shear.ctypes.data_as(dp), base.ctypes.data_as(dp), rho.ctypes.data_as(dp),
+                                                innov.ctypes.data_as(dp))
+        return d, (shear, base, rho, innov)
+
+    def philox_parameters(self, n, first_index=0) -> DispersionSet:
+        """The parameter samples the device generator draws for indices first_index.. (from the same Philox bits)."""
+        from . import philox
+        up = self.uncertainty_params
+        idx = np.arange(first_index, first_index + n, dtype=np.uint64)
+        g = philox.normals(self.philox_seed, idx, 15); u = philox.uniforms(self.philox_seed, idx)
+        d = DispersionSet(n)
+        d.pos[:] = np.asarray(up["initial_position"], float) * g[:, 0:3]; d.vel[:] = np.asarray(up["initial_velocity"], float) * g[:, 3:6]
+        d.att[:] = np.asarray(up["initial_attitude"], float) * g[:, 6:9]; d.omega[:] = np.asarray(up["initial_angular_velocity"], float) * g[:, 9:12]
+        d.mass_multiplier[:] = 1.0 + up["mass_uncertainty"] * g[:, 12]; d.thrust_multiplier[:] = 1.0 + up["thrust_uncertainty"] * g[:, 13]
+        lo, hi = up["wind_speed_range"]; d.wind_speed[:] = lo + (hi - lo) * u[:, 0]
+        lo, hi = up["wind_direction_range"]; d.wind_direction[:] = lo + (hi - lo) * u[:, 1]
+        d.density_multiplier[:] = 1.0 + up["atmospheric_density_uncertainty"] * g[:, 14]
+        d.seed[:] = idx.astype(np.int64)
+        return d
+
+    def run_batch_philox(self, initial_conditions, n, first_index=0) -> BatchRun:
+        """Draw, perturb and fly n samples entirely on the GPU (no host input generation, no input upload)."""
+        eng = get_engine(self.device)
+        alts = self._altitude_grid()
+        eng.set_model(marshal.model_dict(self.rocket, self.motor, self.atmosphere, self._model_simulator(), alts))
+        disp_struct = self.dispersion_struct(initial_conditions)
+        out = np.empty((_abi.OUT_COUNT, n)); iout = np.empty((_abi.IOUT_COUNT, n), np.int32); scal = np.empty((_abi.IN_COUNT, n))
+        for lo in range(0, n, self.chunk_size):
+            hi = min(n, lo + self.chunk_size)
+            eng.generate_inputs(disp_struct, self.philox_seed, first_index + lo, hi - lo)
+            o, io = eng.run_batch_staged(hi - lo, opts=self.run_opts)
+            out[:, lo:hi] = o; iout[:, lo:hi] = io
+            scal[:, lo:hi] = eng.staged_inputs(hi - lo, want_wind=False)[0]
+        self.last_run = BatchRun(self, dict(initial_conditions), self.philox_parameters(n, first_index), out, iout, alts, scal,
+                                 outputs_resident=(n <= self.chunk_size))
+        return self.last_run
+
     def _model_simulator(self):
         return FlightSimulator(self.rocket, self.motor, self.atmosphere, self.wind_model, device=self.device)
 
@@ -294,6 +368,8 @@ class MonteCarloAnalyzer:
         """n_processes is accepted for signature compatibility; the batch runs on the GPU."""
         if optimized:
             return self.run_optimized_monte_carlo(initial_conditions, n_samples)
+        if self.rng == "philox":
+            return self._analyze_run(self.run_batch_philox(initial_conditions, n_samples))
         disp = self.draw_parameters(n_samples)
         run = self.run_batch(initial_conditions, disp)
         return self._analyze_run(run)

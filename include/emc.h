@@ -192,6 +192,43 @@ int emc_run_batch_device(emc_ctx *ctx, const emc_inputs *in_dev, int64_t n, cons
 int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_outputs *out,
                  double *tape, int64_t cap, int64_t *n_states);
 
+/* ---- device-side dispersion draws (reference monte_carlo.py:156-201,225-288; motor.py:95-125,171-186;
+ *      environment.py:125-200,218-265) -------------------------------------------------------------------
+ * Counter-based Philox4x32-10: sample i uses counter (i, j, stream) and the run seed as key.  The structure of the
+ * reference's per-sample streams is kept (one normal stream consumed from its start by the parameter draw, the motor
+ * and the wind generator); the bits are Philox/Box-Muller, so this mode matches the reference in
+ * distribution.  With `gauss`/`unif` given, the same kernel perturbs with the caller's draws (host-seeded NumPy). */
+typedef struct emc_dispersion {
+    double base_pos[3], base_vel[3], base_att[3], base_omega[3];       /* base initial conditions (euler xyz) */
+    double sigma_pos[3], sigma_vel[3], sigma_att[3], sigma_omega[3];   /* monte_carlo.py:36-39 */
+    double mass_sigma;                                                 /* :40 */
+    double wind_speed_lo, wind_speed_hi, wind_dir_lo, wind_dir_hi;     /* :45-46 */
+    double dry_mass, propellant_mass;                                  /* nominal rocket, :315-316 */
+    double thrust_vacuum, thrust_sea_level, mass_flow_rate;            /* nominal Liquid motor, motor.py:177-184 */
+    double nozzle_exit_area, motor_propellant_mass, motor_burn_time;   /* nominal Solid: Ae (motor.py:123), own burn time */
+    double thrust_sigma, flow_sigma, burn_sigma;                       /* motor.py:50-51,149-150 */
+    int32_t motor_kind;                                                /* EMC_MOTOR_LIQUID | EMC_MOTOR_SOLID */
+    int32_t wind_mode;                                                 /* 0: generate_stochastic_profile, 1: perturb_wind_profile + offset */
+    int32_t n_knots, pad_;
+    const double *shear;       /* [n_knots] (z/10)^0.14, mode 0 (environment.py:118-123)            host pointer */
+    const double *base_wind;   /* [n_knots][3], mode 1                                             host pointer */
+    const double *rho;         /* [n_knots] AR(1) correlation (environment.py:175-177)              host pointer */
+    const double *innov;       /* [n_knots] innovation scale; innov[0] = surface turbulence scale   host pointer */
+} emc_dispersion;
+
+/* Fill scalars_dev[EMC_IN_COUNT][ld] and wind_dev[n][n_knots][3] (DEVICE pointers; both NULL = the context's own staging
+ * buffers, to be flown with emc_run_batch_staged) for samples first_index .. first_index+n-1.
+ * gauss/unif: HOST arrays [n][n_gauss] / [n][2] of standard normals / uniforms to use instead of Philox, or NULL. */
+int emc_generate_inputs(emc_ctx *ctx, const emc_dispersion *d, uint64_t seed, int64_t first_index, int64_t n,
+                        const double *gauss, int64_t n_gauss, const double *unif,
+                        double *scalars_dev, int64_t ld, double *wind_dev);
+/* fly the n samples staged by emc_generate_inputs(..., NULL, 0, NULL); outputs to host buffers */
+int emc_run_batch_staged(emc_ctx *ctx, int64_t n, const emc_outputs *out, const emc_run_opts *opts);
+/* copy the staged inputs back (either pointer may be NULL): scalars[EMC_IN_COUNT][n], wind[n][n_knots][3] */
+int emc_staged_inputs(emc_ctx *ctx, int64_t n, double *scalars_host, double *wind_host);
+/* the Philox draws of samples first_index.. : gauss[n][n_gauss], unif[n][2] (host) */
+int emc_philox_draws(emc_ctx *ctx, uint64_t seed, int64_t first_index, int64_t n, int64_t n_gauss, double *gauss, double *unif);
+
 /* ---- per-state result series of one flight (reference simulator.py:496-552, _extract_results) ----------
  * series[EMC_SERIES_COUNT][n_states], field-major, from the tape of emc_run_tape (tape[i] = t, state[14]). */
 enum emc_series_field {
