@@ -14,7 +14,7 @@ import numpy as np
 from . import _abi
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(PKG_DIR, "libemc.so")
+SO_PATH = os.environ.get("EMC_LIB") or os.path.join(PKG_DIR, "libemc.so")    # EMC_LIB: developer override (kernel A/B builds)
 CSRC = os.path.join(PKG_DIR, "csrc")
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

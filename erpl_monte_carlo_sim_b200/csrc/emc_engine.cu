@@ -47,27 +47,29 @@ struct KernelArgs {
     int32_t refill_threshold; int32_t nan_ff;
 };
 
-/* stage the run-constant tables into shared memory: [DevTables][wind altitude grid] */
-__device__ __forceinline__ void stage_tables(double *smem, const KernelArgs &a)
+/* Stage the run-constant tables into shared memory.  The tables are a STATIC __shared__ object and the wind
+ * altitude grid the only dynamic part: objects addressed as shared arrays are read with plain LDS offsets, whereas
+ * pointers carved out of `extern __shared__` storage by pointer arithmetic are generic and made the compiler
+ * rebuild the shared-window address (S2UR CgaCtaId + ULEA) before every table access (profiles/, round 1). */
+__device__ __forceinline__ void stage_tables(DevTables &tb, double *alt, const KernelArgs &a)
 {
     const double *src = reinterpret_cast<const double *>(&c_tables);
+    double *dst = reinterpret_cast<double *>(&tb);
     constexpr int NT = sizeof(DevTables) / sizeof(double);
-    for (int i = threadIdx.x; i < NT; i += blockDim.x) smem[i] = src[i];
+    for (int i = threadIdx.x; i < NT; i += blockDim.x) dst[i] = src[i];
     const int nw = c_model.n_wind;
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) smem[NT + i] = a.wind_alt[i];
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) alt[i] = a.wind_alt[i];
     __syncthreads();
 }
 
-static size_t smem_bytes(int n_wind) { return sizeof(DevTables) + sizeof(double) * (size_t)(n_wind > 0 ? n_wind : 0); }
-static size_t smem_bytes_cold(int n_wind, int block);
+static size_t smem_bytes(int n_wind) { return sizeof(double) * (size_t)(n_wind > 0 ? n_wind : 0); }
 
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) emc_rail_kernel(KernelArgs a)
 {
-    extern __shared__ double smem[];
-    stage_tables(smem, a);
-    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
-    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    extern __shared__ double alt[];
+    __shared__ DevTables Tb;
+    stage_tables(Tb, alt, a);
     unsigned long long steps = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
         Sample S;
@@ -95,10 +97,10 @@ static_assert(sizeof(ColdLane) % 8 == 0 && (sizeof(ColdLane) / 8) % 2 == 1, "Col
 template <int BLOCK, int MINB, int COLD>
 __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
 {
-    extern __shared__ double smem[];
-    stage_tables(smem, a);
-    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
-    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    extern __shared__ double alt[];
+    __shared__ DevTables Tb;
+    __shared__ ColdLane sh_cold[COLD ? BLOCK : 1];
+    stage_tables(Tb, alt, a);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
 
@@ -106,9 +108,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
     int64_t idx = -1;
     State s;
     ColdLane reg_lane;                     /* COLD = 0: plain registers */
-    ColdLane *cold = COLD ? reinterpret_cast<ColdLane *>(smem + sizeof(DevTables) / sizeof(double) + ((c_model.n_wind + 1) & ~1)) + threadIdx.x
-                          : &reg_lane;
-    Track &K = cold->K; Sample &S = cold->S; WindBracket &WB = cold->WB;
+    ColdLane &CL = COLD ? sh_cold[COLD ? threadIdx.x : 0] : reg_lane;
+    Track &K = CL.K; Sample &S = CL.S; WindBracket &WB = CL.WB;
     unsigned long long n_steps = 0, n_replay = 0, n_refill = 0;
     const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
 
@@ -189,10 +190,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
 __global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const double *t, const double *state,
                                                              int32_t *chute, double *state_dot)
 {
-    extern __shared__ double smem[];
-    stage_tables(smem, a);
-    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
-    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    extern __shared__ double alt[];
+    __shared__ DevTables Tb;
+    stage_tables(Tb, alt, a);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     Sample S;
@@ -214,10 +214,9 @@ __global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const
 /* one thread per stored state of ONE flight: the derived series of _extract_results (simulator.py:511-552) */
 __global__ void __launch_bounds__(128) emc_series_kernel(KernelArgs a, const double *tape, int64_t n_states, double *series)
 {
-    extern __shared__ double smem[];
-    stage_tables(smem, a);
-    const DevTables &Tb = *reinterpret_cast<const DevTables *>(smem);
-    const double *alt = smem + sizeof(DevTables) / sizeof(double);
+    extern __shared__ double alt[];
+    __shared__ DevTables Tb;
+    stage_tables(Tb, alt, a);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_states) return;
     Sample S;
@@ -399,21 +398,12 @@ static int check_run_args(emc_ctx *ctx, const emc_inputs *in, int64_t n, const e
     return EMC_OK;
 }
 
-static size_t smem_bytes_cold(int n_wind, int block)
-{
-    const size_t words = sizeof(DevTables) / sizeof(double) + (size_t)(((n_wind > 0 ? n_wind : 0) + 1) & ~1);
-    return words * sizeof(double) + sizeof(ColdLane) * (size_t)block;
-}
-
 template <int BLOCK, int MINB, int COLD>
 static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
 {
     auto kern = emc_flight_kernel<BLOCK, MINB, COLD>;
-    if (COLD) smem = smem_bytes_cold(ctx->dmodel.n_wind, BLOCK);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     if (blocks_per_sm_req > 0 && blocks_per_sm_req < occ) occ = blocks_per_sm_req;
