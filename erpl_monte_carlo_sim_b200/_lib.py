@@ -89,6 +89,8 @@ def load():
         getattr(L, name).restype = C.c_int
     L.emc_extract_series.argtypes = [vp, C.POINTER(_abi.EmcInputs), _dp, i64, _dp]
     L.emc_extract_series.restype = C.c_int
+    L.emc_resident_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.emc_resident_outputs.restype = C.c_int
     L.emc_upload_outputs.argtypes = [vp, vp, i64, i64]
     L.emc_upload_outputs.restype = C.c_int
     for name in ("emc_scratch", "emc_copy_to_host", "emc_copy_to_device", "emc_stats_moments1", "emc_stats_moments2",
@@ -282,6 +284,12 @@ class Engine:
                                              yy.ctypes.data_as(_dp) if yy is not None else None,
                                              out.ctypes.data_as(_dp)), "emc_math_debug")
         return out
+
+    def resident_outputs(self):
+        """(device pointer, leading dimension) of the outputs the last host-buffer run left in HBM."""
+        ptr, ld = C.c_void_p(), C.c_int64()
+        self._check(self._lib.emc_resident_outputs(self._ctx, C.byref(ptr), C.byref(ld)), "emc_resident_outputs")
+        return ptr.value, ld.value
 
     def upload_outputs(self, out):
         out = np.ascontiguousarray(out, np.float64)

@@ -94,8 +94,8 @@ struct alignas(8) ColdLane {
 };
 static_assert(sizeof(ColdLane) % 8 == 0 && (sizeof(ColdLane) / 8) % 2 == 1, "ColdLane must span an odd number of 8-byte words");
 
-template <int BLOCK, int MINB, int COLD>
-__global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
+template <int BLOCK, int COLD>
+__device__ __forceinline__ void flight_body(const KernelArgs &a)
 {
     extern __shared__ double alt[];
     __shared__ DevTables Tb;
@@ -185,6 +185,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a)
         if (n_refill) atomicAdd(a.counters + 3, n_refill);
     }
 }
+
+template <int BLOCK, int MINB, int COLD>
+__global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a) { flight_body<BLOCK, COLD>(a); }
+
+/* 14 warps/SM: 64-thread blocks capped at 144 registers (launch bounds alone round down to 128) */
+__global__ void __maxnreg__(144) emc_flight_kernel_r144(KernelArgs a) { flight_body<64, 1>(a); }
 
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const double *t, const double *state,
@@ -398,21 +404,25 @@ static int check_run_args(emc_ctx *ctx, const emc_inputs *in, int64_t n, const e
     return EMC_OK;
 }
 
-template <int BLOCK, int MINB, int COLD>
-static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
+static cudaError_t launch_kernel(emc_ctx *ctx, void (*kern)(KernelArgs), int block, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
 {
-    auto kern = emc_flight_kernel<BLOCK, MINB, COLD>;
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, BLOCK, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     if (blocks_per_sm_req > 0 && blocks_per_sm_req < occ) occ = blocks_per_sm_req;
     int64_t grid = (int64_t)ctx->sm_count * occ;
-    const int64_t need = (a.n + BLOCK - 1) / BLOCK;
+    const int64_t need = (a.n + block - 1) / block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, BLOCK, smem, ctx->stream>>>(a);
+    kern<<<(unsigned)grid, block, smem, ctx->stream>>>(a);
     return cudaGetLastError();
+}
+
+template <int BLOCK, int MINB, int COLD>
+static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
+{
+    return launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD>, BLOCK, a, smem, blocks_per_sm_req);
 }
 
 /* all pointers in `a` are device pointers */
@@ -444,12 +454,15 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     const int bps = (o.block_threads > 0 || o.blocks_per_sm > 0) ? o.blocks_per_sm : 3;
     cudaError_t e;
     const bool cold = o.cold_state_in_smem >= 0;
-    if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
+    if (bt == 64 && bps == 7) e = launch_kernel(ctx, emc_flight_kernel_r144, 64, a, smem, bps);
+    else if (bt == 64 && bps == 8) e = launch_flight<64, 8, 1>(ctx, a, smem, bps);
+    else if (bt == 96 && bps == 4) e = launch_flight<96, 4, 1>(ctx, a, smem, bps);
+    else if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
     else if (bt == 256) e = launch_flight<256, 1, 0>(ctx, a, smem, bps);
     else if (bt == 128 && bps == 3) e = cold ? launch_flight<128, 3, 1>(ctx, a, smem, bps) : launch_flight<128, 3, 0>(ctx, a, smem, bps);
     else if (bt == 128 && bps >= 4) e = cold ? launch_flight<128, 4, 1>(ctx, a, smem, bps) : launch_flight<128, 4, 0>(ctx, a, smem, bps);
     else if (bt == 128) e = cold ? launch_flight<128, 1, 1>(ctx, a, smem, bps) : launch_flight<128, 1, 0>(ctx, a, smem, bps);
-    else return fail(ctx, EMC_ERR_INVALID, "block_threads must be 64, 128 or 256");
+    else return fail(ctx, EMC_ERR_INVALID, "block_threads must be 64, 96 (with 4 blocks/SM), 128 or 256");
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("flight kernel launch: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->counters.kernel_launches = 2;
@@ -754,6 +767,14 @@ EMC_EXPORT int emc_copy_to_device(emc_ctx *ctx, void *dev, const void *host, int
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(dev, host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_resident_outputs(emc_ctx *ctx, double **out_dev, int64_t *ld)
+{
+    if (!ctx || !out_dev || !ld) return fail(ctx, EMC_ERR_INVALID, "emc_resident_outputs: NULL argument");
+    if (!ctx->d_out || ctx->last_n <= 0) return fail(ctx, EMC_ERR_INVALID, "emc_resident_outputs: no resident outputs");
+    *out_dev = ctx->d_out; *ld = ctx->last_n;
     return EMC_OK;
 }
 

@@ -384,6 +384,50 @@ class MonteCarloAnalyzer:
                                    "cores_used": self.n_cores}
         return analysis
 
+    def run_sweep(self, initial_conditions, pitch_offsets=(0.0,), mass_scales=(1.0,), cd_scales=(1.0,), n_dispersions=1000):
+        """Design sweep (BASELINE config C5): every point of the launch-angle x mass x Cd-scale grid flies the same
+        `n_dispersions` dispersed samples (common random numbers, seeds 0..n-1) as ONE batch; per point the statistics
+        are reduced on the device and the tail is extracted the way the reference's scripts do it by hand: the sample of
+        maximum apogee (find_max_apogee.py:7-17) with its outlier diagnostics (analyze_outlier.py:18-25)."""
+        eng = get_engine(self.device)
+        alts = self._altitude_grid()
+        eng.set_model(marshal.model_dict(self.rocket, self.motor, self.atmosphere, self._model_simulator(), alts))
+        disp = self.draw_parameters(n_dispersions)
+        grid = [(p, ms, cs) for p in pitch_offsets for ms in mass_scales for cs in cd_scales]
+        IN = _abi.IN
+        blocks, winds = [], []
+        for p, ms, cs in grid:
+            ic = dict(initial_conditions)
+            att = np.asarray(ic.get("attitude", [0.0, 0.0, 0.0]), float).copy()
+            att[1] += p
+            ic["attitude"] = att
+            blk, wind, _ = self.build_inputs(ic, disp)
+            blk[IN["dry_mass"]] *= ms; blk[IN["prop_mass"]] *= ms
+            with np.errstate(divide="ignore", invalid="ignore"):
+                blk[IN["burn_time"]] = np.where(blk[IN["mdot"]] > 0, blk[IN["prop_mass"]] / blk[IN["mdot"]], blk[IN["burn_time"]])
+            blk[IN["cd_scale"]] = cs
+            blocks.append(blk); winds.append(wind)
+        scal = np.ascontiguousarray(np.concatenate(blocks, axis=1)); wind = np.ascontiguousarray(np.concatenate(winds, axis=0))
+        out, iout = eng.run_batch(scal, wind, opts=self.run_opts)
+        ptr, ld = eng.resident_outputs()
+        O = _abi.OUT
+        points = []
+        for g, (p, ms, cs) in enumerate(grid):
+            lo = g * n_dispersions
+            st = stats.device_statistics(eng, n_dispersions, out_dev=ptr + 8 * lo, ld=ld)
+            ap = out[O["apogee_altitude"], lo:lo + n_dispersions]
+            with np.errstate(invalid="ignore"):
+                cand = np.where(ap > 0, ap, 0.0)              # find_max_apogee.py:12-15 starts from max_apogee = 0
+            worst = int(np.nanargmax(cand)) if np.any(cand > 0) else -1
+            tail = None
+            if worst >= 0:
+                tail = {"sample": worst, "seed": int(disp.seed[worst]), **summary_extras(out, iout, lo + worst),
+                        "apogee_altitude": float(ap[worst]), "flight_time": float(out[O["flight_time"], lo + worst]),
+                        "range": float(out[O["range"], lo + worst])}
+            points.append({"pitch_offset": p, "mass_scale": ms, "cd_scale": cs, "statistics": st, "max_apogee": tail})
+        self.last_run = BatchRun(self, dict(initial_conditions), disp, out, iout, alts, scal, outputs_resident=True)
+        return {"grid": grid, "points": points, "n_dispersions": n_dispersions}
+
     def resimulate(self, initial_conditions, params):
         """The full `simulate_flight` result (time series included) of one dispersed sample."""
         disp = DispersionSet.from_dicts([params])

@@ -271,6 +271,10 @@ int emc_scratch(emc_ctx *ctx, int64_t bytes, void **dev_ptr);
 int emc_copy_to_host(emc_ctx *ctx, void *host, const void *dev, int64_t bytes);
 int emc_copy_to_device(emc_ctx *ctx, void *dev, const void *host, int64_t bytes);
 
+/* device pointer and leading dimension of the outputs left resident by the last host-buffer run (for statistics over
+ * sub-ranges: pass out_dev + first_sample with the same ld) */
+int emc_resident_outputs(emc_ctx *ctx, double **out_dev, int64_t *ld);
+
 /* make a host [EMC_OUT_COUNT][ld] block the context's resident outputs (for statistics over a run that was
  * executed in several chunks) */
 int emc_upload_outputs(emc_ctx *ctx, const double *out_host, int64_t ld, int64_t n);

@@ -180,3 +180,42 @@ def test_device_statistics_match_numpy_backend():
     np.testing.assert_allclose(got["landing_ellipse"]["covariance"], ref["landing_ellipse"]["covariance"], rtol=1e-11)
     np.testing.assert_allclose(got[key]["percentiles"], np.percentile(out[O["flight_time"]][~MonteCarloAnalyzer.outlier_mask(
         out[O["apogee_altitude"]], out[O["range"]], out[O["flight_time"]])], [5, 25, 50, 75, 95]), rtol=1e-15)
+
+
+def test_design_sweep_config_c5():
+    """BASELINE config C5: launch-angle x mass x Cd-scale grid, common dispersions per point, device statistics per point
+    and tail extraction; checked against the C oracle on the same inputs."""
+    import oracle_lib as O
+    from erpl_monte_carlo_sim_b200 import marshal
+    mc = MonteCarloAnalyzer(Rocket(), LiquidMotor(), StandardAtmosphere(), WindModel())
+    for k in ("initial_velocity", "initial_attitude", "initial_angular_velocity"):       # planar dispersions: flights reach landing
+        mc.uncertainty_params[k] = [mc.uncertainty_params[k][0], 0.0, 0.0] if k != "initial_attitude" else [0.0, 0.005, 0.0]
+    mc.uncertainty_params["initial_angular_velocity"] = [0.0, 0.005, 0.0]
+    mc.uncertainty_params["wind_speed_range"] = [0.0, 0.0]
+    mc.wind_model.turbulence_intensity = 0.0
+    ic = {"attitude": VERTICAL}
+    n = 8
+    sw = mc.run_sweep(ic, pitch_offsets=(0.0, 0.01), mass_scales=(1.0, 1.05), cd_scales=(1.0, 1.1), n_dispersions=n)
+    assert len(sw["points"]) == 8
+    run = mc.last_run
+    md = marshal.model_dict(mc.rocket, mc.motor, mc.atmosphere, mc._model_simulator(), mc._altitude_grid())
+    wind = np.zeros((run.scalars.shape[1], 100, 3))
+    ref, iref = O.batch(md, run.scalars, wind)
+    np.testing.assert_array_equal(run.iout, iref)
+    util.assert_summary_close(run.out, ref, what="C5 sweep", sens=util.oracle_sensitivity(md, run.scalars, wind))
+    O_ = _abi.OUT
+    by = {(p["pitch_offset"], p["mass_scale"], p["cd_scale"]): p for p in sw["points"]}
+    base, heavy, draggy = by[(0.0, 1.0, 1.0)], by[(0.0, 1.05, 1.0)], by[(0.0, 1.0, 1.1)]
+    # some planar flights still diverge in the descent tumble (SURVEY F8) and are filtered as outliers
+    assert base["statistics"]["n_samples"] + base["statistics"]["n_outliers"] == n and base["statistics"]["n_samples"] >= n // 2
+    assert base["statistics"]["apogee_altitude"]["mean"] > 20000
+    assert heavy["statistics"]["apogee_altitude"]["mean"] < base["statistics"]["apogee_altitude"]["mean"]
+    assert draggy["statistics"]["apogee_altitude"]["mean"] < base["statistics"]["apogee_altitude"]["mean"]
+    for g, pt in enumerate(sw["points"]):
+        sl = slice(g * n, (g + 1) * n)
+        ok = ~MonteCarloAnalyzer.outlier_mask(ref[O_["apogee_altitude"], sl], ref[O_["range"], sl], ref[O_["flight_time"], sl])
+        assert pt["statistics"]["n_samples"] == int(ok.sum())
+        assert abs(pt["statistics"]["apogee_altitude"]["mean"] - ref[O_["apogee_altitude"], sl][ok].mean()) <= 1e-6 * 30000
+        assert pt["max_apogee"]["sample"] == int(np.argmax(ref[O_["apogee_altitude"], sl]))
+        assert pt["max_apogee"]["max_abs_angular_velocity"] == run.out[O_["max_abs_omega"], g * n + pt["max_apogee"]["sample"]]
+    assert np.all(run.scalars[_abi.IN["cd_scale"], n:2 * n] == 1.1)
