@@ -72,6 +72,8 @@ def load():
     L.emc_derivative_debug.argtypes = [vp, C.POINTER(_abi.EmcInputs), i64, _dp, _dp, _ip, _dp]
     L.emc_get_counters.argtypes = [vp, C.POINTER(_abi.EmcCounters)]
     L.emc_fp64_peak.argtypes = [vp, _dp, _dp]
+    L.emc_fp64_latency.argtypes = [vp, _dp]
+    L.emc_fp64_latency.restype = C.c_int
     L.emc_math_debug.argtypes = [vp, C.c_int, i64, _dp, _dp, _dp]
     L.emc_math_debug.restype = C.c_int
     L.emc_scratch.argtypes = [vp, i64, C.POINTER(vp)]
@@ -300,6 +302,11 @@ class Engine:
         c = _abi.EmcCounters()
         self._lib.emc_get_counters(self._ctx, C.byref(c))
         return {k: getattr(c, k) for k, _ in _abi.EmcCounters._fields_}
+
+    def fp64_latency(self):
+        c = C.c_double()
+        self._check(self._lib.emc_fp64_latency(self._ctx, C.byref(c)), "emc_fp64_latency")
+        return c.value
 
     def fp64_peak(self):
         tf, ms = C.c_double(), C.c_double()

@@ -262,6 +262,18 @@ __global__ void __launch_bounds__(256) emc_dfma_kernel(double *sink, int iters, 
     if (r == 123456.789) sink[0] = r;     /* never true; keeps the chains alive */
 }
 
+/* one dependent DFMA chain in one warp: cycles per dependent FP64 FMA (clock64 around the chain) */
+__global__ void emc_dfma_latency_kernel(double *sink, long long *cycles, int iters, double a, double b)
+{
+    double x = threadIdx.x * 1e-9;
+    const long long t0 = clock64();
+#pragma unroll 16
+    for (int i = 0; i < iters; ++i) x = fma(x, a, b);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[0] = t1 - t0;
+    if (x == 123456.789) sink[0] = x;
+}
+
 /* ================================================================================================
  *  C ABI
  * ============================================================================================== */
@@ -900,6 +912,23 @@ EMC_EXPORT int emc_get_counters(const emc_ctx *ctx, emc_counters *c)
 {
     if (!ctx || !c) return EMC_ERR_INVALID;
     *c = ctx->counters;
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_fp64_latency(emc_ctx *ctx, double *cycles_per_dependent_fma)
+{
+    if (!ctx || !cycles_per_dependent_fma) return fail(ctx, EMC_ERR_INVALID, "emc_fp64_latency: NULL argument");
+    CK(cudaSetDevice(ctx->device));
+    double *sink = reinterpret_cast<double *>(ctx->d_ctrl + 6);
+    long long *cyc = reinterpret_cast<long long *>(ctx->d_ctrl + 7);
+    const int iters = 1 << 14;
+    emc_dfma_latency_kernel<<<1, 32, 0, ctx->stream>>>(sink, cyc, iters, 0.999999, 1e-9);
+    emc_dfma_latency_kernel<<<1, 32, 0, ctx->stream>>>(sink, cyc, iters, 0.999999, 1e-9);
+    CK(cudaGetLastError());
+    long long h = 0;
+    CK(cudaMemcpyAsync(&h, cyc, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *cycles_per_dependent_fma = (double)h / iters;
     return EMC_OK;
 }
 

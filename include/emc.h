@@ -301,6 +301,8 @@ int emc_math_debug(emc_ctx *ctx, int op, int64_t n, const double *x, const doubl
 
 /* Register-resident DFMA chain: measures this GPU's FP64 FMA peak (the roofline denominator). */
 int emc_fp64_peak(emc_ctx *ctx, double *tflops, double *ms);
+/* One dependent DFMA chain in one warp: SM cycles per dependent FP64 FMA (the latency a single trajectory sees). */
+int emc_fp64_latency(emc_ctx *ctx, double *cycles_per_dependent_fma);
 
 #ifdef __cplusplus
 }
