@@ -160,7 +160,7 @@ def main():
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--refill-threshold", type=int, default=0)
-    ap.add_argument("--cold-smem", type=int, default=1)
+    ap.add_argument("--cold-smem", type=int, default=2)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl != "reference" else a.warmup
     if a.impl == "reference":
@@ -186,7 +186,7 @@ def main():
     eng = _lib.Engine(local)
     eng.set_model(md)
     opts = _lib.run_opts(refill_threshold=a.refill_threshold, block_threads=a.block_threads, blocks_per_sm=a.blocks_per_sm,
-                         cold_state_in_smem=bool(a.cold_smem))
+                         cold_state_in_smem=a.cold_smem)
     peak_tf, _ = eng.fp64_peak()
 
     # ---- device-resident inputs/outputs (torch owns the HBM; the engine gets raw device pointers) ----

@@ -94,10 +94,21 @@ struct alignas(8) ColdLane {
 };
 static_assert(sizeof(ColdLane) % 8 == 0 && (sizeof(ColdLane) / 8) % 2 == 1, "ColdLane must span an odd number of 8-byte words");
 
-template <int BLOCK, int COLD>
-__device__ __forceinline__ void flight_body(const KernelArgs &a)
+/* Dynamic shared memory of the flight kernel: [28][BLOCK] state store (COLD == 2) followed by the wind altitude grid.
+ * It is indexed directly (never through a pointer carved out of it), so the accesses are plain LDS/STS. */
+extern __shared__ double emc_dyn[];
+
+template <int BLOCK>
+struct SharedStore {
+    __device__ __forceinline__ double s(int i) const { return emc_dyn[i * BLOCK + threadIdx.x]; }
+    __device__ __forceinline__ void set_s(int i, double v) { emc_dyn[i * BLOCK + threadIdx.x] = v; }
+    __device__ __forceinline__ double acc(int i) const { return emc_dyn[(14 + i) * BLOCK + threadIdx.x]; }
+    __device__ __forceinline__ void set_acc(int i, double v) { emc_dyn[(14 + i) * BLOCK + threadIdx.x] = v; }
+};
+
+template <int BLOCK, int COLD, class Store>
+__device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *alt)
 {
-    extern __shared__ double alt[];
     __shared__ DevTables Tb;
     __shared__ ColdLane sh_cold[COLD ? BLOCK : 1];
     stage_tables(Tb, alt, a);
@@ -106,7 +117,7 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
 
     bool active = false, drained = false;
     int64_t idx = -1;
-    State s;
+    Store st;
     ColdLane reg_lane;                     /* COLD = 0: plain registers */
     ColdLane &CL = COLD ? sh_cold[COLD ? threadIdx.x : 0] : reg_lane;
     Track &K = CL.K; Sample &S = CL.S; WindBracket &WB = CL.WB;
@@ -133,7 +144,9 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
                             idx = my;
                             load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
                             double t_rail;
+                            State s;
                             load_flight_state(S, a.scalars + idx, a.ld, a.out + idx, a.old, s, t_rail);
+                            store_put(st, s);
                             track_init(K, s, t_rail);
                             wind_bracket_reset(WB);
                             if (!(K.t < c_model.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
@@ -156,18 +169,18 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
         }
         if (active) {
             bool stepped; int64_t rep = 0;
-            const bool retired = lane_advance(c_model, Tb, alt, S, WB, K, s, a.nan_ff != 0, stepped, rep);
+            const bool retired = lane_advance(c_model, Tb, alt, S, WB, K, st, a.nan_ff != 0, stepped, rep);
             if (stepped) {
                 ++n_steps;
                 if (a.tape && (int64_t)K.n_steps < a.tape_cap) {
                     double *row = a.tape + (int64_t)K.n_steps * EMC_TAPE_WIDTH;
                     row[0] = K.t;
-                    const double *sp = reinterpret_cast<const double *>(&s);
-                    for (int c = 0; c < 14; ++c) row[1 + c] = sp[c];
+                    for (int c = 0; c < 14; ++c) row[1 + c] = st.s(c);
                 }
             }
             if (retired) {
                 n_replay += (unsigned long long)rep;
+                State s; store_get(st, s);
                 write_flight_outputs(K, s, a.out + idx, a.iout + idx, a.old);
                 if (a.tape_n) *a.tape_n = (int64_t)K.n_steps + 1 - rep;
                 active = false;
@@ -184,6 +197,15 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
         if (n_replay) atomicAdd(a.counters + 1, n_replay);
         if (n_refill) atomicAdd(a.counters + 3, n_refill);
     }
+}
+
+/* COLD: 0 everything in registers; 1 event bookkeeping / sample constants / brackets in shared memory;
+ *       2 additionally the base state and the RK4 accumulator (SharedStore) */
+template <int BLOCK, int COLD>
+__device__ __forceinline__ void flight_body(const KernelArgs &a)
+{
+    if (COLD == 2) flight_body_impl<BLOCK, 1, SharedStore<BLOCK>>(a, emc_dyn + 28 * BLOCK);
+    else flight_body_impl<BLOCK, (COLD != 0), RegStore>(a, emc_dyn);
 }
 
 template <int BLOCK, int MINB, int COLD>
@@ -419,7 +441,9 @@ static int check_run_args(emc_ctx *ctx, const emc_inputs *in, int64_t n, const e
 static cudaError_t launch_kernel(emc_ctx *ctx, void (*kern)(KernelArgs), int block, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
 {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, block, smem);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     if (blocks_per_sm_req > 0 && blocks_per_sm_req < occ) occ = blocks_per_sm_req;
@@ -461,16 +485,20 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
-    /* default launch: 128 threads, 3 blocks/SM (168 registers, 12 warps/SM), cold lane state in shared memory */
+    /* default launch: 128 threads, 3 blocks/SM (159 registers, 12 warps/SM), cold lane state, base state and RK4
+     * accumulator in shared memory */
     const int bt = o.block_threads > 0 ? o.block_threads : 128;
     const int bps = (o.block_threads > 0 || o.blocks_per_sm > 0) ? o.blocks_per_sm : 3;
     cudaError_t e;
     const bool cold = o.cold_state_in_smem >= 0;
+    const bool store = o.cold_state_in_smem == 0 || o.cold_state_in_smem >= 2;   /* default: base state + RK4 accumulator in shared memory as well */
     if (bt == 64 && bps == 7) e = launch_kernel(ctx, emc_flight_kernel_r144, 64, a, smem, bps);
     else if (bt == 64 && bps == 8) e = launch_flight<64, 8, 1>(ctx, a, smem, bps);
     else if (bt == 96 && bps == 4) e = launch_flight<96, 4, 1>(ctx, a, smem, bps);
     else if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
     else if (bt == 256) e = launch_flight<256, 1, 0>(ctx, a, smem, bps);
+    else if (bt == 128 && bps == 3 && store) e = launch_flight<128, 3, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
+    else if (bt == 128 && bps == 4 && store) e = launch_flight<128, 4, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
     else if (bt == 128 && bps == 3) e = cold ? launch_flight<128, 3, 1>(ctx, a, smem, bps) : launch_flight<128, 3, 0>(ctx, a, smem, bps);
     else if (bt == 128 && bps >= 4) e = cold ? launch_flight<128, 4, 1>(ctx, a, smem, bps) : launch_flight<128, 4, 0>(ctx, a, smem, bps);
     else if (bt == 128) e = cold ? launch_flight<128, 1, 1>(ctx, a, smem, bps) : launch_flight<128, 1, 0>(ctx, a, smem, bps);

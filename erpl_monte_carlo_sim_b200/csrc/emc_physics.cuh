@@ -621,15 +621,50 @@ EMC_HD bool track_post_step(const DevModel &M, const Sample &S, Track &K, const 
     return false;
 }
 
+/* Where a lane keeps its base state s and the RK4 accumulator between stages.  RegStore: registers
+ * (host seam, and the register-resident kernel variants).  The flight kernel can instead keep them in
+ * shared memory (SharedStore in emc_engine.cu): they are touched only at stage boundaries, and the ~56
+ * registers they would pin for the whole derivative are better spent on instruction-level parallelism. */
+struct RegStore {
+    State s_, a_;
+    EMC_HD double s(int i) const { return reinterpret_cast<const double *>(&s_)[i]; }
+    EMC_HD void set_s(int i, double v) { reinterpret_cast<double *>(&s_)[i] = v; }
+    EMC_HD double acc(int i) const { return reinterpret_cast<const double *>(&a_)[i]; }
+    EMC_HD void set_acc(int i, double v) { reinterpret_cast<double *>(&a_)[i] = v; }
+};
+
+template <class Store>
+EMC_HD void store_put(Store &st, const State &s)
+{
+    const double *p = reinterpret_cast<const double *>(&s);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 14; ++i) st.set_s(i, p[i]);
+}
+template <class Store>
+EMC_HD void store_get(const Store &st, State &s)
+{
+    double *p = reinterpret_cast<double *>(&s);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 14; ++i) p[i] = st.s(i);
+}
+
 /* One classical RK4 step (simulator.py:217-229): the four stages share ONE copy of the derivative.
  * Stage 0 doubles as the diagnostics pass of the stored state s (simulator.py:511-552 evaluates the
  * same quantities at the same state).  A lane whose loop has ended (K.finishing) runs stage 0 only,
  * for the diagnostics of its last stored state, with the sticky flag protected: the reference never
  * evaluates the derivative there.  Returns true if a full step was taken. */
+template <class Store>
 EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
-                     WindBracket &WB, Track &K, State &s)
+                     WindBracket &WB, Track &K, Store &st)
 {
-    State ys = s, acc = s, k;     /* acc is overwritten by stage 0 */
+    State ys, k;
+    double *y = reinterpret_cast<double *>(&ys);
+    const double *kk = reinterpret_cast<const double *>(&k);
+    store_get(st, ys);
     Diag dg;
     dg.mach2 = dg.qdyn = dg.abs_aoa = dg.stab = 0.0;
     const bool fin = K.finishing;
@@ -642,36 +677,33 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
         const double ts = (stage == 0) ? K.t : ((stage == 3) ? K.t + M.dt : K.t + M.half_dt);
         derivative(M, Tb, wind_alt, S, WB, ts, ys, K.chute, K.chute_time, k, stage == 0, dg);
         if (stage == 0) {
-            track_diag(K, s, dg);
+            track_diag(K, ys, dg);                      /* ys == s at stage 0 */
             if (fin) { K.chute = chute_keep; K.chute_time = chute_time_keep; return false; }
-            acc = k;
-        } else {
-            const double wgt = (stage == 3) ? 1.0 : 2.0;
-            acc.x += wgt * k.x; acc.y += wgt * k.y; acc.z += wgt * k.z;
-            acc.vx += wgt * k.vx; acc.vy += wgt * k.vy; acc.vz += wgt * k.vz;
-            acc.q0 += wgt * k.q0; acc.q1 += wgt * k.q1; acc.q2 += wgt * k.q2; acc.q3 += wgt * k.q3;
-            acc.wx += wgt * k.wx; acc.wy += wgt * k.wy; acc.wz += wgt * k.wz;
-            acc.pf += wgt * k.pf;
         }
         if (stage < 3) {
+            /* acc = k1 + 2 k2 + 2 k3 (+ k4 below), in the reference's order ((k1 + 2k2) + 2k3) + k4 (:224);
+             * next stage state = s + c k  (:218-222) */
             const double c = (stage == 2) ? M.dt : M.half_dt;
-            ys.x = s.x + c * k.x; ys.y = s.y + c * k.y; ys.z = s.z + c * k.z;
-            ys.vx = s.vx + c * k.vx; ys.vy = s.vy + c * k.vy; ys.vz = s.vz + c * k.vz;
-            ys.q0 = s.q0 + c * k.q0; ys.q1 = s.q1 + c * k.q1; ys.q2 = s.q2 + c * k.q2; ys.q3 = s.q3 + c * k.q3;
-            ys.wx = s.wx + c * k.wx; ys.wy = s.wy + c * k.wy; ys.wz = s.wz + c * k.wz;
-            ys.pf = s.pf + c * k.pf;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = 0; i < 14; ++i) {
+                const double ki = kk[i];
+                st.set_acc(i, (stage == 0) ? ki : fma(2.0, ki, st.acc(i)));
+                y[i] = fma(c, ki, st.s(i));
+            }
+        } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int i = 0; i < 14; ++i) st.set_s(i, fma(M.dt_over_6, st.acc(i) + kk[i], st.s(i)));
         }
     }
-    const double h = M.dt_over_6;
-    s.x += h * acc.x; s.y += h * acc.y; s.z += h * acc.z;
-    s.vx += h * acc.vx; s.vy += h * acc.vy; s.vz += h * acc.vz;
-    s.q0 += h * acc.q0; s.q1 += h * acc.q1; s.q2 += h * acc.q2; s.q3 += h * acc.q3;
-    s.wx += h * acc.wx; s.wy += h * acc.wy; s.wz += h * acc.wz;
-    s.pf += h * acc.pf;
     /* :227 renormalise */
-    const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
-    if (n2 > 1e-24) { const double rn = fast_rsqrt(n2); s.q0 *= rn; s.q1 *= rn; s.q2 *= rn; s.q3 *= rn; }
-    else { s.q0 = 1.0; s.q1 = 0.0; s.q2 = 0.0; s.q3 = 0.0; }
+    const double q0 = st.s(6), q1 = st.s(7), q2 = st.s(8), q3 = st.s(9);
+    const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+    if (n2 > 1e-24) { const double rn = fast_rsqrt(n2); st.set_s(6, q0 * rn); st.set_s(7, q1 * rn); st.set_s(8, q2 * rn); st.set_s(9, q3 * rn); }
+    else { st.set_s(6, 1.0); st.set_s(7, 0.0); st.set_s(8, 0.0); st.set_s(9, 0.0); }
     K.t += M.dt;
     return true;
 }
@@ -805,14 +837,20 @@ EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K, State &
 /* One scheduling quantum of a lane, shared by the flight kernel and the test seam: a full RK4 step
  * plus the event logic, or the closing diagnostics pass.  Returns true when the lane retires (its
  * outputs are final).  `stepped` reports whether a stored state was produced (tape). */
+template <class Store>
 EMC_HD bool lane_advance(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
-                         WindBracket &WB, Track &K, State &s, bool nan_ff, bool &stepped, int64_t &replayed)
+                         WindBracket &WB, Track &K, Store &st, bool nan_ff, bool &stepped, int64_t &replayed)
 {
-    stepped = rk4_step(M, Tb, wind_alt, S, WB, K, s);
+    stepped = rk4_step(M, Tb, wind_alt, S, WB, K, st);
     if (!stepped) {                       /* closing pass done */
-        if (K.replay) replayed += replay_time(M, S, K, s);
+        if (K.replay) {
+            State s; store_get(st, s);
+            replayed += replay_time(M, S, K, s);
+            st.set_s(0, s.x); st.set_s(1, s.y);
+        }
         return true;
     }
+    State s; store_get(st, s);
     bool done = track_post_step(M, S, K, s);
     if (!done && nan_ff) { K.replay = nan_mode(M, S, K, s); done = (K.replay != 0); }
     K.finishing = done;

@@ -158,7 +158,7 @@ typedef struct emc_run_opts {
     int32_t block_threads;    /* 0 = default (128) */
     int32_t blocks_per_sm;    /* 0 = default (3 when block_threads is 0, else the occupancy limit) */
     int32_t nan_fast_forward; /* 1 (default when opts==NULL): replay t += dt only once the altitude is NaN for good */
-    int32_t cold_state_in_smem; /* >= 0 (default): per-lane bookkeeping lives in shared memory (fewer registers, more resident warps); -1: registers */
+    int32_t cold_state_in_smem; /* 0 (default) or 2: per-lane bookkeeping, base state and RK4 accumulator live in shared memory; 1: bookkeeping only; -1: registers */
 } emc_run_opts;
 
 typedef struct emc_ctx emc_ctx;

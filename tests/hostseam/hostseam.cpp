@@ -52,13 +52,15 @@ int hs_batch(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outp
         State s; double t_rail;
         load_flight_state(S, col, in->ld, out, o->ld, s, t_rail);
         Track K; track_init(K, s, t_rail);
+        RegStore st; store_put(st, s);
         WindBracket WB; wind_bracket_reset(WB);
         int64_t ns = 1, replayed = 0;
         if (tape && tape_cap > 0) { tape[0] = K.t; memcpy(tape + 1, &s, sizeof s); }
         if (!(K.t < D.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
         for (;;) {
             bool stepped;
-            bool retired = lane_advance(D, T, m->wind_altitudes, S, WB, K, s, nan_fast_forward != 0, stepped, replayed);
+            bool retired = lane_advance(D, T, m->wind_altitudes, S, WB, K, st, nan_fast_forward != 0, stepped, replayed);
+            store_get(st, s);
             if (stepped) {
                 if (tape && ns < tape_cap) { tape[ns * EMC_TAPE_WIDTH] = K.t; memcpy(tape + ns * EMC_TAPE_WIDTH + 1, &s, sizeof s); }
                 ++ns;
