@@ -18,7 +18,7 @@ from collections.abc import Sequence
 
 import numpy as np
 
-from . import _abi, marshal, stats
+from . import _abi, marshal, report, stats
 from .motor import LiquidMotor, SolidMotor, is_solid
 from .simulator import FlightSimulator, get_engine, summary_extras
 
@@ -427,6 +427,13 @@ class MonteCarloAnalyzer:
             points.append({"pitch_offset": p, "mass_scale": ms, "cd_scale": cs, "statistics": st, "max_apogee": tail})
         self.last_run = BatchRun(self, dict(initial_conditions), disp, out, iout, alts, scal, outputs_resident=True)
         return {"grid": grid, "points": points, "n_dispersions": n_dispersions}
+
+    # report writing (monte_carlo.py:475-560): host I/O in the reference's file layout
+    def _create_output_directory(self):
+        return report.create_output_directory()
+
+    def _save_report(self, analysis, output_dir, max_samples=1000):
+        return report.save_report(self, analysis, output_dir, max_samples=max_samples)
 
     def resimulate(self, initial_conditions, params):
         """The full `simulate_flight` result (time series included) of one dispersed sample."""

@@ -221,3 +221,37 @@ def test_design_sweep_config_c5():
         assert pt["max_apogee"]["sample"] == want
         assert pt["max_apogee"]["max_abs_angular_velocity"] == run.out[O_["max_abs_omega"], g * n + pt["max_apogee"]["sample"]]
     assert np.all(run.scalars[_abi.IN["cd_scale"], n:2 * n] == 1.1)
+
+
+def test_report_layout_feeds_the_reference_scripts(tmp_path):
+    """_save_report writes the reference's file layout (monte_carlo.py:482-560); the per-sample dumps carry every key that
+    find_max_apogee.py:7-17 and analyze_outlier.py:11-49 read."""
+    import json
+    mc = MonteCarloAnalyzer(Rocket(), SolidMotor(), StandardAtmosphere(), WindModel())
+    for k in ("initial_velocity", "initial_attitude", "initial_angular_velocity"):
+        mc.uncertainty_params[k] = [0.0, 0.0, 0.0]
+    mc.uncertainty_params["initial_attitude"] = [0.0, 0.005, 0.0]
+    mc.uncertainty_params["wind_speed_range"] = [0.0, 0.0]
+    mc.wind_model.turbulence_intensity = 0.0
+    an = mc.run_monte_carlo({"attitude": VERTICAL}, n_samples=6)
+    out = mc._save_report(an, str(tmp_path / "mc"), max_samples=4)
+    rep = json.load(open(out + "/monte_carlo_report.json"))
+    assert {"timestamp", "simulation_summary", "apogee_altitude_stats", "range_stats", "flight_time_stats", "uncertainty_parameters",
+            "parameter_ranges_observed", "rocket_parameters", "motor_parameters", "atmosphere_parameters", "wind_model_parameters"} <= set(rep)
+    assert rep["simulation_summary"]["total_simulations"] == an["n_samples"]
+    assert "Apogee Altitude Statistics:" in open(out + "/monte_carlo_report.txt").read()
+    best, best_id = 0, -1                                     # find_max_apogee.py
+    for i in range(100):
+        try:
+            data = json.load(open(f"{out}/simulation_results/sim_{i}.json"))
+        except OSError:
+            continue
+        if data["apogee_altitude"] > best:
+            best, best_id = data["apogee_altitude"], i
+        vel = np.array(data["velocity"]); speed = np.array(data["speed"]); q = np.array(data["quaternion"])      # analyze_outlier.py
+        assert vel.shape[0] == 3 and abs(np.max(speed) - data["max_speed"]) <= 1e-9 * data["max_speed"]
+        assert np.max(np.abs(np.linalg.norm(q, axis=0) - 1)) < 1e-12
+        for key in ("angular_velocity", "altitude", "euler_angles", "stability_margin", "flight_time", "propellant_fraction", "mass",
+                    "thrust", "time", "initial_conditions"):
+            assert key in data
+    assert best_id >= 0 and best > 20000
