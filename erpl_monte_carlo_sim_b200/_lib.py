@@ -72,6 +72,8 @@ def load():
     L.emc_derivative_debug.argtypes = [vp, C.POINTER(_abi.EmcInputs), i64, _dp, _dp, _ip, _dp]
     L.emc_get_counters.argtypes = [vp, C.POINTER(_abi.EmcCounters)]
     L.emc_fp64_peak.argtypes = [vp, _dp, _dp]
+    L.emc_component_debug.argtypes = [vp, C.c_int, i64, _dp, _dp]
+    L.emc_component_debug.restype = C.c_int
     L.emc_fp64_latency.argtypes = [vp, _dp]
     L.emc_fp64_latency.restype = C.c_int
     L.emc_math_debug.argtypes = [vp, C.c_int, i64, _dp, _dp, _dp]
@@ -277,6 +279,20 @@ class Engine:
                                                    state.ctypes.data_as(_dp), ch.ctypes.data_as(_ip),
                                                    sd.ctypes.data_as(_dp)), "emc_derivative_debug")
         return sd, ch
+
+    COMPONENT_SHAPES = {0: (1, 5), 1: (3, 5), 2: (6, 7), 3: (5, 1)}      # component -> (input rows, output rows)
+
+    def component(self, comp, *columns):
+        """Evaluate a model component on the device: columns are broadcast to a common length n -> out[rows][n]."""
+        n_in, n_out = self.COMPONENT_SHAPES[comp]
+        assert len(columns) == n_in
+        cols = np.broadcast_arrays(*[np.atleast_1d(np.asarray(c, np.float64)) for c in columns])
+        n = cols[0].size
+        blk = np.ascontiguousarray(np.stack([c.ravel() for c in cols], axis=0))
+        out = np.empty((n_out, n), np.float64)
+        self._check(self._lib.emc_component_debug(self._ctx, comp, n, blk.ctypes.data_as(_dp), out.ctypes.data_as(_dp)),
+                    "emc_component_debug")
+        return out
 
     def math_debug(self, op, x, y=None):
         x = np.ascontiguousarray(x, np.float64)

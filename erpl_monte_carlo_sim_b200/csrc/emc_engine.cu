@@ -255,6 +255,20 @@ __global__ void __launch_bounds__(128) emc_series_kernel(KernelArgs a, const dou
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(128) emc_component_kernel(int comp, int64_t n, const double *in, double *out)
+{
+    __shared__ DevTables Tb;
+    {
+        const double *src = reinterpret_cast<const double *>(&c_tables);
+        double *dst = reinterpret_cast<double *>(&Tb);
+        for (int i = threadIdx.x; i < (int)(sizeof(DevTables) / sizeof(double)); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) component_eval(c_model, Tb, comp, in + i, out + i, n);
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 __global__ void emc_math_kernel(int op, int64_t n, const double *x, const double *y, double *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -912,6 +926,24 @@ EMC_EXPORT int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_
     emc_stats_linear_hist_kernel<<<stats_grid(ctx, n), 256, 0, ctx->stream>>>(out_dev, ld, n, field, lo, hi, nbins,
                                                                              reinterpret_cast<unsigned long long *>(hist_dev));
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_component_debug(emc_ctx *ctx, int component, int64_t n, const double *in, double *out)
+{
+    static const int n_in[4] = { 1, 3, 6, 5 }, n_out[4] = { 5, 5, 7, 1 };
+    if (!ctx || !in || !out || n < 0 || component < 0 || component > 3) return fail(ctx, EMC_ERR_INVALID, "emc_component_debug: bad argument");
+    if (!ctx->has_model) return fail(ctx, EMC_ERR_NO_MODEL, "emc_set_model has not been called");
+    if (n == 0) return EMC_OK;
+    CK(cudaSetDevice(ctx->device));
+    const size_t ni = (size_t)n_in[component] * n, no = (size_t)n_out[component] * n;
+    CK(grow(&ctx->d_scratch, &ctx->cap_scratch, (ni + no) * sizeof(double)));
+    double *d_in = reinterpret_cast<double *>(ctx->d_scratch), *d_out = d_in + ni;
+    CK(cudaMemcpyAsync(d_in, in, ni * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    emc_component_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(component, n, d_in, d_out);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, d_out, no * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return EMC_OK;
 }

@@ -1001,6 +1001,64 @@ EMC_HD void load_flight_state(const Sample &S, const double *col, int64_t ld, co
     s.pf = propellant_remaining(S, t_rail);
 }
 
+/* rocket.py:138-218 as a standalone function (series extraction and the component test seam; the hot derivative has
+ * its own fused form).  c = {cd, cl, cm(=cpitch), cy, cyaw, cp, cn}.  `mach` is already clamped to 1e300. */
+EMC_HD void aero_coefficients(const DevModel &M, const DevTables &Tb, double mach, double mach2, double alpha, double beta,
+                              double cg, bool power_on, double cd_scale, double c[7])
+{
+    const int jc = brk_find(Tb.cp_lo, Tb.cp_hi, M.n_cp + 1, 1, mach);
+    const double cp = M.cp_location + fma(Tb.cp_s[jc], mach - Tb.cp_x0[jc], Tb.cp_f[jc]);
+    const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, 1, mach);
+    const double dm = mach - Tb.cd_x0[jd];
+    const double cd0 = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * cd_scale;
+    const double cda = fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]);
+    double cd = cd0 + cda * (alpha * alpha);
+    if (!power_on) cd *= M.power_off_factor;
+    const double rad = 4.0 + M.AR_over_cos2 * fabs(1.0 - mach2);
+    const double cl_alpha = M.two_pi_AR_cos / (2.0 + fast_sqrt(rad));
+    double cl = cl_alpha * alpha, cy = cl_alpha * beta, cn = cl_alpha * alpha;
+    const double abs_alpha = fabs(alpha);
+    if (abs_alpha > M.stall_angle) {
+        const double over = (abs_alpha - M.stall_angle) * M.inv_stall_span;
+        double sf = 1.0 - over;
+        sf = (sf > 0.0) ? sf : 0.0;
+        const double sgn = (alpha > 0.0) ? 1.0 : ((alpha < 0.0) ? -1.0 : alpha);
+        cl = cl_alpha * M.stall_angle * sf * sgn;
+        cn = cl;
+        cd *= 1.0 + 0.5 * over;
+        cy *= sf;
+    }
+    const double sm = cp - cg;
+    c[0] = cd; c[1] = cl; c[2] = -cl_alpha * sm * alpha; c[3] = cy; c[4] = -cl_alpha * sm * beta; c[5] = cp; c[6] = cn;
+}
+
+/* component evaluation for one element (emc_component_debug / host seam): in/out are field-major with stride ld */
+EMC_HD void component_eval(const DevModel &M, const DevTables &Tb, int comp, const double *in, double *out, int64_t ld)
+{
+    if (comp == 0) {
+        double T, inv_RT, p;
+        atmosphere(M, in[0], T, inv_RT, p);
+        out[0] = T; out[ld] = p; out[2 * ld] = p * inv_RT; out[3 * ld] = sqrt(1.4 * M.R_gas * T); out[4 * ld] = gravity(M, in[0]);
+    } else if (comp == 1) {
+        const double pf = in[0], dry = in[ld], prop = in[2 * ld];
+        const double mp = prop * pf, mass = dry + mp;
+        const double cg = (dry * M.cg_dry + mp * M.prop_cg) / mass, dcg = M.prop_cg - cg;
+        out[0] = mass; out[ld] = cg; out[2 * ld] = M.Ixx_dry + mp * M.d4sq;
+        out[3 * ld] = M.Iyy_dry + mp * (M.len2_12 + dcg * dcg); out[4 * ld] = out[3 * ld];
+    } else if (comp == 2) {
+        double c[7];
+        const double mach = in[0], mc = (mach > 1e300) ? 1e300 : mach;
+        aero_coefficients(M, Tb, mc, mach * mach, in[ld], in[2 * ld], in[3 * ld], in[4 * ld] != 0.0, in[5 * ld], c);
+        for (int k = 0; k < 7; ++k) out[k * ld] = c[k];
+    } else {
+        Sample S;
+        S.dry_mass = S.prop_mass = S.dry_cg = S.pf_rate = 0.0; S.cd_scale = 1.0; S.wind = nullptr;
+        S.thrust_a = in[2 * ld]; S.nozzle_area = in[3 * ld]; S.burn_time = in[4 * ld];
+        WindBracket B; wind_bracket_reset(B);
+        out[0] = thrust_at(M, Tb, S, B, in[0], in[ld]);
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Per-stored-state result series, simulator.py:511-552 (_extract_results): one call per stored state.
  * `t_shift` is time[i] = t - t_rail: the reference evaluates the thrust history at the SHIFTED time (:543).
@@ -1053,28 +1111,10 @@ EMC_HD void series_state(const DevModel &M, const DevTables &Tb, const double *w
     const double vxz = fast_sqrt(vbx * vbx + vbz * vbz);
     const double beta = (vxz < 1e-6) ? 0.0 : fast_atan2(vby, vxz);
     /* :535-539 rocket.py:105-108,138-218 */
-    const int jc = brk_find(Tb.cp_lo, Tb.cp_hi, M.n_cp + 1, 1, mach_c);
-    const double cp = M.cp_location + fma(Tb.cp_s[jc], mach_c - Tb.cp_x0[jc], Tb.cp_f[jc]);
-    const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, 1, mach_c);
-    const double dm = mach_c - Tb.cd_x0[jd];
-    const double cd0 = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * S.cd_scale;
-    const double cda = fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]);
-    double cd = cd0 + cda * (alpha * alpha);
-    if (!(s.pf > 0.0)) cd *= M.power_off_factor;
-    const double rad = 4.0 + M.AR_over_cos2 * fabs(1.0 - mach2);
-    const double cl_alpha = M.two_pi_AR_cos / (2.0 + fast_sqrt(rad));
-    double cl = cl_alpha * alpha;
-    const double abs_alpha = fabs(alpha);
-    if (abs_alpha > M.stall_angle) {
-        const double over = (abs_alpha - M.stall_angle) * M.inv_stall_span;
-        double sf = 1.0 - over;
-        sf = (sf > 0.0) ? sf : 0.0;
-        const double sgn = (alpha > 0.0) ? 1.0 : ((alpha < 0.0) ? -1.0 : alpha);
-        cl = cl_alpha * M.stall_angle * sf * sgn;
-        cd *= 1.0 + 0.5 * over;
-    }
+    double co[7];
+    aero_coefficients(M, Tb, mach_c, mach2, alpha, beta, cg, s.pf > 0.0, S.cd_scale, co);
+    const double cd = co[0], cl = co[1], cm = co[2], cp = co[5];
     const double sm = cp - cg;
-    const double cm = -cl_alpha * sm * alpha;
     const double qdyn = 0.5 * rho * v2;                                   /* :541 */
     out[EMC_SER_DRAG * ld] = qdyn * cd * M.ref_area;                      /* :542 */
     WindBracket TB; wind_bracket_reset(TB);

@@ -24,6 +24,16 @@ class StandardAtmosphere:
         self.stratosphere_height = 20000.0
         self.stratosphere_temp = 216.65
 
+    # model-evaluation helpers (environment.py:26-108 of the reference): evaluated on the GPU by the engine
+    def get_properties(self, altitude):
+        from .simulator import _scalar_or_array, evaluate_component
+        o = evaluate_component(0, (altitude,), atmosphere=self)
+        return {k: _scalar_or_array(o[i], altitude) for i, k in enumerate(("temperature", "pressure", "density", "speed_of_sound"))}
+
+    def get_gravity(self, altitude):
+        from .simulator import _scalar_or_array, evaluate_component
+        return _scalar_or_array(evaluate_component(0, (altitude,), atmosphere=self)[4], altitude)
+
 
 def _ar1_coefficients(wind_model, altitudes):
     """Per-knot turbulence scale, AR(1) correlation and innovation scale of environment.py:161-185 /
@@ -49,6 +59,13 @@ class WindModel:
         self.power_law_exponent = 0.14
         self.turbulence_intensity = 2.0
         self.correlation_length = 100.0
+
+    def get_wind_at_altitude(self, altitude, wind_profile, altitude_profile):
+        """Three np.interp calls on the columns of the (N,3) table (environment.py:267-276): plain host table lookup."""
+        wind_profile = np.asarray(wind_profile, float)
+        if len(wind_profile) == 0:
+            return np.array([0.0, 0.0, 0.0])
+        return np.array([np.interp(altitude, altitude_profile, wind_profile[:, k]) for k in range(3)])
 
     def power_law_profile(self, altitude, reference_wind_speed, reference_altitude=10.0):
         return reference_wind_speed * (altitude / reference_altitude) ** self.power_law_exponent

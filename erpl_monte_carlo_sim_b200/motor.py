@@ -45,6 +45,23 @@ class SolidMotor:
         out._thrust_multiplier = k
         return out
 
+    # model-evaluation helpers (motor.py:54-93 / 152-169 of the reference); thrust is evaluated on the GPU by the engine
+    def get_thrust(self, time, ambient_pressure=None):
+        from .simulator import _scalar_or_array, evaluate_component
+        p = 101325.0 if ambient_pressure is None else ambient_pressure
+        a = 1.0 if is_solid(self) else self.thrust_vacuum
+        return _scalar_or_array(evaluate_component(3, (time, p, a, self.nozzle_exit_area, self.burn_time), motor=self)[0], time)
+
+    def get_mass_flow_rate(self, time):
+        return 0.0 if (time < 0 or time > self.burn_time) else self.mass_flow_rate
+
+    def get_propellant_remaining(self, time):
+        if time <= 0:
+            return 1.0
+        if time >= self.burn_time:
+            return 0.0
+        return max(0.0, 1.0 - time / self.burn_time)
+
 
 class LiquidMotor:
     def __init__(self, name="Liquid Motor", thrust_vacuum=2590 * LBF, thrust_sea_level=2290 * LBF,
@@ -67,6 +84,23 @@ class LiquidMotor:
         return LiquidMotor(self.name + "_perturbed", thrust_vacuum=self.thrust_vacuum * k_thrust,
                            thrust_sea_level=self.thrust_sea_level * k_thrust,
                            mass_flow_rate=self.mass_flow_rate * k_flow, propellant_mass=self.propellant_mass)
+
+    # model-evaluation helpers (motor.py:54-93 / 152-169 of the reference); thrust is evaluated on the GPU by the engine
+    def get_thrust(self, time, ambient_pressure=None):
+        from .simulator import _scalar_or_array, evaluate_component
+        p = 101325.0 if ambient_pressure is None else ambient_pressure
+        a = 1.0 if is_solid(self) else self.thrust_vacuum
+        return _scalar_or_array(evaluate_component(3, (time, p, a, self.nozzle_exit_area, self.burn_time), motor=self)[0], time)
+
+    def get_mass_flow_rate(self, time):
+        return 0.0 if (time < 0 or time > self.burn_time) else self.mass_flow_rate
+
+    def get_propellant_remaining(self, time):
+        if time <= 0:
+            return 1.0
+        if time >= self.burn_time:
+            return 0.0
+        return max(0.0, 1.0 - time / self.burn_time)
 
 
 def is_solid(motor) -> bool:

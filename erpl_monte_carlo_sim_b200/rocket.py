@@ -52,3 +52,22 @@ class Rocket:
         if total > 0:
             return (nose_cn * nose_x + 0.0 * 0.0 + fins_cn * fins_x) / total
         return self.length / 2
+
+    # model-evaluation helpers (rocket.py:105-218 of the reference): evaluated on the GPU by the engine
+    def get_mass_properties(self, propellant_fraction_remaining):
+        from .simulator import _scalar_or_array, evaluate_component
+        o = evaluate_component(1, (propellant_fraction_remaining, self.dry_mass, self.propellant_mass), rocket=self)
+        return {k: _scalar_or_array(o[i], propellant_fraction_remaining) for i, k in enumerate(("mass", "center_of_mass", "Ixx", "Iyy", "Izz"))}
+
+    def get_aerodynamic_coefficients(self, mach, alpha, beta=0.0, mass_props=None, power_on=True):
+        from .simulator import _scalar_or_array, evaluate_component
+        cg = self.center_of_mass_dry if mass_props is None else mass_props["center_of_mass"]
+        o = evaluate_component(2, (mach, alpha, beta, cg, 1.0 if power_on else 0.0, 1.0), rocket=self)
+        v = lambda i: _scalar_or_array(o[i], mach)
+        return {"cd": v(0), "cl": v(1), "cm": v(2), "cp": v(5), "cn": v(6), "cy": v(3), "croll": 0.0, "cpitch": v(2), "cyaw": v(4)}
+
+    def get_dynamic_cp(self, mach, alpha=0.0):
+        return self.get_aerodynamic_coefficients(mach, alpha)["cp"]
+
+    def get_stability_margin(self, propellant_fraction_remaining):
+        return (self.cp_location - self.get_mass_properties(propellant_fraction_remaining)["center_of_mass"]) / self.reference_diameter

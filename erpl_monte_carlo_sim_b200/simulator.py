@@ -23,6 +23,22 @@ def get_engine(device: int = 0) -> "_lib.Engine":
     return eng
 
 
+def evaluate_component(comp, columns, rocket=None, motor=None, atmosphere=None, device=0):
+    """Model-evaluation helpers of the parameter classes (get_properties, get_thrust, ...): evaluated by the engine's
+    own device functions (emc_component_debug), never by a host re-implementation."""
+    from .environment import StandardAtmosphere
+    from .motor import LiquidMotor
+    from .rocket import Rocket
+    knobs = type("Knobs", (), dict(max_time=300.0, dt_initial=0.01, pitch_damping=20.0, yaw_damping=20.0))()
+    eng = get_engine(device)
+    eng.set_model(marshal.model_dict(rocket or Rocket(), motor or LiquidMotor(), atmosphere or StandardAtmosphere(), knobs, None))
+    return eng.component(comp, *columns)
+
+
+def _scalar_or_array(v, like):
+    return float(v[0]) if np.ndim(like) == 0 else v
+
+
 class FlightSimulator:
     def __init__(self, rocket, motor, atmosphere, wind_model, device: int = 0):
         self.rocket = rocket

@@ -295,6 +295,18 @@ int emc_stats_select_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64
 int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, double lo, double hi,
                           int nbins, uint64_t *hist_dev /*[nbins], zeroed by the call*/);
 
+/* Component evaluation on arrays (the model-evaluation helpers of the reference's parameter classes, run on the device;
+ * also the component known-answer test seam).  in[k][n] / out[k][n] are HOST, field-major.
+ *   EMC_COMP_ATMOSPHERE  in: altitude                          out: temperature, pressure, density, speed_of_sound, gravity
+ *                        (environment.py:26-108)
+ *   EMC_COMP_MASS        in: propellant_fraction, dry_mass, propellant_mass        out: mass, center_of_mass, Ixx, Iyy, Izz
+ *                        (rocket.py:110-136)
+ *   EMC_COMP_AERO        in: mach, alpha, beta, center_of_mass, power_on(0/1), cd_scale
+ *                        out: cd, cl, cm, cy, cyaw, cp, cn                  (rocket.py:105-108,138-218)
+ *   EMC_COMP_THRUST      in: time, ambient_pressure, thrust_a, nozzle_exit_area, burn_time      out: thrust   (motor.py:54-76,152-156) */
+enum { EMC_COMP_ATMOSPHERE = 0, EMC_COMP_MASS = 1, EMC_COMP_AERO = 2, EMC_COMP_THRUST = 3 };
+int emc_component_debug(emc_ctx *ctx, int component, int64_t n, const double *in, double *out);
+
 /* Test seam: the engine's device math helpers on arrays.  op 0: 1/x, 1: 1/sqrt(x), 2: atan2(y, x),
  * 3: sqrt(x), 4: exp(x), 5: log(x) (as used by the derivative kernel: MUFU seed + Newton / minimax polynomials). */
 int emc_math_debug(emc_ctx *ctx, int op, int64_t n, const double *x, const double *y, double *out);

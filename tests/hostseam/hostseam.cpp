@@ -103,4 +103,15 @@ int hs_series(const emc_model *m, const emc_inputs *in, const double *tape, int6
     return 0;
 }
 
+
+__attribute__((visibility("default")))
+int hs_component(const emc_model *m, int comp, int64_t n, const double *in, double *out)
+{
+    if (validate_model(*m)) return -1;
+    DevModel D; DevTables T;
+    build_dev_model(*m, D, T);
+    for (int64_t i = 0; i < n; ++i) component_eval(D, T, comp, in + i, out + i, n);
+    return 0;
+}
+
 }

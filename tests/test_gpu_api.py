@@ -255,3 +255,20 @@ def test_report_layout_feeds_the_reference_scripts(tmp_path):
                     "thrust", "time", "initial_conditions"):
             assert key in data
     assert best_id >= 0 and best > 20000
+
+
+def test_reference_test_fixes_atmosphere_check():
+    """test_fixes.py:18-38 (the reference's own atmosphere test) against the drop-in classes."""
+    atmosphere = StandardAtmosphere()
+    p20, p30, p40 = (atmosphere.get_properties(a) for a in (20000, 30000, 40000))
+    assert p20["pressure"] > p30["pressure"] > p40["pressure"]
+    assert p40["density"] > 1e-6
+    g = atmosphere.get_gravity(np.array([0.0, 25000.0]))
+    assert abs(g[1] - 9.730137457721826) < 1e-14 and g[0] == 9.80665
+    r = Rocket()
+    mp = r.get_mass_properties(0.5)
+    assert abs(mp["mass"] - 145.15) < 1e-12 and abs(mp["center_of_mass"] - 5.690630382363072) < 1e-14
+    c = r.get_aerodynamic_coefficients(0.9, 0.05, -0.02, mp, True)
+    assert abs(c["cd"] - 0.568375) < 1e-13 and abs(c["cyaw"] - 0.03557241984551255) < 1e-14
+    assert abs(LiquidMotor().get_thrust(1.0, 50000.0) - (2590 * 4.44822 - LiquidMotor().nozzle_exit_area * 50000.0)) < 1e-9
+    assert SolidMotor().get_thrust(20.0) == 0.0 and abs(r.get_stability_margin(1.0) - (r.cp_location - 5.620520067834935) / 0.219) < 1e-12

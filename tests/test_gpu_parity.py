@@ -232,3 +232,15 @@ def test_gpu_math_helpers(engine):
     got, ref = engine.math_debug(2, sp_x, sp_y), np.arctan2(sp_y, sp_x)
     np.testing.assert_allclose(got, ref, rtol=3e-16, atol=0, equal_nan=True)
     assert np.array_equal(np.signbit(got[:4]), np.signbit(ref[:4]))
+
+
+def test_gpu_components_match_reference(engine):
+    """Atmosphere, gravity, mass properties, aerodynamic coefficients and thrust evaluated by the device functions
+    against the reference's own values (components.npz) — SURVEY §4 component KATs."""
+    z = util.golden("components")
+    models = {"liquid": _abi.model_from_npz(z, "liquid_"), "solid": _abi.model_from_npz(z, "solid_")}
+
+    def ev(kind, comp, cols):
+        engine.set_model(models[kind])
+        return engine.component(comp, *cols)
+    util.check_components(ev, z)

@@ -115,3 +115,9 @@ def test_seam_series_match_reference():
         idx, rows, sref = util.series_reference(z, name)
         got = util.hostseam_series(md, sc, wind, rows.copy())
         util.assert_series_close(got, sref, name)
+
+
+def test_seam_components_match_reference():
+    z = util.golden("components")
+    models = {"liquid": _abi.model_from_npz(z, "liquid_"), "solid": _abi.model_from_npz(z, "solid_")}
+    util.check_components(lambda kind, comp, cols: util.hostseam_component(models[kind], comp, cols), z)

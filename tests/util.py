@@ -228,3 +228,32 @@ def hostseam_series(md, scalars, wind, tape_rows):
     rc = HS.hs_series(C.byref(m), C.byref(ins), tape_rows.ctypes.data_as(_dp), C.c_int64(n), out.ctypes.data_as(_dp))
     assert rc == 0
     return out
+
+
+def hostseam_component(md, comp, cols):
+    HS = hostseam_lib()
+    m, keep = _abi.pack_model(md)
+    n_out = {0: 5, 1: 5, 2: 7, 3: 1}[comp]
+    blk = np.ascontiguousarray(np.stack([np.asarray(c, np.float64) for c in np.broadcast_arrays(*cols)], axis=0))
+    n = blk.shape[1]
+    out = np.empty((n_out, n))
+    rc = HS.hs_component(C.byref(m), C.c_int(comp), C.c_int64(n), blk.ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+    assert rc == 0
+    return out
+
+
+def check_components(evaluate, z):
+    """Component known-answer tests against the reference (tests/golden/components.npz); `evaluate(kind, comp, cols)`
+    runs the engine's component functions for the 'liquid' or 'solid' model."""
+    o = evaluate("liquid", 0, (z["atm_z"],))
+    np.testing.assert_allclose(o[:3].T, z["atm_out"], rtol=4e-15)
+    np.testing.assert_allclose(o[4], z["gravity"], rtol=2e-15)
+    o = evaluate("liquid", 1, (z["mp_pf"], 113.4 * z["mp_mult"], 63.5 * z["mp_mult"]))
+    np.testing.assert_allclose(o[:4].T, z["mp_out"], rtol=1e-15)
+    o = evaluate("liquid", 2, (z["aero_mach"], z["aero_alpha"], z["aero_beta"], z["aero_cg"], z["aero_power_on"].astype(float), 1.0))
+    np.testing.assert_allclose(o[[0, 1, 2, 3, 4, 5]].T, z["aero_out"], rtol=2e-14, atol=1e-16)
+    ls, ss = z["liquid_scalars"], z["solid_scalars"]
+    o = evaluate("liquid", 3, (z["thr_t"], z["thr_p"], ls[0], ls[1], ls[3]))
+    np.testing.assert_allclose(o[0], z["thr_liquid"], rtol=1e-15)
+    o = evaluate("solid", 3, (z["thr_t"], z["thr_p"], ss[0], ss[1], ss[3]))
+    np.testing.assert_allclose(o[0], z["thr_solid"], rtol=1e-15)
