@@ -26,6 +26,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE flight-kernel launch on this workload (100 k C3 samples), from
+# `ncu --set full` (profiles/r1_flight_kernel_bench.txt): 31.97 MB + 0.71 MB.  Algorithmic bytes: 30.4 MB in + 30 MB out.
+FLIGHT_KERNEL_DRAM_BYTES_100K = 32.68e6
 STATS_LAUNCHES = 4 + 2 + 3 * 6     # moments1 (+3 finish), moments2 (+1 finish), 3 metrics x 6 radix-select passes
 FLOP_PER_STEP = 1600.0          # 4*348 + 203 ~ 1.6 kflop per accepted RK4 step
 CSV_ALT = np.array([0.0, 5000.0, 10000.0, 15000.0, 20000.0, 25000.0])                # sample_wind.csv:2-7
@@ -266,7 +269,8 @@ def main():
             "replayed_steps_per_trajectory": replay_all / a.steps / n_total,
             "kernel_ms_per_step": {"flight": flight_ms / a.steps, "rail": rail_ms / a.steps},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf * world, "unit": "TFLOP/s",
-                         "frac": achieved_tf / (peak_tf * world), "traffic": None,
+                         "frac": achieved_tf / (peak_tf * world),
+                         "traffic": FLIGHT_KERNEL_DRAM_BYTES_100K if (a.workload == "c3" and n == 100_000) else None, "traffic_unit": "bytes/launch (ncu)",
                          "note": "achieved = whole-job RK4 steps/s x 1600 flop (SURVEY 8d) over the flight kernel's CUDA-event time "
                                  "(max over ranks); peak = in-run DFMA-chain microbenchmark (emc_fp64_peak) x n_gpus"},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
