@@ -557,9 +557,10 @@ static int upload_inputs(emc_ctx *ctx, const emc_inputs *in, int64_t n, KernelAr
 {
     const size_t ns = (size_t)EMC_IN_COUNT * (size_t)n;
     CK(grow(&ctx->d_scalars, &ctx->cap_scalars, ns));
-    /* compact the leading dimension to n on the way up */
-    CK(cudaMemcpy2DAsync(ctx->d_scalars, sizeof(double) * n, in->scalars, sizeof(double) * in->ld, sizeof(double) * n,
-                         EMC_IN_COUNT, cudaMemcpyHostToDevice, ctx->stream));
+    /* compact the leading dimension to n on the way up (one contiguous copy when it already is n) */
+    if (in->ld == n) CK(cudaMemcpyAsync(ctx->d_scalars, in->scalars, sizeof(double) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    else CK(cudaMemcpy2DAsync(ctx->d_scalars, sizeof(double) * n, in->scalars, sizeof(double) * in->ld, sizeof(double) * n,
+                              EMC_IN_COUNT, cudaMemcpyHostToDevice, ctx->stream));
     a.scalars = ctx->d_scalars; a.ld = n;
     if (ctx->dmodel.has_wind) {
         const size_t row = (size_t)ctx->dmodel.n_wind * 3;
@@ -569,8 +570,11 @@ static int upload_inputs(emc_ctx *ctx, const emc_inputs *in, int64_t n, KernelAr
             a.wind_stride = 0;
         } else {
             CK(grow(&ctx->d_wind, &ctx->cap_wind, row * (size_t)n));
-            CK(cudaMemcpy2DAsync(ctx->d_wind, sizeof(double) * row, in->wind, sizeof(double) * in->wind_sample_stride,
-                                 sizeof(double) * row, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+            if (in->wind_sample_stride == (int64_t)row)
+                CK(cudaMemcpyAsync(ctx->d_wind, in->wind, sizeof(double) * row * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+            else
+                CK(cudaMemcpy2DAsync(ctx->d_wind, sizeof(double) * row, in->wind, sizeof(double) * in->wind_sample_stride,
+                                     sizeof(double) * row, (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
             a.wind_stride = (int64_t)row;
         }
         a.wind = ctx->d_wind;
@@ -583,6 +587,11 @@ static int upload_inputs(emc_ctx *ctx, const emc_inputs *in, int64_t n, KernelAr
 
 static int download_outputs(emc_ctx *ctx, const emc_outputs *out, int64_t n)
 {
+    if (out->ld == n) {
+        CK(cudaMemcpyAsync(out->out, ctx->d_out, sizeof(double) * (size_t)EMC_OUT_COUNT * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out->iout, ctx->d_iout, sizeof(int32_t) * (size_t)EMC_IOUT_COUNT * n, cudaMemcpyDeviceToHost, ctx->stream));
+        return EMC_OK;
+    }
     CK(cudaMemcpy2DAsync(out->out, sizeof(double) * out->ld, ctx->d_out, sizeof(double) * n, sizeof(double) * n,
                          EMC_OUT_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpy2DAsync(out->iout, sizeof(int32_t) * out->ld, ctx->d_iout, sizeof(int32_t) * n, sizeof(int32_t) * n,
