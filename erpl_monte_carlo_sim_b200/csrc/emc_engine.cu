@@ -884,9 +884,13 @@ EMC_EXPORT int emc_stats_moments1(emc_ctx *ctx, const double *out_dev, int64_t l
     CK(grow(&ctx->d_partial, &ctx->cap_partial, need));
     double *ps = ctx->d_partial, *pmin = ps + (size_t)g * ST_SUM_COUNT, *pmax = pmin + (size_t)g * ST_MM_COUNT;
     emc_stats_moments1_kernel<<<g, 256, 0, ctx->stream>>>(out_dev, ld, n, ps, pmin, pmax);
-    emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(ps, g, ST_SUM_COUNT, 0, sum_dev);
-    emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(pmin, g, ST_MM_COUNT, 1, min_dev);
-    emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(pmax, g, ST_MM_COUNT, 2, max_dev);
+    if (min_dev == sum_dev + ST_SUM_COUNT && max_dev == min_dev + ST_MM_COUNT) {     /* contiguous result block: one launch */
+        emc_stats_finish3_kernel<<<1, 32, 0, ctx->stream>>>(ps, pmin, pmax, g, sum_dev);
+    } else {
+        emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(ps, g, ST_SUM_COUNT, 0, sum_dev);
+        emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(pmin, g, ST_MM_COUNT, 1, min_dev);
+        emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(pmax, g, ST_MM_COUNT, 2, max_dev);
+    }
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return EMC_OK;
@@ -920,6 +924,30 @@ EMC_EXPORT int emc_stats_select_hist(emc_ctx *ctx, const double *out_dev, int64_
     a.n_prefix = n_prefix; a.field = field; a.shift = shift; a.prefix_shift = prefix_shift;
     CK(cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * (size_t)n_prefix * EMC_SELECT_BINS, ctx->stream));
     emc_stats_select_kernel<<<stats_grid(ctx, n), 256, 0, ctx->stream>>>(out_dev, ld, n, a, reinterpret_cast<unsigned long long *>(hist_dev));
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_stats_select_hist3(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int shift, int prefix_shift,
+                                      const uint64_t *prefixes /*[3][EMC_SELECT_MAX_PREFIX]*/, const int32_t *n_prefix /*[3]*/,
+                                      uint64_t *hist_dev /*[n_prefix[0]+n_prefix[1]+n_prefix[2]][EMC_SELECT_BINS], metric-major*/)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!hist_dev || !prefixes || !n_prefix || shift < 0 || shift > 63) return fail(ctx, EMC_ERR_INVALID, "emc_stats_select_hist3: bad argument");
+    Select3Args a;
+    memset(&a, 0, sizeof a);
+    for (int f = 0; f < 3; ++f) {
+        if (n_prefix[f] < 0 || n_prefix[f] > EMC_SELECT_MAX_PREFIX) return fail(ctx, EMC_ERR_INVALID, "emc_stats_select_hist3: n_prefix");
+        a.n_prefix[f] = n_prefix[f];
+        for (int u = 0; u < n_prefix[f]; ++u) a.prefix[f][u] = prefixes[f * EMC_SELECT_MAX_PREFIX + u];
+    }
+    a.row0[0] = 0; a.row0[1] = n_prefix[0]; a.row0[2] = n_prefix[0] + n_prefix[1];
+    const size_t rows = (size_t)(n_prefix[0] + n_prefix[1] + n_prefix[2]);
+    a.shift = shift; a.prefix_shift = prefix_shift;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(hist_dev, 0, sizeof(uint64_t) * rows * EMC_SELECT_BINS, ctx->stream));
+    emc_stats_select3_kernel<<<stats_grid(ctx, n), 256, 0, ctx->stream>>>(out_dev, ld, n, a, reinterpret_cast<unsigned long long *>(hist_dev));
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
     return EMC_OK;

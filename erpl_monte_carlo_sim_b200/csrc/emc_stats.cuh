@@ -142,6 +142,52 @@ struct SelectArgs {
     int n_prefix, field, shift, prefix_shift;     /* digit = (key >> shift) & (BINS-1); prefix = key >> prefix_shift (64 -> all match) */
 };
 
+/* all three metrics in one pass over the samples: hist[f][u][digit] */
+struct Select3Args {
+    unsigned long long prefix[3][EMC_SELECT_MAX_PREFIX];
+    int n_prefix[3], row0[3];          /* rows of metric f start at row0[f] in the compact histogram block */
+    int shift, prefix_shift;
+};
+
+__global__ void __launch_bounds__(256) emc_stats_select3_kernel(const double *out, int64_t ld, int64_t n, Select3Args a,
+                                                                unsigned long long *hist /*[n_prefix[0]+n_prefix[1]+n_prefix[2]][BINS], metric-major*/)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v[3] = { out[EMC_OUT_APOGEE_ALTITUDE * ld + i], out[EMC_OUT_RANGE * ld + i], out[EMC_OUT_FLIGHT_TIME * ld + i] };
+        int why;
+        if (classify_outlier(v[0], v[1], v[2], &why)) continue;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const unsigned long long key = ordered_key(v[f]);
+            const unsigned long long pre = (a.prefix_shift >= 64) ? 0ull : (key >> a.prefix_shift);
+            const unsigned digit = (unsigned)((key >> a.shift) & (EMC_SELECT_BINS - 1));
+            for (int u = 0; u < a.n_prefix[f]; ++u)
+                if (pre == a.prefix[f][u]) atomicAdd(&hist[(size_t)(a.row0[f] + u) * EMC_SELECT_BINS + digit], 1ull);
+        }
+    }
+}
+
+/* min, max and sum partials finished by ONE launch: result = [sum block | min block | max block] */
+__global__ void emc_stats_finish3_kernel(const double *p_sum, const double *p_min, const double *p_max, int nblocks, double *result)
+{
+    const int k = threadIdx.x;
+    if (k < ST_SUM_COUNT) {
+        double x = p_sum[k];
+        for (int b = 1; b < nblocks; ++b) x += p_sum[(size_t)b * ST_SUM_COUNT + k];
+        result[k] = x;
+    } else if (k < ST_SUM_COUNT + ST_MM_COUNT) {
+        const int j = k - ST_SUM_COUNT;
+        double x = p_min[j];
+        for (int b = 1; b < nblocks; ++b) x = fmin(x, p_min[(size_t)b * ST_MM_COUNT + j]);
+        result[k] = x;
+    } else if (k < ST_SUM_COUNT + 2 * ST_MM_COUNT) {
+        const int j = k - ST_SUM_COUNT - ST_MM_COUNT;
+        double x = p_max[j];
+        for (int b = 1; b < nblocks; ++b) x = fmax(x, p_max[(size_t)b * ST_MM_COUNT + j]);
+        result[k] = x;
+    }
+}
+
 __global__ void __launch_bounds__(256) emc_stats_select_kernel(const double *out, int64_t ld, int64_t n, SelectArgs a,
                                                                unsigned long long *hist /*[n_prefix][BINS]*/)
 {

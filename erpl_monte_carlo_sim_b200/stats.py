@@ -67,7 +67,7 @@ class DeviceBackend:
         self.out_ptr = C.c_void_p(out_dev) if out_dev else None
         self.ld = int(ld) if ld is not None else 0
         self.distributed = _dist_active() if distributed is None else bool(distributed)
-        words = NSUM + 2 * NMM + 5 + N2 + MAXP * BINS
+        words = NSUM + 2 * NMM + 5 + N2 + 3 * MAXP * BINS
         base = C.c_void_p()
         engine._check(engine._lib.emc_scratch(engine._ctx, words * 8, C.byref(base)), "emc_scratch")
         self.base = base.value
@@ -92,7 +92,26 @@ class DeviceBackend:
         e._check(e._lib.emc_stats_moments1(e._ctx, self.out_ptr, self.ld, self.n, vp(bs.ptr), vp(bmin.ptr), vp(bmax.ptr)),
                  "emc_stats_moments1")
         self._reduce(bs, "sum"); self._reduce(bmin, "min"); self._reduce(bmax, "max")
-        return bs.get(), bmin.get(), bmax.get()
+        allv = self._blk(0, NSUM + 2 * NMM).get()                 # one device->host copy for the three blocks
+        return allv[:NSUM], allv[NSUM:NSUM + NMM], allv[NSUM + NMM:]
+
+    def select_hist3(self, shift, prefix_shift, prefix_lists):
+        """One pass over the samples for all three metrics: prefix_lists[f] = list of prefixes of metric f."""
+        e = self.e
+        pre = (C.c_uint64 * (3 * MAXP))()
+        cnt = (C.c_int32 * 3)()
+        for f in range(3):
+            cnt[f] = len(prefix_lists[f])
+            for u, p in enumerate(prefix_lists[f]):
+                pre[f * MAXP + u] = p
+        rows = sum(len(p) for p in prefix_lists)
+        bh = self._blk(NSUM + 2 * NMM + 5 + N2, rows * BINS, np.uint64)          # compact: only the rows in use
+        e._check(e._lib.emc_stats_select_hist3(e._ctx, self.out_ptr, self.ld, self.n, shift, prefix_shift, pre, cnt,
+                                               C.c_void_p(bh.ptr)), "emc_stats_select_hist3")
+        self._reduce(bh, "sum")
+        h = bh.get().view(np.int64).reshape(rows, BINS)
+        edges = np.cumsum([0] + [len(p) for p in prefix_lists])
+        return [h[edges[f]:edges[f + 1]] for f in range(3)]
 
     def moments2(self, center):
         e, vp = self.e, C.c_void_p
@@ -135,6 +154,27 @@ def _lerp(a, b, t):
     """numpy/lib/_function_base_impl.py::_lerp — the interpolation np.percentile(method='linear') applies."""
     d = b - a
     return b - d * (1 - t) if t >= 0.5 else a + d * t
+
+
+def radix_select3(backend, ranks):
+    """radix_select for the three metrics in lockstep (one pass over the samples per digit) when the backend offers
+    `select_hist3` and every metric needs <= MAXP distinct prefixes; otherwise metric by metric."""
+    if not hasattr(backend, "select_hist3") or len(ranks) > MAXP:
+        return [radix_select(backend, f, ranks) for f in range(3)]
+    targets = [{r: (0, r) for r in ranks} for _ in range(3)]
+    for shift, pshift in SELECT_PASSES:
+        width = (64 - shift) if pshift >= 64 else (pshift - shift)
+        uniq = [sorted({t[0] for t in targets[f].values()}) for f in range(3)]
+        hists = backend.select_hist3(shift, pshift, uniq)
+        for f in range(3):
+            cums = {pre: np.cumsum(hists[f][u]) for u, pre in enumerate(uniq[f])}
+            nxt = {}
+            for r, (pre, rem) in targets[f].items():
+                cum = cums[pre]
+                b = int(np.searchsorted(cum, rem, side="right"))
+                nxt[r] = ((pre << width) | b, rem - (int(cum[b - 1]) if b > 0 else 0))
+            targets[f] = nxt
+    return [{r: _key_to_double(t[0]) for r, t in targets[f].items()} for f in range(3)]
 
 
 def radix_select(backend, field, ranks):
@@ -183,8 +223,9 @@ def compute_statistics(backend, histogram_bins=0):
     hi_idx = np.minimum(lo_idx + 1, m - 1)
     gamma = pos - lo_idx
     ranks = sorted(set(lo_idx.tolist()) | set(hi_idx.tolist()))
+    vals = radix_select3(backend, ranks)
     for f, key in enumerate(METRICS):
-        val = radix_select(backend, f, ranks)
+        val = vals[f]
         res[key]["percentiles"] = [float(_lerp(val[int(a)], val[int(b)], g)) for a, b, g in zip(lo_idx, hi_idx, gamma)]
     if histogram_bins:
         res["histograms"] = {}

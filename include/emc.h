@@ -291,6 +291,11 @@ int emc_stats_select_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64
                           int prefix_shift, const uint64_t *prefixes /*host, [n_prefix]*/, int n_prefix,
                           uint64_t *hist_dev /*[n_prefix][EMC_SELECT_BINS], zeroed by the call*/);
 
+/* the same digit pass for all three metrics at once: prefixes[3][EMC_SELECT_MAX_PREFIX] (host), n_prefix[3],
+ * hist_dev[n_prefix[0]+n_prefix[1]+n_prefix[2]][EMC_SELECT_BINS] (compact, metric-major) */
+int emc_stats_select_hist3(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int shift, int prefix_shift,
+                           const uint64_t *prefixes, const int32_t *n_prefix, uint64_t *hist_dev);
+
 /* fixed-bin histogram over the valid samples; field 0 apogee, 1 range, 2 flight_time, 3 landing x, 4 landing y */
 int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, double lo, double hi,
                           int nbins, uint64_t *hist_dev /*[nbins], zeroed by the call*/);
