@@ -283,7 +283,7 @@ EMC_HD double fast_atan2(double y, double x)
  * follows then yields NaN, which is np.interp's answer) */
 EMC_HD int brk_find(const double *lo, const double *hi, int nb, int j, double x)
 {
-    if (!(x >= lo[j] && x < hi[j]) && (x == x)) {
+    if (!(x >= lo[j] && x < hi[j])) {          /* rare; a NaN x fails both searches and keeps j */
         while (j < nb - 1 && x >= hi[j]) ++j;
         while (j > 0 && x < lo[j]) --j;
     }
@@ -687,10 +687,17 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int i = 0; i < 14; ++i) {
-                const double ki = kk[i];
-                st.set_acc(i, (stage == 0) ? ki : fma(2.0, ki, st.acc(i)));
-                y[i] = fma(c, ki, st.s(i));
+            for (int i = 0; i < 14; ++i) y[i] = fma(c, kk[i], st.s(i));
+            if (stage == 0) {                         /* warp-uniform: stage 0 only stores, stages 1-2 accumulate */
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int i = 0; i < 14; ++i) st.set_acc(i, kk[i]);
+            } else {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int i = 0; i < 14; ++i) st.set_acc(i, fma(2.0, kk[i], st.acc(i)));
             }
         } else {
 #if defined(__CUDA_ARCH__)
