@@ -91,7 +91,10 @@ def load():
     L.emc_run_batch_staged.argtypes = [vp, i64, C.POINTER(_abi.EmcOutputs), C.POINTER(_abi.EmcRunOpts)]
     L.emc_staged_inputs.argtypes = [vp, i64, _dp, _dp]
     L.emc_philox_draws.argtypes = [vp, C.c_uint64, i64, i64, i64, _dp, _dp]
-    for name in ("emc_generate_inputs", "emc_run_batch_staged", "emc_staged_inputs", "emc_philox_draws"):
+    L.emc_generate_inputs_numpy.argtypes = [vp, C.POINTER(_abi.EmcDispersion), i64, i64, vp, i64, vp]
+    L.emc_numpy_draws.argtypes = [vp, i64, i64, i64, _dp, _dp, _dp]
+    for name in ("emc_generate_inputs", "emc_run_batch_staged", "emc_staged_inputs", "emc_philox_draws", "emc_generate_inputs_numpy",
+                 "emc_numpy_draws"):
         getattr(L, name).restype = C.c_int
     L.emc_extract_series.argtypes = [vp, C.POINTER(_abi.EmcInputs), _dp, i64, _dp]
     L.emc_extract_series.restype = C.c_int
@@ -235,6 +238,20 @@ class Engine:
                                                   C.c_void_p(scalars_ptr) if scalars_ptr else None, ld,
                                                   C.c_void_p(wind_ptr) if wind_ptr else None), "emc_generate_inputs")
         self._staged_knots = int(d.n_knots)
+
+    def generate_inputs_numpy(self, disp, first_seed, n, scalars_ptr=None, ld=0, wind_ptr=None):
+        """The reference's own MT19937 / legacy-Gaussian streams (seed = first_seed + i) regenerated on the device."""
+        d, _keep = disp
+        self._check(self._lib.emc_generate_inputs_numpy(self._ctx, C.byref(d), first_seed, n,
+                                                        C.c_void_p(scalars_ptr) if scalars_ptr else None, ld,
+                                                        C.c_void_p(wind_ptr) if wind_ptr else None), "emc_generate_inputs_numpy")
+        self._staged_knots = int(d.n_knots)
+
+    def numpy_draws(self, first_seed, n, n_gauss):
+        g = np.empty((n, n_gauss), np.float64); u = np.empty((n, 2), np.float64); d = np.empty(n, np.float64)
+        self._check(self._lib.emc_numpy_draws(self._ctx, first_seed, n, n_gauss, g.ctypes.data_as(_dp), u.ctypes.data_as(_dp),
+                                              d.ctypes.data_as(_dp)), "emc_numpy_draws")
+        return g, u, d
 
     def run_batch_staged(self, n, opts=None):
         outs, out, iout = _abi.outputs_alloc(n)

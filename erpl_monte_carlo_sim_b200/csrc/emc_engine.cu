@@ -698,9 +698,54 @@ EMC_EXPORT int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t 
 /* ---------------------------------------------------------------------------------------------------
  *  device-side dispersions
  * ------------------------------------------------------------------------------------------------- */
+static int generate_core(emc_ctx *ctx, const emc_dispersion *d, uint64_t seed, int64_t first_index, int64_t n,
+                         const double *gauss, int64_t n_gauss, const double *unif, int draws_on_device,
+                         double *scalars_dev, int64_t ld, double *wind_dev);
+
 EMC_EXPORT int emc_generate_inputs(emc_ctx *ctx, const emc_dispersion *d, uint64_t seed, int64_t first_index, int64_t n,
                                    const double *gauss, int64_t n_gauss, const double *unif,
                                    double *scalars_dev, int64_t ld, double *wind_dev)
+{
+    return generate_core(ctx, d, seed, first_index, n, gauss, n_gauss, unif, 0, scalars_dev, ld, wind_dev);
+}
+
+static int numpy_draws_device(emc_ctx *ctx, int64_t first_seed, int64_t n, int64_t G, double **g_dev, double **u_dev)
+{
+    CK(cudaSetDevice(ctx->device));
+    CK(grow(&ctx->d_draws, &ctx->cap_draws, (size_t)n * (size_t)(G + 3)));
+    *g_dev = ctx->d_draws; *u_dev = ctx->d_draws + (size_t)n * G;
+    emc_numpy_draws_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(first_seed, n, G, *g_dev, *u_dev, *u_dev + 2 * (size_t)n);
+    CK(cudaGetLastError());
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_numpy_draws(emc_ctx *ctx, int64_t first_seed, int64_t n, int64_t n_gauss, double *gauss, double *unif, double *density)
+{
+    if (!ctx || !gauss || !unif || n < 0 || n_gauss < 14) return fail(ctx, EMC_ERR_INVALID, "emc_numpy_draws: bad argument (n_gauss >= 14)");
+    if (n == 0) return EMC_OK;
+    double *g = nullptr, *u = nullptr;
+    if (int rc = numpy_draws_device(ctx, first_seed, n, n_gauss, &g, &u)) return rc;
+    CK(cudaMemcpyAsync(gauss, g, sizeof(double) * (size_t)n * n_gauss, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(unif, u, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (density) CK(cudaMemcpyAsync(density, u + 2 * (size_t)n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_generate_inputs_numpy(emc_ctx *ctx, const emc_dispersion *d, int64_t first_seed, int64_t n,
+                                         double *scalars_dev, int64_t ld, double *wind_dev)
+{
+    if (!ctx || !d || n < 0) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs_numpy: bad argument");
+    if (n == 0) return generate_core(ctx, d, 0, first_seed, 0, nullptr, 0, nullptr, 0, scalars_dev, ld, wind_dev);
+    const int64_t G = (3 * (int64_t)d->n_knots > 15) ? 3 * (int64_t)d->n_knots : 15;
+    double *g = nullptr, *u = nullptr;
+    if (int rc = numpy_draws_device(ctx, first_seed, n, G, &g, &u)) return rc;
+    return generate_core(ctx, d, 0, first_seed, n, g, G, u, 1, scalars_dev, ld, wind_dev);
+}
+
+static int generate_core(emc_ctx *ctx, const emc_dispersion *d, uint64_t seed, int64_t first_index, int64_t n,
+                         const double *gauss, int64_t n_gauss, const double *unif, int draws_on_device,
+                         double *scalars_dev, int64_t ld, double *wind_dev)
 {
     if (!ctx || !d || n < 0) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: bad argument");
     if (d->n_knots < 0 || d->n_knots > EMC_MAX_WIND_KNOTS) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: n_knots");
@@ -733,7 +778,8 @@ EMC_EXPORT int emc_generate_inputs(emc_ctx *ctx, const emc_dispersion *d, uint64
         D.scale0 = d->innov[0];
     }
     const double *g_dev = nullptr, *u_dev = nullptr;
-    if (gauss || unif) {
+    if (draws_on_device) { g_dev = gauss; u_dev = unif; }
+    else if (gauss || unif) {
         if (!gauss || !unif) return fail(ctx, EMC_ERR_INVALID, "emc_generate_inputs: gauss and unif must be given together");
         CK(grow(&ctx->d_draws, &ctx->cap_draws, (size_t)n * (size_t)(n_gauss + 2)));
         CK(cudaMemcpyAsync(ctx->d_draws, gauss, sizeof(double) * (size_t)n * n_gauss, cudaMemcpyHostToDevice, ctx->stream));

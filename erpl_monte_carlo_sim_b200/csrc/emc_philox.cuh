@@ -174,4 +174,84 @@ __global__ void emc_philox_draws_kernel(uint64_t seed, int64_t first, int64_t n,
     unif[2 * i] = a; unif[2 * i + 1] = b;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * NumPy-compatible draws on the device: MT19937 seeded like np.random.seed(i) / RandomState(i) (init_genrand) and
+ * NumPy's legacy Gaussian (polar method with the cached second value) and 53-bit doubles.  One thread regenerates
+ * the stream of ONE sample seed: gauss[i][0..G) are the first G standard normals of RandomState(seed) — the stream the
+ * motor perturbation and the wind generator consume (monte_carlo.py:274,287,323) and whose first 14 values are also the
+ * parameter draws (np.random.seed(i), monte_carlo.py:162-170) — and unif[i] the two uniforms that follow
+ * those 14 normals in the parameter stream (:171-172), dens[i] the normal after them (:173).  Same bits as NumPy except where CUDA's log/sqrt differ from
+ * the host libm in the last place.
+ * ---------------------------------------------------------------------------------------------- */
+struct MT19937 {
+    uint32_t mt[624];
+    int pos;
+    __device__ void seed(uint32_t s)
+    {
+        for (int i = 0; i < 624; ++i) { mt[i] = s; s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1); }
+        pos = 624;
+    }
+    __device__ void twist()
+    {
+        const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, A = 0x9908b0dfu;
+        int k = 0;
+        for (; k < 624 - 397; ++k) { const uint32_t y = (mt[k] & UP) | (mt[k + 1] & LO); mt[k] = mt[k + 397] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+        for (; k < 623; ++k) { const uint32_t y = (mt[k] & UP) | (mt[k + 1] & LO); mt[k] = mt[k + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? A : 0u); }
+        const uint32_t y = (mt[623] & UP) | (mt[0] & LO);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? A : 0u);
+        pos = 0;
+    }
+    __device__ uint32_t next32()
+    {
+        if (pos == 624) twist();
+        uint32_t y = mt[pos++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    __device__ double next_double()
+    {
+        const uint32_t a = next32() >> 5, b = next32() >> 6;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+    /* one polar-method pair: first = f*x2 (returned first by legacy_gauss), second = f*x1 (the cached value) */
+    __device__ void gauss_pair(double &first, double &second)
+    {
+        double x1, x2, r2;
+        do {
+            x1 = 2.0 * next_double() - 1.0;
+            x2 = 2.0 * next_double() - 1.0;
+            r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));     /* no FMA contraction: near r2 = 1 one ulp of r2 is 1e-13 of log(r2) */
+        } while (r2 >= 1.0 || r2 == 0.0);
+        const double f = sqrt(-2.0 * log(r2) / r2);
+        first = f * x2; second = f * x1;
+    }
+};
+
+__global__ void __launch_bounds__(64) emc_numpy_draws_kernel(int64_t first_seed, int64_t n, int64_t G, double *gauss, double *unif, double *dens)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    MT19937 rng;
+    rng.seed((uint32_t)((uint64_t)(first_seed + i) & 0xffffffffu));
+    double *g = gauss + i * G;
+    for (int64_t k = 0; k < G; k += 2) {
+        double a, b;
+        rng.gauss_pair(a, b);
+        g[k] = a;
+        if (k + 1 < G) g[k + 1] = b;
+        if (k == 12) {
+            /* after the 7th pair (14 normals) the PARAMETER stream draws two uniforms; the wind/motor stream goes on with
+             * more normals from the same position.  Both read the same not-yet-overwritten first block of 624 words
+             * (7 pairs consume ~36 words), so they are taken with a copy of the cursor. */
+            const int keep = rng.pos;
+            unif[2 * i] = rng.next_double();
+            unif[2 * i + 1] = rng.next_double();
+            double d0, d1;
+            rng.gauss_pair(d0, d1);                 /* the parameter stream's 15th normal (density multiplier, :173) */
+            dens[i] = d0;
+            rng.pos = keep;
+        }
+    }
+}
+
 }  // namespace emc

@@ -145,7 +145,10 @@ class MonteCarloAnalyzer:
         self.chunk_size = 1 << 16
         self.run_opts = None
         self.histogram_bins = 0
-        self.rng = "numpy"          # "numpy": the reference's own MT19937 streams (bit-matched inputs); "philox": drawn on the GPU
+        # "numpy": the reference's own MT19937 streams drawn on the host (bit-matched inputs)
+        # "numpy-device": the same streams regenerated on the GPU (same bits up to the last place of log/sqrt)
+        # "philox": counter-based draws on the GPU (same distribution and stream structure)
+        self.rng = "numpy"
         self.philox_seed = 0
         self.last_run = None
 
@@ -312,9 +315,18 @@ class MonteCarloAnalyzer:
     def philox_parameters(self, n, first_index=0) -> DispersionSet:
         """The parameter samples the device generator draws for indices first_index.. (from the same Philox bits)."""
         from . import philox
-        up = self.uncertainty_params
         idx = np.arange(first_index, first_index + n, dtype=np.uint64)
-        g = philox.normals(self.philox_seed, idx, 15); u = philox.uniforms(self.philox_seed, idx)
+        return self._parameters_from_draws(philox.normals(self.philox_seed, idx, 15), philox.uniforms(self.philox_seed, idx), idx)
+
+    def numpy_device_parameters(self, n, first_seed=0) -> DispersionSet:
+        """draw_parameters() from the MT19937 streams the device regenerates (no per-sample host loop)."""
+        g, u, dens = get_engine(self.device).numpy_draws(first_seed, n, 15)
+        g[:, 14] = dens
+        return self._parameters_from_draws(g, u, np.arange(first_seed, first_seed + n, dtype=np.uint64))
+
+    def _parameters_from_draws(self, g, u, idx) -> DispersionSet:
+        up = self.uncertainty_params
+        n = len(idx)
         d = DispersionSet(n)
         d.pos[:] = np.asarray(up["initial_position"], float) * g[:, 0:3]; d.vel[:] = np.asarray(up["initial_velocity"], float) * g[:, 3:6]
         d.att[:] = np.asarray(up["initial_attitude"], float) * g[:, 6:9]; d.omega[:] = np.asarray(up["initial_angular_velocity"], float) * g[:, 9:12]
@@ -325,7 +337,12 @@ class MonteCarloAnalyzer:
         d.seed[:] = idx.astype(np.int64)
         return d
 
-    def run_batch_philox(self, initial_conditions, n, first_index=0) -> BatchRun:
+    def run_batch_numpy_device(self, initial_conditions, n, first_seed=0) -> BatchRun:
+        """Host-seeded semantics without the host: MT19937(seed = sample index) and NumPy's legacy Gaussian regenerated,
+        perturbed and flown on the GPU."""
+        return self.run_batch_philox(initial_conditions, n, first_index=first_seed, numpy_streams=True)
+
+    def run_batch_philox(self, initial_conditions, n, first_index=0, numpy_streams=False) -> BatchRun:
         """Draw, perturb and fly n samples entirely on the GPU (no host input generation, no input upload)."""
         eng = get_engine(self.device)
         alts = self._altitude_grid()
@@ -334,12 +351,15 @@ class MonteCarloAnalyzer:
         out = np.empty((_abi.OUT_COUNT, n)); iout = np.empty((_abi.IOUT_COUNT, n), np.int32); scal = np.empty((_abi.IN_COUNT, n))
         for lo in range(0, n, self.chunk_size):
             hi = min(n, lo + self.chunk_size)
-            eng.generate_inputs(disp_struct, self.philox_seed, first_index + lo, hi - lo)
+            if numpy_streams:
+                eng.generate_inputs_numpy(disp_struct, first_index + lo, hi - lo)
+            else:
+                eng.generate_inputs(disp_struct, self.philox_seed, first_index + lo, hi - lo)
             o, io = eng.run_batch_staged(hi - lo, opts=self.run_opts)
             out[:, lo:hi] = o; iout[:, lo:hi] = io
             scal[:, lo:hi] = eng.staged_inputs(hi - lo, want_wind=False)[0]
-        self.last_run = BatchRun(self, dict(initial_conditions), self.philox_parameters(n, first_index), out, iout, alts, scal,
-                                 outputs_resident=(n <= self.chunk_size))
+        params = self.numpy_device_parameters(n, first_index) if numpy_streams else self.philox_parameters(n, first_index)
+        self.last_run = BatchRun(self, dict(initial_conditions), params, out, iout, alts, scal, outputs_resident=(n <= self.chunk_size))
         return self.last_run
 
     def _model_simulator(self):
@@ -370,6 +390,8 @@ class MonteCarloAnalyzer:
             return self.run_optimized_monte_carlo(initial_conditions, n_samples)
         if self.rng == "philox":
             return self._analyze_run(self.run_batch_philox(initial_conditions, n_samples))
+        if self.rng == "numpy-device":
+            return self._analyze_run(self.run_batch_numpy_device(initial_conditions, n_samples))
         disp = self.draw_parameters(n_samples)
         run = self.run_batch(initial_conditions, disp)
         return self._analyze_run(run)

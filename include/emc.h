@@ -222,6 +222,16 @@ typedef struct emc_dispersion {
 int emc_generate_inputs(emc_ctx *ctx, const emc_dispersion *d, uint64_t seed, int64_t first_index, int64_t n,
                         const double *gauss, int64_t n_gauss, const double *unif,
                         double *scalars_dev, int64_t ld, double *wind_dev);
+/* The same, with the reference's OWN streams regenerated on the device: sample i uses MT19937 seeded with
+ * first_seed + i (np.random.seed(i) / RandomState(i)) and NumPy's legacy polar Gaussian — the draws a host-seeded run
+ * uploads, without the host loop.  scalars_dev/wind_dev as above (NULL = stage inside the context). */
+int emc_generate_inputs_numpy(emc_ctx *ctx, const emc_dispersion *d, int64_t first_seed, int64_t n,
+                              double *scalars_dev, int64_t ld, double *wind_dev);
+/* the device-regenerated NumPy draws themselves: gauss[n][n_gauss] (RandomState(seed).standard_normal(n_gauss)) and
+ * unif[n][2] (the two random_sample() values that follow the first 14 normals in the parameter stream) and, if not
+ * NULL, density[n] (the normal drawn after them); host arrays */
+int emc_numpy_draws(emc_ctx *ctx, int64_t first_seed, int64_t n, int64_t n_gauss, double *gauss, double *unif, double *density);
+
 /* fly the n samples staged by emc_generate_inputs(..., NULL, 0, NULL); outputs to host buffers */
 int emc_run_batch_staged(emc_ctx *ctx, int64_t n, const emc_outputs *out, const emc_run_opts *opts);
 /* copy the staged inputs back (either pointer may be NULL): scalars[EMC_IN_COUNT][n], wind[n][n_knots][3] */

@@ -114,3 +114,47 @@ def test_philox_monte_carlo_end_to_end():
     assert abs(np.median(steps_p[steps_p < 10000]) / np.median(steps_h[steps_h < 10000]) - 1) < 0.03
     an = mc.run_monte_carlo(ic, n_samples=2000)
     assert an["n_samples"] + an["n_outliers"] == 2000 and an["results"][0]["parameters"]["random_seed"] >= 0
+
+
+@pytest.mark.gpu
+def test_device_regenerates_numpy_streams(engine):
+    """MT19937 + NumPy's legacy Gaussian on the device: uniforms bit-identical, normals within 4 ulp of NumPy's
+    (CUDA log/sqrt vs libm), for small and large seeds and more than one block of 624 words."""
+    seeds = [0, 1, 2, 41, 99999, 123456789]
+    for first in seeds:
+        g, u, dens = engine.numpy_draws(first, 3, 300)
+        for i in range(3):
+            rs = np.random.RandomState(first + i)
+            a = rs.standard_normal(14); uu = rs.random_sample(2); dd = rs.standard_normal()
+            ref = np.random.RandomState(first + i).standard_normal(300)
+            np.testing.assert_array_equal(u[i], uu)
+            assert np.max(np.abs(g[i] - ref) / np.spacing(np.abs(ref))) <= 4.0
+            assert abs(dens[i] - dd) <= 4.0 * np.spacing(abs(dd))
+            np.testing.assert_array_equal(ref[:14], a)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("solid,csv,name", [(False, False, "mc_liquid_default"), (True, True, "mc_solid_csv")])
+def test_numpy_device_mode_matches_host_seeded_goldens(engine, solid, csv, name):
+    """rng = "numpy-device": inputs regenerated on the GPU equal the reference's host-seeded inputs to rounding and the
+    flights match the reference's goldens."""
+    z = util.golden(name)
+    mc = _mc(solid, csv)
+    n = z["scalars"].shape[1]
+    b = z["base_ic"]
+    ic = {"position": b[0], "velocity": b[1], "attitude": b[2], "angular_velocity": b[3]}
+    engine.set_model(_abi.model_from_npz(z))
+    engine.generate_inputs_numpy(mc.dispersion_struct(ic), 0, n)
+    sc, wind = engine.staged_inputs(n)
+    np.testing.assert_allclose(sc, z["scalars"], rtol=5e-15, atol=1e-16)
+    np.testing.assert_allclose(wind, z["wind"], rtol=1e-12, atol=1e-13)
+    run = mc.run_batch_numpy_device(ic, n)
+    np.testing.assert_array_equal(run.iout, z["iout"])
+    util.assert_summary_close(run.out, z["out"], what="numpy-device " + name,
+                              sens=util.oracle_sensitivity(_abi.model_from_npz(z), z["scalars"], z["wind"]))
+    np.testing.assert_allclose(_param_matrix(run.disp), z["params"], rtol=5e-15, atol=1e-17)
+
+
+def _param_matrix(d):
+    return np.column_stack([d.pos, d.vel, d.att, d.omega, d.mass_multiplier, d.thrust_multiplier, d.wind_speed, d.wind_direction,
+                            d.density_multiplier])
