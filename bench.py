@@ -125,6 +125,21 @@ def secondary_measurements(eng, opts, peak_tf):
     return out
 
 
+def hbm_side(blk, wind, h_out, h_iout, flight_ms, world):
+    """The same launch against the HBM roof (to show which roof binds): algorithmic bytes = inputs read once + outputs
+    written once, over the flight kernel's time; peak from MEASURED_PEAKS.json (driver-written) or the recipe's fallback."""
+    peak, src = 6650.0, "of fallback (B200_PROFILING.md)"
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peak, src = float(json.load(f)["hbm_gbs"]), "of measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    alg = float(blk.nbytes + wind.nbytes + h_out.nbytes + h_iout.nbytes)
+    ach = alg * world / (flight_ms * 1e-3) / 1e9
+    return {"algorithmic_bytes_per_launch": alg, "achieved": ach, "peak": peak * world, "unit": "GB/s", "frac": ach / (peak * world),
+            "peak_source": src}
+
+
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -272,7 +287,8 @@ def main():
                          "frac": achieved_tf / (peak_tf * world),
                          "traffic": FLIGHT_KERNEL_DRAM_BYTES_100K if (a.workload == "c3" and n == 100_000) else None, "traffic_unit": "bytes/launch (ncu)",
                          "note": "achieved = whole-job RK4 steps/s x 1600 flop (SURVEY 8d) over the flight kernel's CUDA-event time "
-                                 "(max over ranks); peak = in-run DFMA-chain microbenchmark (emc_fp64_peak) x n_gpus"},
+                                 "(max over ranks); peak = in-run DFMA-chain microbenchmark (emc_fp64_peak) x n_gpus",
+                         "hbm": hbm_side(blk, wind, h_out, h_iout, flight_ms / a.steps, world)},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
                     "h2d_bytes_per_step": int(blk.nbytes + wind.nbytes), "d2h_bytes_per_step": int(h_out.nbytes + h_iout.nbytes)},
             "gpu_launches": (2 + STATS_LAUNCHES) * a.steps * world,
