@@ -146,11 +146,10 @@ EMC_HD double fast_rcp(double x)
 #if defined(__CUDA_ARCH__)
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    return r;
+    /* one cubic step from the ~20-bit seed: r (1 + e + e^2), e = 1 - x r; error e^3 ~ 2^-60 */
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
 #else
     return 1.0 / x;
 #endif
@@ -161,13 +160,10 @@ EMC_HD double fast_rsqrt(double x)
 #if defined(__CUDA_ARCH__)
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double h = 0.5 * y;
-    double e = fma(-x * y, y, 1.0);          /* 1 - x*y^2 */
-    y = fma(h, e, y);
-    h = 0.5 * y;
-    e = fma(-x * y, y, 1.0);
-    y = fma(h, e, y);
-    return y;
+    /* one cubic step from the ~20-bit seed: y (1 + e/2 + 3 e^2/8), e = 1 - x y^2; error ~ e^3 */
+    const double e = fma(-x * y, y, 1.0);
+    const double t = fma(0.375, e, 0.5) * e;
+    return fma(y, t, y);
 #else
     return 1.0 / sqrt(x);
 #endif
@@ -413,9 +409,11 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double Iyy = M.Iyy_dry + mp * (M.len2_12 + dcg * dcg);
 
     /* :324  rotation matrix body->inertial, utils.py:100-111 (q already unit) */
-    const double r00 = 1.0 - 2.0 * (qy * qy + qz * qz), r01 = 2.0 * (qx * qy - qw * qz), r02 = 2.0 * (qx * qz + qw * qy);
-    const double r10 = 2.0 * (qx * qy + qw * qz), r11 = 1.0 - 2.0 * (qx * qx + qz * qz), r12 = 2.0 * (qy * qz - qw * qx);
-    const double r20 = 2.0 * (qx * qz - qw * qy), r21 = 2.0 * (qy * qz + qw * qx), r22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+    /* the factors of two are folded into one operand (exact), so 2*(a*b - c*d) costs one product and one FMA */
+    const double x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    const double r00 = 1.0 - (qy * y2 + qz * z2), r01 = qx * y2 - qw * z2, r02 = qx * z2 + qw * y2;
+    const double r10 = qx * y2 + qw * z2, r11 = 1.0 - (qx * x2 + qz * z2), r12 = qy * z2 - qw * x2;
+    const double r20 = qx * z2 - qw * y2, r21 = qy * z2 + qw * x2, r22 = 1.0 - (qx * x2 + qy * y2);
 
     /* :328-338  atmosphere + wind */
     double T, inv_RT, p;
@@ -674,7 +672,7 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
 #pragma unroll 1
 #endif
     for (int stage = 0; stage < 4; ++stage) {
-        const double ts = (stage == 0) ? K.t : ((stage == 3) ? K.t + M.dt : K.t + M.half_dt);
+        const double ts = K.t + ((stage == 0) ? 0.0 : ((stage == 3) ? M.dt : M.half_dt));   /* warp-uniform offset */
         derivative(M, Tb, wind_alt, S, WB, ts, ys, K.chute, K.chute_time, k, stage == 0, dg);
         if (stage == 0) {
             track_diag(K, ys, dg);                      /* ys == s at stage 0 */
@@ -932,9 +930,11 @@ EMC_HD int rail_phase(const DevModel &M, const DevTables &Tb, const double *wind
     double qw, qx, qy, qz;
     if (n2 > 1e-24) { double rn = 1.0 / sqrt(n2); qw = q0 * rn; qx = q1 * rn; qy = q2 * rn; qz = q3 * rn; }
     else { qw = 1.0; qx = 0.0; qy = 0.0; qz = 0.0; }
-    const double r00 = 1.0 - 2.0 * (qy * qy + qz * qz), r01 = 2.0 * (qx * qy - qw * qz), r02 = 2.0 * (qx * qz + qw * qy);
-    const double r10 = 2.0 * (qx * qy + qw * qz), r11 = 1.0 - 2.0 * (qx * qx + qz * qz), r12 = 2.0 * (qy * qz - qw * qx);
-    const double r20 = 2.0 * (qx * qz - qw * qy), r21 = 2.0 * (qy * qz + qw * qx), r22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+    /* the factors of two are folded into one operand (exact), so 2*(a*b - c*d) costs one product and one FMA */
+    const double x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    const double r00 = 1.0 - (qy * y2 + qz * z2), r01 = qx * y2 - qw * z2, r02 = qx * z2 + qw * y2;
+    const double r10 = qx * y2 + qw * z2, r11 = 1.0 - (qx * x2 + qz * z2), r12 = qy * z2 - qw * x2;
+    const double r20 = qx * z2 - qw * y2, r21 = qy * z2 + qw * x2, r22 = 1.0 - (qx * x2 + qy * y2);
     const double dx = r00, dy = r10, dz = r20;                /* :57 body x in inertial axes */
     WindBracket WB;
     wind_bracket_reset(WB);
@@ -1105,9 +1105,11 @@ EMC_HD void series_state(const DevModel &M, const DevTables &Tb, const double *w
     const bool q_ok = n2 > 1e-24;
     const double rn = fast_rsqrt(q_ok ? n2 : 1.0);
     const double qw = q_ok ? s.q0 * rn : 1.0, qx = q_ok ? s.q1 * rn : 0.0, qy = q_ok ? s.q2 * rn : 0.0, qz = q_ok ? s.q3 * rn : 0.0;
-    const double r00 = 1.0 - 2.0 * (qy * qy + qz * qz), r01 = 2.0 * (qx * qy - qw * qz), r02 = 2.0 * (qx * qz + qw * qy);
-    const double r10 = 2.0 * (qx * qy + qw * qz), r11 = 1.0 - 2.0 * (qx * qx + qz * qz), r12 = 2.0 * (qy * qz - qw * qx);
-    const double r20 = 2.0 * (qx * qz - qw * qy), r21 = 2.0 * (qy * qz + qw * qx), r22 = 1.0 - 2.0 * (qx * qx + qy * qy);
+    /* the factors of two are folded into one operand (exact), so 2*(a*b - c*d) costs one product and one FMA */
+    const double x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
+    const double r00 = 1.0 - (qy * y2 + qz * z2), r01 = qx * y2 - qw * z2, r02 = qx * z2 + qw * y2;
+    const double r10 = qx * y2 + qw * z2, r11 = 1.0 - (qx * x2 + qz * z2), r12 = qy * z2 - qw * x2;
+    const double r20 = qx * z2 - qw * y2, r21 = qy * z2 + qw * x2, r22 = 1.0 - (qx * x2 + qy * y2);
     const double vbx = r00 * ux + r10 * uy + r20 * uz, vby = r01 * ux + r11 * uy + r21 * uz, vbz = r02 * ux + r12 * uy + r22 * uz;
     const double v2 = ux * ux + uy * uy + uz * uz;
     const double mach2 = v2 * (inv_RT * K_MISC[7]);
