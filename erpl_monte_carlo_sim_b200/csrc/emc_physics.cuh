@@ -172,8 +172,8 @@ EMC_HD double fast_rsqrt(double x)
 /* sqrt(x) for x >= 0 via x*rsqrt(x); 0 -> 0, NaN -> NaN */
 EMC_HD double fast_sqrt(double x)
 {
-    const double r = x * fast_rsqrt(x);
-    return (x > 0.0) ? ((x <= 1.7976931348623157e308) ? r : x) : ((x == 0.0) ? 0.0 : NAN);
+    const double r = x * fast_rsqrt(x);        /* x < 0 and NaN give NaN by themselves; +-0 and +inf (0*inf, inf*0) are passed through */
+    return (x == 0.0 || x > 1.7976931348623157e308) ? x : r;
 }
 
 EMC_HD long long d2ll(double v)
@@ -252,7 +252,7 @@ EMC_HD double fast_atan2(double y, double x)
     const bool swap = ay > ax;
     const double num = swap ? ax : ay, den = swap ? ay : ax;
     double t = num * fast_rcp(den);
-    t = (den > 0.0) ? t : ((den == 0.0) ? 0.0 : t);      /* atan2(0, 0) = 0; NaN stays NaN */
+    t = (den == 0.0) ? 0.0 : t;                          /* atan2(0, 0) = 0 (0 * rcp(0) is NaN); NaN stays NaN */
     const double u = t * t, u2 = u * u;
     /* two interleaved Horner chains (even / odd coefficients) for instruction-level parallelism */
     double pe = K_ATAN[18], po = K_ATAN[17];

@@ -56,7 +56,9 @@ def remez(n, a=mp.mpf(0), b=mp.mpf(1), iters=30):
     return c, max(abs(e) for e in ev)
 
 if __name__ == "__main__":
+    import os
+    umax = mp.mpf(os.environ.get("ATAN_UMAX", "1"))          # 0.1715728752538099 = tan(pi/8)^2 for the two-step reduction
     for n in [int(a) for a in sys.argv[1:]] or [16, 18, 20]:
-        c, e = remez(n)
+        c, e = remez(n, b=umax)
         print(f"// degree {n} in u: max weighted (relative) error {mp.nstr(e, 5)}")
         print("{" + ", ".join(repr(float(x)) for x in c) + "}")
