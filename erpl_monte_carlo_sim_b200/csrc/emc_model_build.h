@@ -6,6 +6,7 @@
 #pragma once
 #include <math.h>
 #include <string.h>
+#include <cmath>
 
 #include "emc_physics.cuh"
 
@@ -47,6 +48,30 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
     D.p25 = D.p20 * exp(-g * 5000.0 / (R * m.stratosphere_temp));                     /* :72-75 */
     D.expo_25 = g / (R * 0.0028);                                                     /* :76,81 */
     D.R_gas = R; D.g0 = g;
+    {
+        /* p0*(1 - a z)^e, a = L/T0, about zc: p0*(1 - a zc)^e * (1 - ap zeta)^e with ap = a zh/(1 - a zc); binomial series
+         * c_k = c_{k-1} * (e - k + 1)/k * (-ap).  Used on [-2 km, troposphere_height] when the series has converged to
+         * 1e-18 by degree 16 (standard atmosphere: ap = 0.16, last kept term 1e-20). */
+        D.tp_lo = INFINITY; D.tp_hi = -INFINITY; D.tp_zc = 0.0; D.tp_inv_zh = 0.0;
+        const long double zlo = -2000.0L, zhi = m.troposphere_height;
+        const long double zc = 0.5L * (zlo + zhi), zh = 0.5L * (zhi - zlo);
+        const long double a = (long double)L / (long double)m.sea_level_temperature, base = 1.0L - a * zc;
+        const long double e = (long double)g / ((long double)R * (long double)L);
+        if (zh > 0.0L && base > 0.0L && std::isfinite((double)e) && std::isfinite((double)a)) {
+            const long double ap = a * zh / base;
+            long double c = (long double)m.sea_level_pressure * powl(base, e);
+            long double ck[18];
+            for (int k = 0; k <= 17; ++k) {
+                if (k > 0) c *= (e - (long double)(k - 1)) / (long double)k * (-ap);
+                ck[k] = c;
+            }
+            /* the dropped tail (k >= 17, at |zeta| = 1) against the value itself */
+            if (fabsl(ap) < 0.25L && std::isfinite((double)ck[0]) && ck[0] != 0.0L && fabsl(ck[17]) < 1e-18L * fabsl(ck[0])) {
+                for (int k = 0; k <= 16; ++k) D.tp_c[k] = (double)ck[k];
+                D.tp_lo = (double)zlo; D.tp_hi = (double)zhi; D.tp_zc = (double)zc; D.tp_inv_zh = (double)(1.0L / zh);
+            }
+        }
+    }
 
     D.cg_dry = m.center_of_mass_dry; D.prop_cg = m.center_of_mass_dry - 0.5;          /* rocket.py:116 */
     const double d4 = m.diameter / 4;

@@ -73,6 +73,11 @@ struct DevModel {
     double p20, p25;     /* :56-62, :72-75 */
     double expo_25;      /* g/(R*0.0028)                   :81 */
     double R_gas, g0;
+    /* troposphere pressure as ONE polynomial: p0*(1 - L z/T0)^(g/(R L)) expanded about the middle of [tp_lo, tp_hi]
+     * (binomial series in zeta = (z - tp_zc)*tp_inv_zh, |zeta| <= 1, truncation < 1e-18 relative; built in long double
+     * by build_dev_model).  Replaces exp(e*log(T/T0)) where nearly every sounding-rocket step is flown; an atmosphere
+     * whose constants do not allow it has tp_lo = +inf and takes the exp/log path. */
+    double tp_lo, tp_hi, tp_zc, tp_inv_zh, tp_c[17];
     /* mass properties, rocket.py:110-136 */
     double cg_dry, prop_cg, d4sq, len2_12, Ixx_dry, Iyy_dry;
     /* aerodynamics, rocket.py:138-218 */
@@ -289,6 +294,22 @@ EMC_HD int brk_find(const double *lo, const double *hi, int nb, int j, double x)
 /* ---------------- atmosphere: T and 1/(R*T), p  (environment.py:26-103) ---------------- */
 EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, double &p)
 {
+    if (z >= M.tp_lo && z <= M.tp_hi) {          /* troposphere (environment.py:28-33): T linear, p by the series above */
+        T = M.T0 - M.lapse * z;
+        inv_RT = fast_rcp(M.R_gas * T);
+        const double zeta = (z - M.tp_zc) * M.tp_inv_zh, z2 = zeta * zeta;
+        double pe = M.tp_c[16], po = M.tp_c[15];
+        pe = fma(pe, z2, M.tp_c[14]);  po = fma(po, z2, M.tp_c[13]);
+        pe = fma(pe, z2, M.tp_c[12]);  po = fma(po, z2, M.tp_c[11]);
+        pe = fma(pe, z2, M.tp_c[10]);  po = fma(po, z2, M.tp_c[9]);
+        pe = fma(pe, z2, M.tp_c[8]);   po = fma(po, z2, M.tp_c[7]);
+        pe = fma(pe, z2, M.tp_c[6]);   po = fma(po, z2, M.tp_c[5]);
+        pe = fma(pe, z2, M.tp_c[4]);   po = fma(po, z2, M.tp_c[3]);
+        pe = fma(pe, z2, M.tp_c[2]);   po = fma(po, z2, M.tp_c[1]);
+        pe = fma(pe, z2, M.tp_c[0]);
+        p = fma(po, zeta, pe);
+        return;
+    }
     /* every layer is p = base * exp(arg); the two pow() layers use arg = e*log(T/Tb) */
     double base, arg, lx = 1.0, le = 0.0;
     bool use_log = false;

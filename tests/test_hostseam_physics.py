@@ -73,8 +73,9 @@ def test_seam_ballistic_nan_fast_forward():
     rows = [i for k, i in OUT.items() if k != "max_abs_omega"]
     util.assert_summary_close(fast[0][rows], full[0][rows], rtol=1e-9, what="fast-forward vs full integration")
     cmp_rows = np.zeros_like(ref[0]); cmp_rows[:] = np.nan
+    sens = util.oracle_sensitivity(md, sc, wind)         # blown-up synthetic flights amplify one ulp beyond 1e-6
     util.assert_summary_close(fast[0][:, same], np.where(np.isin(np.arange(ref[0].shape[0]), rows)[:, None], ref[0], fast[0])[:, same],
-                              what="fast-forward vs oracle")
+                              what="fast-forward vs oracle", sens=sens[:, same])
     # max|omega| keeps its value at the fast-forward point: never above the full integration's
     assert np.all(fast[0][OUT["max_abs_omega"]] <= full[0][OUT["max_abs_omega"]] * (1 + 1e-12))
 
@@ -121,3 +122,31 @@ def test_seam_components_match_reference():
     z = util.golden("components")
     models = {"liquid": _abi.model_from_npz(z, "liquid_"), "solid": _abi.model_from_npz(z, "solid_")}
     util.check_components(lambda kind, comp, cols: util.hostseam_component(models[kind], comp, cols), z)
+
+
+def test_troposphere_pressure_series_matches_the_power_law():
+    """The engine evaluates p0*(T/T0)^(g/(R L)) below the tropopause as one polynomial (DevModel.tp_c); it must agree with
+    the reference's expression (environment.py:28-33, through the oracle) to rounding over the whole layer, hand over to
+    the general path outside [-2 km, tropopause] without a jump, and switch itself off for an atmosphere it cannot
+    represent."""
+    import ctypes as C
+    z = util.golden("components")
+    md = _abi.model_from_npz(z, "liquid_")
+    alt = np.concatenate([np.linspace(-2500.0, 12000.0, 3001), [-2000.0, -2000.0000001, 11000.0, 11000.0000001, 0.0, -0.0]])
+    got = util.hostseam_component(md, 0, (alt,))
+    L = O.lib()
+    m, keep = _abi.pack_model(md)
+    ref = np.empty((3, alt.size))
+    T, p, rho = C.c_double(), C.c_double(), C.c_double()
+    for i, a in enumerate(alt):
+        L.orc_atmosphere(C.byref(m), C.c_double(a), C.byref(T), C.byref(p), C.byref(rho))
+        ref[:, i] = (T.value, p.value, rho.value)
+    np.testing.assert_allclose(got[:3], ref, rtol=3e-15)
+    # a lapse rate the series cannot cover in 17 terms falls back to exp/log and still matches
+    md2 = dict(md); md2["temperature_lapse_rate"] = 0.02
+    got2 = util.hostseam_component(md2, 0, (alt[:3001:50],))
+    m2, keep2 = _abi.pack_model(md2)
+    for i, a in enumerate(alt[:3001:50]):
+        L.orc_atmosphere(C.byref(m2), C.c_double(a), C.byref(T), C.byref(p), C.byref(rho))
+        if np.isfinite(p.value):
+            np.testing.assert_allclose(got2[1, i], p.value, rtol=2e-14)
