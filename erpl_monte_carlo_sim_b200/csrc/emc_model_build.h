@@ -117,9 +117,35 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
             else { lo[b] = x[b - 1]; hi[b] = x[b]; x0[b] = x[b - 1]; f0[b] = f[b - 1]; sl[b] = (f[b] - f[b - 1]) / (x[b] - x[b - 1]); }
         }
     };
-    fill(m.n_cd, m.cd_mach, m.cd0, T.cd_lo, T.cd_hi, T.cd_x0, T.cd0_f, T.cd0_s);
-    fill(m.n_cd, m.cd_mach, m.cda, T.cd_lo, T.cd_hi, T.cd_x0, T.cda_f, T.cda_s);
-    fill(m.n_cp, m.cp_mach, m.cp_shift, T.cp_lo, T.cp_hi, T.cp_x0, T.cp_f, T.cp_s);
+    {
+        /* Mach union grid: own brackets of each table first, then every union bracket copies the entries of the original
+         * bracket that contains it (a union bracket never straddles an original knot) */
+        const int BC = EMC_MAX_CD_KNOTS + 2, BP = EMC_MAX_CP_KNOTS + 2;
+        double cd_lo[BC], cd_hi[BC], cd_x0[BC], cd0_f[BC], cd0_s[BC], cda_f[BC], cda_s[BC];
+        double cp_lo[BP], cp_hi[BP], cp_x0[BP], cp_f[BP], cp_s[BP];
+        fill(m.n_cd, m.cd_mach, m.cd0, cd_lo, cd_hi, cd_x0, cd0_f, cd0_s);
+        fill(m.n_cd, m.cd_mach, m.cda, cd_lo, cd_hi, cd_x0, cda_f, cda_s);
+        fill(m.n_cp, m.cp_mach, m.cp_shift, cp_lo, cp_hi, cp_x0, cp_f, cp_s);
+        double u[EMC_MAX_CD_KNOTS + EMC_MAX_CP_KNOTS];
+        int nu = 0, i = 0, j = 0;
+        while (i < m.n_cd || j < m.n_cp) {
+            double v;
+            if (j >= m.n_cp || (i < m.n_cd && m.cd_mach[i] <= m.cp_mach[j])) v = m.cd_mach[i++];
+            else v = m.cp_mach[j++];
+            if (nu == 0 || v != u[nu - 1]) u[nu++] = v;
+        }
+        D.n_mb = nu + 1;
+        for (int b = 0; b <= nu; ++b) {
+            const double lo = (b == 0) ? -INFINITY : u[b - 1], hi = (b == nu) ? INFINITY : u[b];
+            T.m_lo[b] = lo; T.m_hi[b] = hi;
+            int bc = 0, bp = 0;                         /* original bracket with lo_orig <= lo (brackets are half-open [lo, hi)) */
+            while (bc < m.n_cd && cd_hi[bc] <= lo) ++bc;
+            while (bp < m.n_cp && cp_hi[bp] <= lo) ++bp;
+            if (b == 0) { bc = 0; bp = 0; }
+            T.cd_x0[b] = cd_x0[bc]; T.cd0_f[b] = cd0_f[bc]; T.cd0_s[b] = cd0_s[bc]; T.cda_f[b] = cda_f[bc]; T.cda_s[b] = cda_s[bc];
+            T.cp_x0[b] = cp_x0[bp]; T.cp_f[b] = cp_f[bp]; T.cp_s[b] = cp_s[bp];
+        }
+    }
     if (D.n_thrust > 0) fill(D.n_thrust, m.thrust_time, m.thrust_curve, T.th_lo, T.th_hi, T.th_x0, T.th_f, T.th_s);
 }
 

@@ -89,7 +89,7 @@ struct DevModel {
     double max_time, dt_rail, dt, half_dt, dt_over_6, pitch_damping, yaw_damping, rail_length;
     /* wind grid */
     double wind_alt0, wind_inv_dz;
-    int32_t motor_kind, n_cd, n_cp, n_thrust, has_wind, n_wind, wind_uniform, pad_;
+    int32_t motor_kind, n_cd, n_cp, n_thrust, has_wind, n_wind, wind_uniform, n_mb;   /* n_mb: brackets of the Mach union grid */
 };
 
 /* Tables staged into shared memory by the kernels (host seam: plain struct), stored as BRACKETS so
@@ -99,13 +99,15 @@ struct DevModel {
  *   b = n      [x[n-1], +inf)     value f[n-1],  slope 0
  * Slopes are computed on the host with the expression np.interp uses (bit-identical).  Each lane
  * remembers its bracket (Mach and burn time move slowly), so a lookup is two compares and an FMA. */
-#define EMC_BRK_CD (EMC_MAX_CD_KNOTS + 2)
-#define EMC_BRK_CP (EMC_MAX_CP_KNOTS + 2)
+/* The Cd and CP tables are both functions of Mach: their brackets are stored on the UNION of the two knot vectors
+ * (m_lo/m_hi), each union bracket carrying the anchor, value and slope of the ORIGINAL Cd bracket and of the original
+ * CP bracket it lies in — the same numbers the separate tables would use, found with one search instead of two. */
+#define EMC_BRK_M (EMC_MAX_CD_KNOTS + EMC_MAX_CP_KNOTS + 2)
 #define EMC_BRK_TH (EMC_MAX_THRUST_KNOTS + 2)
 struct DevTables {
-    double cd_lo[EMC_BRK_CD], cd_hi[EMC_BRK_CD], cd_x0[EMC_BRK_CD];
-    double cd0_f[EMC_BRK_CD], cd0_s[EMC_BRK_CD], cda_f[EMC_BRK_CD], cda_s[EMC_BRK_CD];
-    double cp_lo[EMC_BRK_CP], cp_hi[EMC_BRK_CP], cp_x0[EMC_BRK_CP], cp_f[EMC_BRK_CP], cp_s[EMC_BRK_CP];
+    double m_lo[EMC_BRK_M], m_hi[EMC_BRK_M];
+    double cd_x0[EMC_BRK_M], cd0_f[EMC_BRK_M], cd0_s[EMC_BRK_M], cda_f[EMC_BRK_M], cda_s[EMC_BRK_M];
+    double cp_x0[EMC_BRK_M], cp_f[EMC_BRK_M], cp_s[EMC_BRK_M];
     double th_lo[EMC_BRK_TH], th_hi[EMC_BRK_TH], th_x0[EMC_BRK_TH], th_f[EMC_BRK_TH], th_s[EMC_BRK_TH];
 };
 
@@ -123,7 +125,7 @@ struct Sample {
 struct WindBracket {
     double lo, hi, x0;
     double f0[3], s[3];
-    int32_t j_cd, j_cp, j_th;      /* remembered brackets of the Cd/CP-vs-Mach and thrust-vs-time tables */
+    int32_t j_m, j_th;             /* remembered brackets of the Mach (Cd + CP) and thrust-vs-time tables */
 };
 
 struct State {
@@ -467,9 +469,9 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
         /* Mach-table brackets (rocket.py:105-108,156-157): shared by Cd0/Cda, separate knots for CP */
         double mach = fast_sqrt(mach2);
         mach = (mach > 1e300) ? 1e300 : mach;     /* +inf clamps like np.interp (right value), NaN stays NaN */
-        const int jc = brk_find(Tb.cp_lo, Tb.cp_hi, M.n_cp + 1, WB.j_cp, mach);
-        WB.j_cp = jc;
-        const double cp = M.cp_location + fma(Tb.cp_s[jc], mach - Tb.cp_x0[jc], Tb.cp_f[jc]);
+        const int jm = brk_find(Tb.m_lo, Tb.m_hi, M.n_mb, WB.j_m, mach);
+        WB.j_m = jm;
+        const double cp = M.cp_location + fma(Tb.cp_s[jm], mach - Tb.cp_x0[jm], Tb.cp_f[jm]);
         const double sm = cp - cg;
         /* utils.py:160-164 */
         const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
@@ -487,11 +489,9 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
             const double cb = b_dead ? 1.0 : vxz * rvb, sb = b_dead ? 0.0 : vby * rvb;
 
             /* rocket.py:138-218 */
-            const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, WB.j_cd, mach);
-            WB.j_cd = jd;
-            const double dm = mach - Tb.cd_x0[jd];
-            const double cd0 = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * S.cd_scale;
-            const double cda = fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]);
+            const double dm = mach - Tb.cd_x0[jm];
+            const double cd0 = fma(Tb.cd0_s[jm], dm, Tb.cd0_f[jm]) * S.cd_scale;
+            const double cda = fma(Tb.cda_s[jm], dm, Tb.cda_f[jm]);
             double cd = cd0 + cda * (alpha * alpha);
             if (!(pf > 0.0)) cd *= M.power_off_factor;
             const double abs_alpha = fabs(alpha);
@@ -927,7 +927,7 @@ EMC_HD void wind_bracket_reset(WindBracket &B)
 {
     B.lo = 1.0; B.hi = 0.0; B.x0 = 0.0;     /* empty interval: first use loads */
     B.f0[0] = B.f0[1] = B.f0[2] = 0.0; B.s[0] = B.s[1] = B.s[2] = 0.0;
-    B.j_cd = 1; B.j_cp = 1; B.j_th = 1;
+    B.j_m = 1; B.j_th = 1;
 }
 
 /* motor.py:86-93 */
@@ -975,8 +975,8 @@ EMC_HD int rail_phase(const DevModel &M, const DevTables &Tb, const double *wind
         const double rx = dx * speed - w[0], ry = dy * speed - w[1], rz = dz * speed - w[2];
         const double rel_speed = rx * dx + ry * dy + rz * dz;  /* :80 */
         const double mach = fast_sqrt((rx * rx + ry * ry + rz * rz) * (inv_RT * (1.0 / 1.4)));
-        const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, WB.j_cd, mach);
-        WB.j_cd = jd;
+        const int jd = brk_find(Tb.m_lo, Tb.m_hi, M.n_mb, WB.j_m, mach);
+        WB.j_m = jd;
         const double dm = mach - Tb.cd_x0[jd];
         const double cd = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * S.cd_scale
                           + fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]) * 0.0;                 /* alpha = 0, :82-83 */
@@ -1034,9 +1034,9 @@ EMC_HD void load_flight_state(const Sample &S, const double *col, int64_t ld, co
 EMC_HD void aero_coefficients(const DevModel &M, const DevTables &Tb, double mach, double mach2, double alpha, double beta,
                               double cg, bool power_on, double cd_scale, double c[7])
 {
-    const int jc = brk_find(Tb.cp_lo, Tb.cp_hi, M.n_cp + 1, 1, mach);
+    const int jc = brk_find(Tb.m_lo, Tb.m_hi, M.n_mb, 1, mach);
     const double cp = M.cp_location + fma(Tb.cp_s[jc], mach - Tb.cp_x0[jc], Tb.cp_f[jc]);
-    const int jd = brk_find(Tb.cd_lo, Tb.cd_hi, M.n_cd + 1, 1, mach);
+    const int jd = jc;
     const double dm = mach - Tb.cd_x0[jd];
     const double cd0 = fma(Tb.cd0_s[jd], dm, Tb.cd0_f[jd]) * cd_scale;
     const double cda = fma(Tb.cda_s[jd], dm, Tb.cda_f[jd]);

@@ -150,3 +150,37 @@ def test_troposphere_pressure_series_matches_the_power_law():
         L.orc_atmosphere(C.byref(m2), C.c_double(a), C.byref(T), C.byref(p), C.byref(rho))
         if np.isfinite(p.value):
             np.testing.assert_allclose(got2[1, i], p.value, rtol=2e-14)
+
+
+def test_mach_union_grid_reproduces_both_tables():
+    """Cd(M) and CP(M) are looked up on the union of their knot vectors with one search; values must be the ones
+    np.interp gives on the separate tables (rocket.py:105-108,156-157), for shared, interleaved and disjoint knots,
+    at the knots themselves and beyond both ends."""
+    import ctypes as C
+    z = util.golden("components")
+    base = _abi.model_from_npz(z, "liquid_")
+    rng = np.random.RandomState(5)
+    L = O.lib()
+    L.orc_aero_coefficients.restype = None
+    for trial in range(12):
+        n_cd, n_cp = rng.randint(2, 17), rng.randint(2, 17)
+        cdm = np.sort(rng.choice(np.arange(0, 60), n_cd, replace=False)) * 0.1
+        cpm = np.sort(rng.choice(np.arange(0, 60), n_cp, replace=False)) * 0.1 + (0.0 if trial % 3 else 0.05)
+        if trial == 4:
+            cpm = cdm[-1] + 1.0 + np.arange(n_cp) * 0.5        # disjoint ranges
+        md = dict(base)
+        md["cd_mach"], md["cd0"], md["cda"] = cdm, 0.2 + rng.rand(n_cd), rng.rand(n_cd) * 5
+        md["cp_mach"], md["cp_shift"] = cpm, rng.randn(n_cp) * 0.2
+        mach = np.concatenate([cdm, cpm, rng.rand(200) * 8.0 - 0.5, np.nextafter(cdm, 0), np.nextafter(cpm, 100)])
+        mach = np.abs(mach)
+        alpha = rng.randn(mach.size) * 0.1; beta = rng.randn(mach.size) * 0.1
+        got = util.hostseam_component(md, 2, (mach, alpha, beta, 1.3, 1.0, 1.0))
+        m, keep = _abi.pack_model(md)
+        c = (C.c_double * 6)()
+        ref = np.empty((6, mach.size))
+        for i in range(mach.size):
+            L.orc_aero_coefficients(C.byref(m), C.c_double(mach[i]), C.c_double(alpha[i]), C.c_double(beta[i]), C.c_double(1.3),
+                                    C.c_int(1), C.c_double(1.0), c)
+            ref[:, i] = list(c)
+        np.testing.assert_allclose(got[:6], ref, rtol=2e-14, atol=1e-16, err_msg=f"trial {trial}")
+        np.testing.assert_allclose(got[5], ref[5], rtol=4e-16)            # CP: table value + cp_location, one FMA rounding apart
