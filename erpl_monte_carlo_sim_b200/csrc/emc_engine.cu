@@ -331,6 +331,7 @@ struct emc_ctx {
     double *d_tape = nullptr; size_t cap_tape = 0;
     unsigned char *d_scratch = nullptr; size_t cap_scratch = 0;
     double *d_partial = nullptr; size_t cap_partial = 0;
+    double *d_summary = nullptr; size_t cap_summary = 0;
     double *d_disp = nullptr; size_t cap_disp = 0;    /* dispersion tables (shear/base wind/rho/innov) */
     double *d_draws = nullptr; size_t cap_draws = 0;  /* caller-supplied draws */
     int64_t staged_n = 0; int staged_knots = 0;
@@ -400,7 +401,7 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
-    cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
+    cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_summary); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -954,6 +955,46 @@ EMC_EXPORT int emc_stats_moments2(emc_ctx *ctx, const double *out_dev, int64_t l
     emc_stats_finish_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_partial, g, ST2_COUNT, 0, sum_dev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_stats_summary(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct,
+                                 double *result)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!result || !percentiles || n_pct < 1 || n_pct > EMC_SUMMARY_MAX_PCT) return fail(ctx, EMC_ERR_INVALID, "emc_stats_summary: bad argument (1 <= n_pct <= 8)");
+    CK(cudaSetDevice(ctx->device));
+    const int nt = 2 * n_pct, rows = 3 * nt;
+    const size_t res_words = 32 + (size_t)rows, words = res_words + 2 * (size_t)rows + (size_t)rows * EMC_SELECT_BINS;
+    CK(grow(&ctx->d_summary, &ctx->cap_summary, words));
+    SummaryLayout L;
+    L.res = ctx->d_summary; L.nt = nt;
+    L.prefix = reinterpret_cast<unsigned long long *>(ctx->d_summary + res_words);
+    L.rem = reinterpret_cast<long long *>(ctx->d_summary + res_words + rows);
+    L.hist = reinterpret_cast<unsigned long long *>(ctx->d_summary + res_words + 2 * (size_t)rows);
+    SummaryPct P;
+    memset(&P, 0, sizeof P);
+    P.n_pct = n_pct;
+    for (int j = 0; j < n_pct; ++j) P.pct[j] = percentiles[j];
+    const int g = stats_grid(ctx, n);
+    CK(grow(&ctx->d_partial, &ctx->cap_partial, (size_t)g * (ST_SUM_COUNT + 2 * ST_MM_COUNT)));
+    double *ps = ctx->d_partial, *pmin = ps + (size_t)g * ST_SUM_COUNT, *pmax = pmin + (size_t)g * ST_MM_COUNT;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(ctx->d_summary, 0, sizeof(double) * words, st));
+    emc_stats_moments1_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, ps, pmin, pmax);
+    emc_stats_finish3_kernel<<<1, 32, 0, st>>>(ps, pmin, pmax, g, L.res);
+    emc_stats_plan_kernel<<<1, 32, 0, st>>>(L, P);
+    emc_stats_moments2_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, L.res + 26, ps);
+    emc_stats_finish_kernel<<<1, 32, 0, st>>>(ps, g, ST2_COUNT, 0, L.res + 20);
+    static const int passes[6][2] = { { 55, 64 }, { 44, 55 }, { 33, 44 }, { 22, 33 }, { 11, 22 }, { 0, 11 } };
+    for (int k = 0; k < 6; ++k) {
+        const int shift = passes[k][0], pshift = passes[k][1];
+        emc_stats_select_dev_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, L, shift, pshift);
+        emc_stats_select_finish_kernel<<<rows, 32, 0, st>>>(L, (pshift >= 64) ? 64 - shift : pshift - shift, k == 5);
+    }
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(result, L.res, sizeof(double) * res_words, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     return EMC_OK;
 }
 

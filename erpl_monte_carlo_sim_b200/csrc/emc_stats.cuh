@@ -222,4 +222,106 @@ __global__ void __launch_bounds__(256) emc_stats_linear_hist_kernel(const double
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * The whole summary as ONE stream-ordered chain (single GPU): moments1 -> plan -> moments2 -> 6 x (digit histogram,
+ * digit decision) -> values, with every intermediate (means, order-statistic ranks, radix-select prefixes) kept in
+ * device memory, so the host synchronises once.  Same arithmetic as stats.compute_statistics / radix_select3.
+ * Layout of the state block (8-byte words):
+ *   [0, 20)            sum | min | max            (moments1)
+ *   [20, 26)           centred second moments      (moments2)
+ *   [26, 31)           means ap rg ft x y
+ *   [32, 32 + 3 NT)    order statistics val[f][t], NT = 2 * n_pct targets per metric (lo and hi rank of each percentile)
+ *   then prefix[3][NT] (u64), rem[3][NT] (i64), hist[3][NT][BINS] (u64)
+ * ---------------------------------------------------------------------------------------------- */
+#define EMC_SUMMARY_MAX_PCT 8
+struct SummaryLayout {
+    double *res;                  /* words [0, 32 + 3 NT) */
+    unsigned long long *prefix;   /* [3][NT] */
+    long long *rem;               /* [3][NT] */
+    unsigned long long *hist;     /* [3][NT][BINS] */
+    int nt;                       /* 2 * n_pct */
+};
+struct SummaryPct { double pct[EMC_SUMMARY_MAX_PCT]; int n_pct; };
+
+/* np.percentile(method="linear") ranks: q = p/100, pos = (m-1) q, lo = floor(pos), hi = min(lo+1, m-1) */
+__global__ void emc_stats_plan_kernel(SummaryLayout L, SummaryPct P)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double valid = L.res[ST_VALID];
+    const long long m = llrint(valid);
+    for (int k = 0; k < 5; ++k) L.res[26 + k] = (m > 0) ? L.res[ST_SUM_AP + k] / (double)m : NAN;
+    for (int j = 0; j < P.n_pct; ++j) {
+        const double q = P.pct[j] / 100.0;
+        const double pos = (double)(m - 1) * q;
+        long long lo = (long long)floor(pos), hi = lo + 1;
+        if (hi > m - 1) hi = m - 1;
+        for (int f = 0; f < 3; ++f) {
+            L.prefix[f * L.nt + 2 * j] = 0ull;  L.rem[f * L.nt + 2 * j] = (m > 0) ? lo : -1;
+            L.prefix[f * L.nt + 2 * j + 1] = 0ull;  L.rem[f * L.nt + 2 * j + 1] = (m > 0) ? hi : -1;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) emc_stats_select_dev_kernel(const double *out, int64_t ld, int64_t n, SummaryLayout L,
+                                                                   int shift, int prefix_shift)
+{
+    __shared__ unsigned long long pre_sh[3 * 2 * EMC_SUMMARY_MAX_PCT];
+    __shared__ int live;
+    if (threadIdx.x == 0) live = (L.rem[0] >= 0);
+    if (threadIdx.x < 3 * L.nt) pre_sh[threadIdx.x] = L.prefix[threadIdx.x];
+    __syncthreads();
+    if (!live) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v[3] = { out[EMC_OUT_APOGEE_ALTITUDE * ld + i], out[EMC_OUT_RANGE * ld + i], out[EMC_OUT_FLIGHT_TIME * ld + i] };
+        int why;
+        if (classify_outlier(v[0], v[1], v[2], &why)) continue;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) {
+            const unsigned long long key = ordered_key(v[f]);
+            const unsigned long long pre = (prefix_shift >= 64) ? 0ull : (key >> prefix_shift);
+            const unsigned digit = (unsigned)((key >> shift) & (EMC_SELECT_BINS - 1));
+            for (int t = 0; t < L.nt; ++t)
+                if (pre == pre_sh[f * L.nt + t]) atomicAdd(&L.hist[((size_t)(f * L.nt + t)) * EMC_SELECT_BINS + digit], 1ull);
+        }
+    }
+}
+
+/* one warp per (metric, target): b = first digit whose cumulative count exceeds the remaining rank
+ * (np.searchsorted(cum, rem, side="right")), prefix <- prefix << width | b, rem -= cum[b-1]; the row is zeroed for the
+ * next pass.  After the last pass the prefix is the full key: its value is written to val. */
+__global__ void __launch_bounds__(32) emc_stats_select_finish_kernel(SummaryLayout L, int width, int last)
+{
+    const int row = blockIdx.x, lane = threadIdx.x;
+    long long rem = L.rem[row];
+    if (rem < 0) { if (last && lane == 0) L.res[32 + row] = NAN; return; }
+    unsigned long long *h = L.hist + (size_t)row * EMC_SELECT_BINS;
+    const int per = EMC_SELECT_BINS / 32;
+    unsigned long long mine = 0;
+    for (int k = 0; k < per; ++k) mine += h[lane * per + k];
+    unsigned long long incl = mine;                                  /* inclusive scan over lanes */
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const unsigned long long before = incl - mine;
+    const bool here = (unsigned long long)rem >= before && (unsigned long long)rem < incl;     /* the target digit is in my chunk */
+    const unsigned who = __ballot_sync(0xffffffffu, here);
+    if (who == 0u) { if (last && lane == 0) L.res[32 + row] = NAN; return; }                   /* rank beyond the population */
+    const int owner = __ffs(who) - 1;
+    if (lane == owner) {
+        unsigned long long cum = before;
+        int b = lane * per;
+        for (;; ++b) { const unsigned long long c = h[b]; if ((unsigned long long)rem < cum + c) break; cum += c; }
+        const unsigned long long pre = (L.prefix[row] << width) | (unsigned long long)b;
+        L.prefix[row] = pre;
+        L.rem[row] = rem - (long long)cum;
+        if (last) {
+            const unsigned long long bits = (pre >> 63) ? (pre & 0x7fffffffffffffffull) : ~pre;
+            L.res[32 + row] = __longlong_as_double((long long)bits);
+        }
+    }
+    __syncwarp();
+    for (int k = 0; k < per; ++k) h[lane * per + k] = 0ull;
+}
+
 }  // namespace emc

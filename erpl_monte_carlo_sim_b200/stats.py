@@ -95,6 +95,18 @@ class DeviceBackend:
         allv = self._blk(0, NSUM + 2 * NMM).get()                 # one device->host copy for the three blocks
         return allv[:NSUM], allv[NSUM:NSUM + NMM], allv[NSUM + NMM:]
 
+    def summary(self, percentiles):
+        """Single-GPU fast path: every pass chained on the device, one synchronisation (emc_stats_summary).
+        Returns (sum, min, max, s2, val) with val[f][2j], val[f][2j+1] the lo / hi order statistic of percentile j."""
+        e = self.e
+        npct = len(percentiles)
+        pct = (C.c_double * npct)(*[float(p) for p in percentiles])
+        res = np.empty(32 + 3 * 2 * npct, np.float64)
+        e._check(e._lib.emc_stats_summary(e._ctx, self.out_ptr, self.ld, self.n, pct, npct, res.ctypes.data_as(C.POINTER(C.c_double))),
+                 "emc_stats_summary")
+        return (res[:NSUM], res[NSUM:NSUM + NMM], res[NSUM + NMM:NSUM + 2 * NMM], res[20:26],
+                res[32:].reshape(3, 2 * npct))
+
     def select_hist3(self, shift, prefix_shift, prefix_lists):
         """One pass over the samples for all three metrics: prefix_lists[f] = list of prefixes of metric f."""
         e = self.e
@@ -199,7 +211,13 @@ def radix_select(backend, field, ranks):
 
 
 def compute_statistics(backend, histogram_bins=0):
-    s, mn, mx = backend.moments1()
+    fused = None
+    if hasattr(backend, "summary") and getattr(backend, "fused", True) and not getattr(backend, "distributed", True) \
+            and len(PERCENTILES) <= 8:
+        fused = backend.summary(PERCENTILES)          # one stream-ordered chain on the device, one host sync
+        s, mn, mx = fused[0], fused[1], fused[2]
+    else:
+        s, mn, mx = backend.moments1()
     S = dict(zip(SUM_FIELDS, s))
     m = int(round(S["valid"]))
     res = {"n_total": int(round(S["n"])), "n_samples": m, "n_outliers": int(round(S["outlier"])), "n_failed": 0,
@@ -211,7 +229,7 @@ def compute_statistics(backend, histogram_bins=0):
         res["landing_ellipse"] = {"mean": [nan, nan], "covariance": [[nan, nan], [nan, nan]]}
         return res
     means = np.array([S["sum_apogee"], S["sum_range"], S["sum_time"], S["sum_x"], S["sum_y"]]) / m
-    s2 = backend.moments2(means)
+    s2 = fused[3] if fused is not None else backend.moments2(means)
     for f, key in enumerate(METRICS):
         res[key] = {"mean": float(means[f]), "std": float(math.sqrt(s2[f] / m)), "min": float(mn[f]), "max": float(mx[f])}
     res["landing_ellipse"] = {"mean": [float(means[3]), float(means[4])],
@@ -223,10 +241,15 @@ def compute_statistics(backend, histogram_bins=0):
     hi_idx = np.minimum(lo_idx + 1, m - 1)
     gamma = pos - lo_idx
     ranks = sorted(set(lo_idx.tolist()) | set(hi_idx.tolist()))
-    vals = radix_select3(backend, ranks)
-    for f, key in enumerate(METRICS):
-        val = vals[f]
-        res[key]["percentiles"] = [float(_lerp(val[int(a)], val[int(b)], g)) for a, b, g in zip(lo_idx, hi_idx, gamma)]
+    if fused is not None:
+        for f, key in enumerate(METRICS):
+            v = fused[4][f]
+            res[key]["percentiles"] = [float(_lerp(v[2 * j], v[2 * j + 1], g)) for j, g in enumerate(gamma)]
+    else:
+        vals = radix_select3(backend, ranks)
+        for f, key in enumerate(METRICS):
+            val = vals[f]
+            res[key]["percentiles"] = [float(_lerp(val[int(a)], val[int(b)], g)) for a, b, g in zip(lo_idx, hi_idx, gamma)]
     if histogram_bins:
         res["histograms"] = {}
         for f, key in enumerate(METRICS + ("landing_x", "landing_y")):
@@ -240,6 +263,9 @@ def compute_statistics(backend, histogram_bins=0):
     return res
 
 
-def device_statistics(engine, n, out_dev=None, ld=None, distributed=None, histogram_bins=0):
-    """Statistics of the `n` samples in `out_dev` (device pointer; None = the engine's last run_batch outputs)."""
-    return compute_statistics(DeviceBackend(engine, n, out_dev, ld, distributed), histogram_bins)
+def device_statistics(engine, n, out_dev=None, ld=None, distributed=None, histogram_bins=0, fused=True):
+    """Statistics of the `n` samples in `out_dev` (device pointer; None = the engine's last run_batch outputs).
+    fused=False forces the pass-by-pass path a multi-GPU job uses (blocks all-reduced between passes)."""
+    backend = DeviceBackend(engine, n, out_dev, ld, distributed)
+    backend.fused = bool(fused)
+    return compute_statistics(backend, histogram_bins)

@@ -306,6 +306,15 @@ int emc_stats_select_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64
 int emc_stats_select_hist3(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int shift, int prefix_shift,
                            const uint64_t *prefixes, const int32_t *n_prefix, uint64_t *hist_dev);
 
+/* The whole single-GPU summary in one stream-ordered chain (no host round trips between the passes): counts by reason,
+ * sum / min / max, centred second moments and the np.percentile(method="linear") order statistics of apogee, range and
+ * flight time over the valid samples.  result (host) = sum[14] | min[3] | max[3] | s2[6] | means[5] | 0 |
+ * val[3][2*n_pct] (lo and hi order statistic of every percentile; NaN when there is no valid sample).
+ * n_pct <= 8.  out_dev NULL = the context's resident outputs.  Multi-GPU jobs use the pass-by-pass entry points above,
+ * whose blocks are all-reduced between passes. */
+int emc_stats_summary(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct,
+                      double *result);
+
 /* fixed-bin histogram over the valid samples; field 0 apogee, 1 range, 2 flight_time, 3 landing x, 4 landing y */
 int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, double lo, double hi,
                           int nbins, uint64_t *hist_dev /*[nbins], zeroed by the call*/);

@@ -182,6 +182,44 @@ def test_device_statistics_match_numpy_backend():
         out[O["apogee_altitude"]], out[O["range"]], out[O["flight_time"]])], [5, 25, 50, 75, 95]), rtol=1e-15)
 
 
+def test_fused_and_pass_by_pass_statistics_agree():
+    """emc_stats_summary (one device-side chain, single GPU) and the pass-by-pass path (multi-GPU) give identical
+    results, including ties, a single valid sample and no valid sample at all."""
+    from erpl_monte_carlo_sim_b200 import stats as S
+    from erpl_monte_carlo_sim_b200.simulator import get_engine
+    from stats_numpy_backend import NumpyBackend
+    rng = np.random.RandomState(9)
+    O = _abi.OUT
+    eng = get_engine(0)
+    cases = []
+    for n, valid in ((50000, "most"), (4097, "ties"), (300, "one"), (257, "none"), (1, "most")):
+        out = np.zeros((_abi.OUT_COUNT, n))
+        out[O["apogee_altitude"]] = rng.normal(9000, 3000, n); out[O["range"]] = np.abs(rng.normal(40000, 15000, n))
+        out[O["flight_time"]] = rng.normal(11, 1, n); out[O["final_x"]] = rng.normal(0, 2e4, n); out[O["final_y"]] = rng.normal(0, 4e4, n)
+        if valid == "ties":
+            out[O["flight_time"]] = np.round(out[O["flight_time"]] * 2) / 2; out[O["apogee_altitude"]] = 5000.0
+            out[O["range"], ::3] = -0.0; out[O["range"], 1::3] = 0.0
+        if valid == "one":
+            out[O["apogee_altitude"]] = np.nan; out[O["apogee_altitude"], 123] = 7777.0
+        if valid == "none":
+            out[O["apogee_altitude"]] = 1e6
+        cases.append(out)
+    for out in cases:
+        n = out.shape[1]
+        eng.upload_outputs(out)
+        a = S.device_statistics(eng, n, fused=True)
+        b = S.device_statistics(eng, n, fused=False)
+        ref = S.compute_statistics(NumpyBackend(out[O["apogee_altitude"]], out[O["range"]], out[O["flight_time"]], out[O["final_x"]],
+                                                out[O["final_y"]]))
+        assert a["n_samples"] == b["n_samples"] == ref["n_samples"] and a["outlier_reasons"] == b["outlier_reasons"]
+        for key in ("apogee_altitude", "range", "flight_time"):
+            for f in ("mean", "std", "min", "max"):
+                assert a[key][f] == b[key][f] or (np.isnan(a[key][f]) and np.isnan(b[key][f])), (n, key, f, a[key][f], b[key][f])
+            np.testing.assert_array_equal(a[key]["percentiles"], b[key]["percentiles"])
+            np.testing.assert_array_equal(a[key]["percentiles"], ref[key]["percentiles"])
+        np.testing.assert_array_equal(a["landing_ellipse"]["covariance"], b["landing_ellipse"]["covariance"])
+
+
 def test_design_sweep_config_c5():
     """BASELINE config C5: launch-angle x mass x Cd-scale grid, common dispersions per point, device statistics per point
     and tail extraction; checked against the C oracle on the same inputs."""
