@@ -33,6 +33,103 @@ inline const char *validate_model(const emc_model &m)
     return nullptr;
 }
 
+/* Pressure above the troposphere exactly as atmosphere()'s general path defines it (environment.py:35-103), in long
+ * double, from the folded double constants the kernels use.  layer: 1 (h_tropo, h_strat], 2 (h_strat, 25 km],
+ * 3 (25 km, 32 km], 4 above 32 km. */
+inline long double atm_pressure_ld(const DevModel &D, int layer, long double z)
+{
+    if (layer == 1) return (long double)D.p11 * expl((long double)D.k_iso * (z - (long double)D.h_tropo));
+    if (layer == 2) return (long double)D.p20 * expl((long double)D.k_iso * (z - (long double)D.h_strat));
+    if (layer == 3) {
+        long double T = (long double)D.T_strat + 0.001L * (z - (long double)D.h_strat);
+        if (T > 228.65L) T = 228.65L;
+        return (long double)D.p25 * expl((long double)D.expo_25 * logl(T * (long double)D.inv_T_strat));
+    }
+    long double T = 228.65L - 0.0028L * (z - 32000.0L);
+    if (T < 180.0L) T = 180.0L;
+    return 868.02L * expl(-(z - 32000.0L) * ((long double)D.g0 / ((long double)D.R_gas * T)));
+}
+
+/* degree-16 Chebyshev interpolant of f on [a, b] as monomial coefficients in zeta = (z - zc)/zh; returns the largest
+ * relative error of the DOUBLE even/odd Horner evaluation the kernel performs, sampled on 97 points */
+template <class F>
+inline double atm_fit_segment(F f, long double a, long double b, double c[17])
+{
+    const int N = 17;
+    const long double zc = 0.5L * (a + b), zh = 0.5L * (b - a), PI = 3.14159265358979323846264338327950288L;
+    long double fx[N], ck[N];
+    for (int i = 0; i < N; ++i) fx[i] = f(zc + zh * cosl(PI * (i + 0.5L) / N));
+    for (int k = 0; k < N; ++k) {
+        long double acc = 0.0L;
+        for (int i = 0; i < N; ++i) acc += fx[i] * cosl(PI * k * (i + 0.5L) / N);
+        ck[k] = acc * (k == 0 ? 1.0L : 2.0L) / N;
+    }
+    /* Chebyshev -> monomial: T_0 = 1, T_1 = x, T_{k+1} = 2 x T_k - T_{k-1} */
+    long double mono[N] = { 0 }, t0[N] = { 0 }, t1[N] = { 0 }, t2[N];
+    t0[0] = 1.0L; t1[1] = 1.0L;
+    mono[0] += ck[0];
+    for (int j = 0; j < N; ++j) mono[j] += ck[1] * t1[j];
+    for (int k = 2; k < N; ++k) {
+        for (int j = 0; j < N; ++j) t2[j] = (j > 0 ? 2.0L * t1[j - 1] : 0.0L) - t0[j];
+        for (int j = 0; j < N; ++j) { mono[j] += ck[k] * t2[j]; t0[j] = t1[j]; t1[j] = t2[j]; }
+    }
+    for (int j = 0; j < N; ++j) c[j] = (double)mono[j];
+    const double dzc = (double)zc, dizh = (double)(1.0L / zh);
+    double worst = 0.0;
+    for (int i = 0; i <= 96; ++i) {
+        const long double zl = a + (b - a) * i / 96.0L;
+        const double z = (double)zl;
+        const double zeta = (z - dzc) * dizh, z2 = zeta * zeta;
+        double pe = c[16], po = c[15];
+        for (int k = 14; k >= 2; k -= 2) { pe = fma(pe, z2, c[k]); po = fma(po, z2, c[k - 1]); }
+        pe = fma(pe, z2, c[0]);
+        const double p = fma(po, zeta, pe);
+        const long double ref = f((long double)z);
+        const double err = (double)fabsl(((long double)p - ref) / ref);
+        if (!(err <= worst)) worst = err;          /* NaN counts as failure */
+    }
+    return worst;
+}
+
+inline void build_atmosphere_segments(DevModel &D)
+{
+    D.n_atm = 0;
+    const double z180 = 32000.0 + (228.65 - 180.0) / 0.0028;
+    struct Layer { int id; double lo, hi, tb, ts, tz0, tmin, tmax; };
+    const Layer layers[5] = {
+        { 1, D.h_tropo, D.h_strat, D.T_strat, 0.0, D.h_tropo, -INFINITY, INFINITY },
+        { 2, D.h_strat, 25000.0, D.T_strat, 0.001, D.h_strat, -INFINITY, 228.65 },
+        { 3, 25000.0, 32000.0, D.T_strat, 0.001, D.h_strat, -INFINITY, 228.65 },
+        { 4, 32000.0, z180, 228.65, -0.0028, 32000.0, 180.0, INFINITY },
+        { 4, z180, 100000.0, 228.65, -0.0028, 32000.0, 180.0, INFINITY },
+    };
+    if (!(D.h_tropo < D.h_strat && D.h_strat < 25000.0)) return;      /* non-standard layer order: keep the general path */
+    for (const Layer &Ly : layers) {
+        auto f = [&](long double z) { return atm_pressure_ld(D, Ly.id, z); };
+        bool done = false;
+        for (int pieces = 1; pieces <= 8 && !done; ++pieces) {
+            if (D.n_atm + pieces > EMC_ATM_SEG) break;
+            double cc[8][17];
+            bool good = true;
+            for (int q = 0; q < pieces && good; ++q) {
+                const long double a = Ly.lo + (long double)(Ly.hi - Ly.lo) * q / pieces, b = Ly.lo + (long double)(Ly.hi - Ly.lo) * (q + 1) / pieces;
+                good = atm_fit_segment(f, a, b, cc[q]) < 4e-16;
+            }
+            if (!good) continue;
+            for (int q = 0; q < pieces; ++q) {
+                const long double a = Ly.lo + (long double)(Ly.hi - Ly.lo) * q / pieces, b = Ly.lo + (long double)(Ly.hi - Ly.lo) * (q + 1) / pieces;
+                const int j = D.n_atm++;
+                D.at_lo[j] = (q == 0) ? Ly.lo : (double)a; D.at_hi[j] = (q == pieces - 1) ? Ly.hi : (double)b;
+                D.at_zc[j] = (double)(0.5L * (a + b)); D.at_izh[j] = (double)(1.0L / (0.5L * (b - a)));
+                D.at_tb[j] = Ly.tb; D.at_ts[j] = Ly.ts; D.at_tz0[j] = Ly.tz0; D.at_tmin[j] = Ly.tmin; D.at_tmax[j] = Ly.tmax;
+                for (int k = 0; k < 17; ++k) D.at_c[j][k] = cc[q][k];
+            }
+            done = true;
+        }
+        if (!done) break;       /* this layer and everything above it keep the exp/log path */
+    }
+}
+
 inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
 {
     memset(&D, 0, sizeof D);
@@ -72,6 +169,8 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
             }
         }
     }
+
+    build_atmosphere_segments(D);
 
     D.cg_dry = m.center_of_mass_dry; D.prop_cg = m.center_of_mass_dry - 0.5;          /* rocket.py:116 */
     const double d4 = m.diameter / 4;

@@ -35,6 +35,7 @@
 #define EMC_HD inline
 #define EMC_KDECL static const double
 #endif
+#define EMC_LIKELY(x) __builtin_expect(!!(x), 1)
 
 namespace emc {
 
@@ -64,6 +65,7 @@ EMC_KDECL K_MISC[10] = {
 /* ------------------------------------------------------------------------------------------------
  * Run constants (device: __constant__ memory, so they are instruction operands, not registers)
  * ---------------------------------------------------------------------------------------------- */
+#define EMC_ATM_SEG 16
 struct DevModel {
     /* atmosphere, environment.py:13-24 + literals of :52-90 */
     double T0, lapse, inv_T0, p0, h_tropo, h_strat, T_strat, inv_T_strat;
@@ -78,6 +80,13 @@ struct DevModel {
      * by build_dev_model).  Replaces exp(e*log(T/T0)) where nearly every sounding-rocket step is flown; an atmosphere
      * whose constants do not allow it has tp_lo = +inf and takes the exp/log path. */
     double tp_lo, tp_hi, tp_zc, tp_inv_zh, tp_c[17];
+    /* the layers above it, each cut into segments (at_lo, at_hi] that carry a degree-16 polynomial of the pressure in
+     * zeta = (z - at_zc)*at_izh (Chebyshev interpolant of the layer's own formula, fitted and verified in long double by
+     * build_dev_model) and the layer's temperature line T = clamp(at_tb + at_ts*(z - at_tz0), at_tmin, at_tmax).
+     * Altitudes no segment covers (above 100 km, NaN, a layer the fit could not represent) take the exp/log path. */
+    double at_lo[EMC_ATM_SEG], at_hi[EMC_ATM_SEG], at_zc[EMC_ATM_SEG], at_izh[EMC_ATM_SEG];
+    double at_tb[EMC_ATM_SEG], at_ts[EMC_ATM_SEG], at_tz0[EMC_ATM_SEG], at_tmin[EMC_ATM_SEG], at_tmax[EMC_ATM_SEG];
+    double at_c[EMC_ATM_SEG][17];
     /* mass properties, rocket.py:110-136 */
     double cg_dry, prop_cg, d4sq, len2_12, Ixx_dry, Iyy_dry;
     /* aerodynamics, rocket.py:138-218 */
@@ -90,6 +99,7 @@ struct DevModel {
     /* wind grid */
     double wind_alt0, wind_inv_dz;
     int32_t motor_kind, n_cd, n_cp, n_thrust, has_wind, n_wind, wind_uniform, n_mb;   /* n_mb: brackets of the Mach union grid */
+    int32_t n_atm, pad_;                                                              /* segments in at_* */
 };
 
 /* Tables staged into shared memory by the kernels (host seam: plain struct), stored as BRACKETS so
@@ -125,7 +135,7 @@ struct Sample {
 struct WindBracket {
     double lo, hi, x0;
     double f0[3], s[3];
-    int32_t j_m, j_th;             /* remembered brackets of the Mach (Cd + CP) and thrust-vs-time tables */
+    int32_t j_m, j_th, j_atm;      /* remembered brackets: Mach (Cd + CP) table, thrust-vs-time table, atmosphere segment */
 };
 
 struct State {
@@ -294,9 +304,9 @@ EMC_HD int brk_find(const double *lo, const double *hi, int nb, int j, double x)
 }
 
 /* ---------------- atmosphere: T and 1/(R*T), p  (environment.py:26-103) ---------------- */
-EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, double &p)
+EMC_HD void atmosphere(const DevModel &M, double z, int &j_atm, double &T, double &inv_RT, double &p)
 {
-    if (z >= M.tp_lo && z <= M.tp_hi) {          /* troposphere (environment.py:28-33): T linear, p by the series above */
+    if (EMC_LIKELY(z >= M.tp_lo && z <= M.tp_hi)) {          /* troposphere (environment.py:28-33): T linear, p by the series above */
         T = M.T0 - M.lapse * z;
         inv_RT = fast_rcp(M.R_gas * T);
         const double zeta = (z - M.tp_zc) * M.tp_inv_zh, z2 = zeta * zeta;
@@ -311,6 +321,34 @@ EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, d
         pe = fma(pe, z2, M.tp_c[0]);
         p = fma(po, zeta, pe);
         return;
+    }
+    if (M.n_atm > 0) {                          /* upper layers (environment.py:35-103) by segment polynomial */
+        int j = j_atm;
+        bool ok = (z > M.at_lo[j]) && (z <= M.at_hi[j]);
+        if (!ok) {
+            for (int k = 0; k < M.n_atm; ++k)
+                if (z > M.at_lo[k] && z <= M.at_hi[k]) { j = k; ok = true; break; }
+        }
+        if (ok) {
+            j_atm = j;
+            T = M.at_tb[j] + M.at_ts[j] * (z - M.at_tz0[j]);
+            T = py_min(T, M.at_tmax[j]);
+            T = py_max(T, M.at_tmin[j]);
+            inv_RT = fast_rcp(M.R_gas * T);
+            const double *c = M.at_c[j];
+            const double zeta = (z - M.at_zc[j]) * M.at_izh[j], z2 = zeta * zeta;
+            double pe = c[16], po = c[15];
+            pe = fma(pe, z2, c[14]);  po = fma(po, z2, c[13]);
+            pe = fma(pe, z2, c[12]);  po = fma(po, z2, c[11]);
+            pe = fma(pe, z2, c[10]);  po = fma(po, z2, c[9]);
+            pe = fma(pe, z2, c[8]);   po = fma(po, z2, c[7]);
+            pe = fma(pe, z2, c[6]);   po = fma(po, z2, c[5]);
+            pe = fma(pe, z2, c[4]);   po = fma(po, z2, c[3]);
+            pe = fma(pe, z2, c[2]);   po = fma(po, z2, c[1]);
+            pe = fma(pe, z2, c[0]);
+            p = fma(po, zeta, pe);
+            return;
+        }
     }
     /* every layer is p = base * exp(arg); the two pow() layers use arg = e*log(T/Tb) */
     double base, arg, lx = 1.0, le = 0.0;
@@ -335,6 +373,12 @@ EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, d
     if (use_log) arg = le * fast_log(lx);
     if (z > 32000.0 || z != z) arg = -(z - 32000.0) * (M.g0 * inv_RT);   /* -(z-32000)/(R*T/g) */
     p = base * fast_exp(arg);
+}
+
+EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, double &p)
+{
+    int j = 0;
+    atmosphere(M, z, j, T, inv_RT, p);
 }
 
 /* environment.py:105-108 */
@@ -440,7 +484,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
 
     /* :328-338  atmosphere + wind */
     double T, inv_RT, p;
-    atmosphere(M, s.z, T, inv_RT, p);
+    atmosphere(M, s.z, WB.j_atm, T, inv_RT, p);
     const double rho = p * inv_RT;
     double w[3];
     wind_at(M, wind_alt, S, s.z, WB, w);
@@ -927,7 +971,7 @@ EMC_HD void wind_bracket_reset(WindBracket &B)
 {
     B.lo = 1.0; B.hi = 0.0; B.x0 = 0.0;     /* empty interval: first use loads */
     B.f0[0] = B.f0[1] = B.f0[2] = 0.0; B.s[0] = B.s[1] = B.s[2] = 0.0;
-    B.j_m = 1; B.j_th = 1;
+    B.j_m = 1; B.j_th = 1; B.j_atm = 0;
 }
 
 /* motor.py:86-93 */

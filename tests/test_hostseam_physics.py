@@ -125,14 +125,17 @@ def test_seam_components_match_reference():
 
 
 def test_troposphere_pressure_series_matches_the_power_law():
-    """The engine evaluates p0*(T/T0)^(g/(R L)) below the tropopause as one polynomial (DevModel.tp_c); it must agree with
-    the reference's expression (environment.py:28-33, through the oracle) to rounding over the whole layer, hand over to
-    the general path outside [-2 km, tropopause] without a jump, and switch itself off for an atmosphere it cannot
-    represent."""
+    """The engine evaluates the layered pressure law as polynomials in altitude (DevModel.tp_c below the tropopause, the
+    at_* segments above it up to 100 km); they must agree with the reference's expressions (environment.py:26-103, through
+    the oracle) to rounding over every layer and at every layer edge, hand over to the exp/log path outside without a
+    jump, and switch themselves off for an atmosphere they cannot represent."""
     import ctypes as C
     z = util.golden("components")
     md = _abi.model_from_npz(z, "liquid_")
-    alt = np.concatenate([np.linspace(-2500.0, 12000.0, 3001), [-2000.0, -2000.0000001, 11000.0, 11000.0000001, 0.0, -0.0]])
+    edges = np.array([11000.0, 20000.0, 25000.0, 32000.0, 32000.0 + 48.65 / 0.0028, 100000.0])
+    alt = np.concatenate([np.linspace(-2500.0, 12000.0, 3001), [-2000.0, -2000.0000001, 11000.0, 11000.0000001, 0.0, -0.0],
+                          np.linspace(11000.0, 105000.0, 9401), edges, np.nextafter(edges, 0), np.nextafter(edges, 1e9),
+                          [1e6, np.inf]])
     got = util.hostseam_component(md, 0, (alt,))
     L = O.lib()
     m, keep = _abi.pack_model(md)
@@ -142,6 +145,7 @@ def test_troposphere_pressure_series_matches_the_power_law():
         L.orc_atmosphere(C.byref(m), C.c_double(a), C.byref(T), C.byref(p), C.byref(rho))
         ref[:, i] = (T.value, p.value, rho.value)
     np.testing.assert_allclose(got[:3], ref, rtol=3e-15)
+    assert np.isnan(util.hostseam_component(md, 0, (np.array([np.nan]),))[:3]).all()
     # a lapse rate the series cannot cover in 17 terms falls back to exp/log and still matches
     md2 = dict(md); md2["temperature_lapse_rate"] = 0.02
     got2 = util.hostseam_component(md2, 0, (alt[:3001:50],))
