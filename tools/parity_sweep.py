@@ -1,0 +1,59 @@
+"""Developer tool (GPU box): one-off wide parity check of the CUDA path against the C oracle on the bench workloads
+(more samples than the test-suite affords).  Prints one JSON line per workload."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import bench  # noqa: E402
+import oracle_lib as O  # noqa: E402
+import util  # noqa: E402
+from erpl_monte_carlo_sim_b200 import _abi, _lib  # noqa: E402
+
+eng = _lib.Engine(0)
+for workload, n, seed0 in (("c3", int(os.environ.get("N_C3", "20000")), 300000), ("planar", int(os.environ.get("N_PLANAR", "1500")), 700000)):
+    md, blk, wind, _ = bench.make_workload(workload, n, seed0)
+    eng.set_model(md)
+    out, iout = eng.run_batch(blk, wind)
+    t0 = time.time()
+    ref, iref = O.batch(md, blk, wind)
+    t_or = time.time() - t0
+    same = np.all(iout == iref, axis=0)
+    sens = util.oracle_sensitivity(md, blk, wind)
+    err = util.summary_errors(out, ref)
+    finite = np.isfinite(err)
+    tol = np.maximum(1e-6, 10.0 * sens)
+    bad = finite & (err > tol) & same[None, :]
+    well = np.all(sens < 1e-9, axis=0) & same        # well-conditioned flights: plain 1e-6 rule, and how close we really are
+    from erpl_monte_carlo_sim_b200 import MonteCarloAnalyzer
+    OUT = _abi.OUT
+    mask = lambda o: MonteCarloAnalyzer.outlier_mask(o[OUT["apogee_altitude"]], o[OUT["range"]], o[OUT["flight_time"]])
+    mg, mr = mask(out), mask(ref)
+    differ = ~same
+    if os.environ.get("VERBOSE"):
+        names = list(OUT)
+        for f, i in list(zip(*np.nonzero(bad)))[:40]:
+            print("  violation", int(i), names[f], "err %.2e sens %.2e" % (err[f, i], sens[f, i]), "ref", ref[f, i], "got", out[f, i],
+                  "valid" if not mr[i] else "outlier", "steps", int(iref[0, i]), "first_nan", int(iref[3, i]), flush=True)
+        ev = np.where(np.isfinite(err), err, 0.0)[:, ~mr]
+        worst = np.argsort(-ev.max(axis=0))[:5]
+        vi = np.flatnonzero(~mr)
+        for w in worst:
+            f = int(np.argmax(ev[:, w])); i = int(vi[w])
+            print("  valid-worst", i, names[f], "err %.2e sens %.2e" % (err[f, i], sens[f, i]), "ref", ref[f, i], "got", out[f, i], flush=True)
+        for i in np.flatnonzero(differ & ~(np.isnan(out[OUT["max_speed"]]) & np.isnan(ref[OUT["max_speed"]])))[:10]:
+            print("  differ-not-both-nan", int(i), iout[:, i].tolist(), iref[:, i].tolist(), "max_speed", out[OUT["max_speed"], i], ref[OUT["max_speed"], i], flush=True)
+    print(json.dumps({"workload": workload, "n": n, "first_seed": seed0, "integer_outputs_identical": int(same.sum()),
+                      "integer_mismatch": int((~same).sum()),
+                      "integer_mismatch_all_blown_up_in_both (max_speed inf or NaN)": bool(not np.any(np.isfinite(out[OUT["max_speed"]][differ])) and not np.any(np.isfinite(ref[OUT["max_speed"]][differ]))),
+                      "valid_flights": int((~mr).sum()), "valid_sets_identical": bool(np.array_equal(mg, mr)),
+                      "valid_flights_integer_exact": bool(np.array_equal(iout[:, ~mr], iref[:, ~mr])),
+                      "valid_flights_max_scaled_error": float(np.nanmax(err[:, ~mr])) if (~mr).any() else None,
+                      "violations_beyond_conditioning_aware_tolerance": int(bad.sum()),
+                      "well_conditioned_flights": int(well.sum()),
+                      "max_scaled_error_well_conditioned": float(np.nanmax(np.where(np.isfinite(err[:, well]), err[:, well], 0.0))) if well.any() else None,
+                      "oracle_seconds": round(t_or, 1)}), flush=True)
