@@ -151,8 +151,8 @@ struct Diag {
 EMC_HD double py_max(double a, double b) { return (b > a) ? b : a; }   /* Python max(a, b) */
 EMC_HD double py_min(double a, double b) { return (b < a) ? b : a; }   /* Python min(a, b) */
 /* running np.max / np.min over a series: NaN propagates and sticks */
-EMC_HD void np_max_acc(double &m, double v) { m = (v > m || v != v) ? v : m; }   /* a NaN m stays: both tests are False */
-EMC_HD void np_min_acc(double &m, double v) { m = (v < m || v != v) ? v : m; }
+EMC_HD void np_max_acc(double &m, double v) { if (v > m || v != v) m = v; }   /* a NaN m stays: both tests are False */
+EMC_HD void np_min_acc(double &m, double v) { if (v < m || v != v) m = v; }
 
 /* ---------------- cheap reciprocal / reciprocal square root / atan2 ----------------
  * Device: MUFU seed + Newton steps in DFMA, no slow-path branches (operands here are positive, normal
