@@ -731,17 +731,19 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
     Diag dg;
     dg.mach2 = dg.qdyn = dg.abs_aoa = dg.stab = 0.0;
     const bool fin = K.finishing;
+    /* the sticky parachute flag (F12) is carried in registers through the four stages and written back once */
     const bool chute_keep = K.chute;
-    const double chute_time_keep = K.chute_time;
+    bool chute = chute_keep;
+    double chute_time = K.chute_time;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int stage = 0; stage < 4; ++stage) {
         const double ts = K.t + ((stage == 0) ? 0.0 : ((stage == 3) ? M.dt : M.half_dt));   /* warp-uniform offset */
-        derivative(M, Tb, wind_alt, S, WB, ts, ys, K.chute, K.chute_time, k, stage == 0, dg);
+        derivative(M, Tb, wind_alt, S, WB, ts, ys, chute, chute_time, k, stage == 0, dg);
         if (stage == 0) {
             track_diag(K, ys, dg);                      /* ys == s at stage 0 */
-            if (fin) { K.chute = chute_keep; K.chute_time = chute_time_keep; return false; }
+            if (fin) return false;                      /* diagnostic pass only: a latch by this evaluation is dropped */
         }
         if (stage < 3) {
             /* acc = k1 + 2 k2 + 2 k3 (+ k4 below), in the reference's order ((k1 + 2k2) + 2k3) + k4 (:224);
@@ -774,6 +776,7 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
     const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
     if (n2 > 1e-24) { const double rn = fast_rsqrt(n2); st.set_s(6, q0 * rn); st.set_s(7, q1 * rn); st.set_s(8, q2 * rn); st.set_s(9, q3 * rn); }
     else { st.set_s(6, 1.0); st.set_s(7, 0.0); st.set_s(8, 0.0); st.set_s(9, 0.0); }
+    if (chute != chute_keep) { K.chute = true; K.chute_time = chute_time; }
     K.t += M.dt;
     return true;
 }
