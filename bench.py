@@ -27,8 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE flight-kernel launch on this workload (100 k C3 samples), from
-# `ncu --set full` (profiles/r1_flight_kernel_bench.txt): 31.81 MB + 0.53 MB.  Algorithmic bytes: 30.4 MB in + 30 MB out.
-FLIGHT_KERNEL_DRAM_BYTES_100K = 32.34e6
+# `ncu --set full` (profiles/r1_flight_kernel_bench.txt): 32.28 MB + 0.54 MB.  Algorithmic bytes: 30.4 MB in + 30 MB out.
+FLIGHT_KERNEL_DRAM_BYTES_100K = 32.82e6
 STATS_LAUNCHES = 2 + 2 + 6         # N > 1, pass by pass: moments1 (+1 finish), moments2 (+1 finish), 6 radix-select passes over all three metrics
 STATS_LAUNCHES_FUSED = 2 + 1 + 2 + 12   # N = 1, emc_stats_summary: moments1 + finish, plan, moments2 + finish, 6 x (digit histogram + digit decision)
 FLOP_PER_STEP = 1600.0          # 4*348 + 203 ~ 1.6 kflop per accepted RK4 step
