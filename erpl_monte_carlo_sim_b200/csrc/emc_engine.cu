@@ -4,12 +4,15 @@
  * Kernels
  *   emc_rail_kernel        one thread per sample, convergent: the launch-rail Euler loop
  *                          (reference simulator.py:42-125) -> rail_* outputs = state at rail exit.
- *   emc_flight_kernel      PERSISTENT: one trajectory per lane, state in registers; lanes whose
+ *   emc_flight_kernel      PERSISTENT: one trajectory per lane — the stage state and the derivative in registers, the
+ *                          base state, the RK4 accumulator and the per-lane bookkeeping in shared memory; lanes whose
  *                          trajectory ended (simulator.py:238-264) are found with a warp ballot and
  *                          refilled from a global atomic work queue, so a warp never idles behind its
  *                          longest flight.  Run-constant tables (Cd/CP vs Mach, thrust curve, wind
- *                          altitude grid) are staged once into shared memory; scalars sit in
- *                          __constant__ memory.  Summaries are written as field-major SoA.
+ *                          altitude grid) are staged once into shared memory; scalars and the atmosphere
+ *                          polynomials sit in __constant__ memory.  Summaries are written as field-major SoA.
+ *   emc_stats_*_kernel     classification, moments, exact percentiles (emc_stats.cuh); emc_generate_kernel /
+ *                          emc_numpy_draws_kernel: dispersions drawn on the device (emc_philox.cuh).
  *   emc_derivative_kernel  test seam: one derivative evaluation per thread (simulator.py:295-460).
  *   emc_dfma_kernel        register-resident DFMA chains: measures the FP64 roofline denominator.
  *

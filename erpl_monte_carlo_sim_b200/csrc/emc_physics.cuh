@@ -15,8 +15,9 @@
  *
  * It is NOT a transliteration.  Per-run constants are folded on the host (DevModel), table slopes
  * are precomputed, reciprocals are shared, sin/cos of the aerodynamic angles come from velocity
- * ratios instead of sincos(atan2()), pow() is exp(e*log()) with one shared exp() for all five
- * atmosphere layers, and the four RK4 stages share one copy of the derivative code.  These changes
+ * ratios instead of sincos(atan2()), the layered pressure law is evaluated as per-layer polynomials in
+ * altitude (exp(e*log()) only outside them), the Cd and CP tables share one Mach search, and the four
+ * RK4 stages share one copy of the derivative code.  These changes
  * move results by a few ulp per evaluation; the parity bar is 1e-6 relative per flight (tests/).
  * Python/NumPy NaN semantics of max()/min()/np.interp/np.argmax are kept where they decide control
  * flow.
