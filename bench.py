@@ -29,8 +29,7 @@ sys.path.insert(0, ROOT)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE flight-kernel launch on this workload (100 k C3 samples), from
 # `ncu --set full` (profiles/r1_flight_kernel_bench.txt): 32.28 MB + 0.54 MB.  Algorithmic bytes: 30.4 MB in + 30 MB out.
 FLIGHT_KERNEL_DRAM_BYTES_100K = 32.82e6
-STATS_LAUNCHES = 2 + 2 + 6         # N > 1, pass by pass: moments1 (+1 finish), moments2 (+1 finish), 6 radix-select passes over all three metrics
-STATS_LAUNCHES_FUSED = 2 + 1 + 2 + 12   # N = 1, emc_stats_summary: moments1 + finish, plan, moments2 + finish, 6 x (digit histogram + digit decision)
+STATS_LAUNCHES_FUSED = 2 + 1 + 2 + 12   # the statistics chain: moments1 + finish, plan, moments2 + finish, 6 x (digit histogram + digit decision); NCCL kernels not counted
 FLOP_PER_STEP = 1600.0          # 4*348 + 203 ~ 1.6 kflop per accepted RK4 step
 CSV_ALT = np.array([0.0, 5000.0, 10000.0, 15000.0, 20000.0, 25000.0])                # sample_wind.csv:2-7
 CSV_WIND = np.array([[2.0, 0, 0], [5, 1, 0], [8, 2, 0], [10, 2, 0], [12, 3, 0], [15, 3, 0]], float)
@@ -292,7 +291,7 @@ def main():
                          "hbm": hbm_side(blk, wind, h_out, h_iout, flight_ms / a.steps, world)},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
                     "h2d_bytes_per_step": int(blk.nbytes + wind.nbytes), "d2h_bytes_per_step": int(h_out.nbytes + h_iout.nbytes)},
-            "gpu_launches": (2 + (STATS_LAUNCHES_FUSED if world == 1 else STATS_LAUNCHES)) * a.steps * world,
+            "gpu_launches": (2 + STATS_LAUNCHES_FUSED) * a.steps * world,
             "clocks": sampler.summary(),
             "statistics": {k: last_stats[0][k] for k in ("n_total", "n_samples", "n_outliers", "apogee_altitude", "range", "flight_time", "landing_ellipse")},
             "e2e_equals_resident": parity_hint,

@@ -88,6 +88,10 @@ def load():
     L.emc_stats_select_hist3.restype = C.c_int
     L.emc_stats_summary.argtypes = [vp, vp, i64, i64, _dp, C.c_int, _dp]
     L.emc_stats_summary.restype = C.c_int
+    L.emc_stats_summary_stage.argtypes = [vp, vp, i64, i64, _dp, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), _dp]
+    L.emc_stats_summary_stage.restype = C.c_int
+    L.emc_stream.argtypes = [vp, C.POINTER(C.c_void_p)]
+    L.emc_stream.restype = C.c_int
     L.emc_stats_linear_hist.argtypes = [vp, vp, i64, i64, C.c_int, C.c_double, C.c_double, C.c_int, vp]
     L.emc_generate_inputs.argtypes = [vp, C.POINTER(_abi.EmcDispersion), C.c_uint64, i64, i64, _dp, i64, _dp, vp, i64, vp]
     L.emc_run_batch_staged.argtypes = [vp, i64, C.POINTER(_abi.EmcOutputs), C.POINTER(_abi.EmcRunOpts)]

@@ -961,12 +961,13 @@ EMC_EXPORT int emc_stats_moments2(emc_ctx *ctx, const double *out_dev, int64_t l
     return EMC_OK;
 }
 
-EMC_EXPORT int emc_stats_summary(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct,
-                                 double *result)
+/* One stage of the summary chain, enqueued on the context stream without synchronising (stage 14 copies the result and
+ * synchronises).  Stages: 0 moments1 -> block sum|min|max (20 words); 1 plan + moments2 -> block s2 (6 words);
+ * 2+2k digit histogram of pass k -> block hist (3*2*n_pct*2048 words); 3+2k digit decision of pass k; 14 end.
+ * A multi-GPU caller all-reduces `block` on the same stream between stages; a single GPU just runs 0..14. */
+static int summary_stage(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct, int stage,
+                         void **block_dev, int64_t *block_words, double *result)
 {
-    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
-    if (!result || !percentiles || n_pct < 1 || n_pct > EMC_SUMMARY_MAX_PCT) return fail(ctx, EMC_ERR_INVALID, "emc_stats_summary: bad argument (1 <= n_pct <= 8)");
-    CK(cudaSetDevice(ctx->device));
     const int nt = 2 * n_pct, rows = 3 * nt;
     const size_t res_words = 32 + (size_t)rows, words = res_words + 2 * (size_t)rows + (size_t)rows * EMC_SELECT_BINS;
     CK(grow(&ctx->d_summary, &ctx->cap_summary, words));
@@ -975,29 +976,74 @@ EMC_EXPORT int emc_stats_summary(emc_ctx *ctx, const double *out_dev, int64_t ld
     L.prefix = reinterpret_cast<unsigned long long *>(ctx->d_summary + res_words);
     L.rem = reinterpret_cast<long long *>(ctx->d_summary + res_words + rows);
     L.hist = reinterpret_cast<unsigned long long *>(ctx->d_summary + res_words + 2 * (size_t)rows);
-    SummaryPct P;
-    memset(&P, 0, sizeof P);
-    P.n_pct = n_pct;
-    for (int j = 0; j < n_pct; ++j) P.pct[j] = percentiles[j];
     const int g = stats_grid(ctx, n);
     CK(grow(&ctx->d_partial, &ctx->cap_partial, (size_t)g * (ST_SUM_COUNT + 2 * ST_MM_COUNT)));
     double *ps = ctx->d_partial, *pmin = ps + (size_t)g * ST_SUM_COUNT, *pmax = pmin + (size_t)g * ST_MM_COUNT;
     cudaStream_t st = ctx->stream;
-    CK(cudaMemsetAsync(ctx->d_summary, 0, sizeof(double) * words, st));
-    emc_stats_moments1_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, ps, pmin, pmax);
-    emc_stats_finish3_kernel<<<1, 32, 0, st>>>(ps, pmin, pmax, g, L.res);
-    emc_stats_plan_kernel<<<1, 32, 0, st>>>(L, P);
-    emc_stats_moments2_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, L.res + 26, ps);
-    emc_stats_finish_kernel<<<1, 32, 0, st>>>(ps, g, ST2_COUNT, 0, L.res + 20);
+    if (block_dev) *block_dev = nullptr;
+    if (block_words) *block_words = 0;
     static const int passes[6][2] = { { 55, 64 }, { 44, 55 }, { 33, 44 }, { 22, 33 }, { 11, 22 }, { 0, 11 } };
-    for (int k = 0; k < 6; ++k) {
-        const int shift = passes[k][0], pshift = passes[k][1];
-        emc_stats_select_dev_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, L, shift, pshift);
-        emc_stats_select_finish_kernel<<<rows, 32, 0, st>>>(L, (pshift >= 64) ? 64 - shift : pshift - shift, k == 5);
+    if (stage == 0) {
+        CK(cudaMemsetAsync(ctx->d_summary, 0, sizeof(double) * words, st));
+        emc_stats_moments1_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, ps, pmin, pmax);
+        emc_stats_finish3_kernel<<<1, 32, 0, st>>>(ps, pmin, pmax, g, L.res);
+        if (block_dev) *block_dev = L.res;
+        if (block_words) *block_words = ST_SUM_COUNT + 2 * ST_MM_COUNT;
+    } else if (stage == 1) {
+        SummaryPct P;
+        memset(&P, 0, sizeof P);
+        P.n_pct = n_pct;
+        for (int j = 0; j < n_pct; ++j) P.pct[j] = percentiles[j];
+        emc_stats_plan_kernel<<<1, 32, 0, st>>>(L, P);
+        emc_stats_moments2_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, L.res + 26, ps);
+        emc_stats_finish_kernel<<<1, 32, 0, st>>>(ps, g, ST2_COUNT, 0, L.res + 20);
+        if (block_dev) *block_dev = L.res + 20;
+        if (block_words) *block_words = ST2_COUNT;
+    } else if (stage >= 2 && stage <= 13) {
+        const int k = (stage - 2) / 2, shift = passes[k][0], pshift = passes[k][1];
+        if ((stage & 1) == 0) {
+            emc_stats_select_dev_kernel<<<g, 256, 0, st>>>(out_dev, ld, n, L, shift, pshift);
+            if (block_dev) *block_dev = L.hist;
+            if (block_words) *block_words = (int64_t)rows * EMC_SELECT_BINS;
+        } else {
+            emc_stats_select_finish_kernel<<<rows, 32, 0, st>>>(L, (pshift >= 64) ? 64 - shift : pshift - shift, k == 5);
+        }
+    } else if (stage == 14) {
+        if (!result) return fail(ctx, EMC_ERR_INVALID, "emc_stats_summary: NULL result");
+        CK(cudaMemcpyAsync(result, L.res, sizeof(double) * res_words, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    } else {
+        return fail(ctx, EMC_ERR_INVALID, "emc_stats_summary_stage: stage must be 0..14");
     }
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(result, L.res, sizeof(double) * res_words, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_stats_summary_stage(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct,
+                                       int stage, void **block_dev, int64_t *block_words, double *result)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!percentiles || n_pct < 1 || n_pct > EMC_SUMMARY_MAX_PCT) return fail(ctx, EMC_ERR_INVALID, "emc_stats_summary_stage: bad argument (1 <= n_pct <= 8)");
+    CK(cudaSetDevice(ctx->device));
+    return summary_stage(ctx, out_dev, ld, n, percentiles, n_pct, stage, block_dev, block_words, result);
+}
+
+EMC_EXPORT int emc_stats_summary(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct,
+                                 double *result)
+{
+    if (int rc = stats_source(ctx, out_dev, ld, n)) return rc;
+    if (!result || !percentiles || n_pct < 1 || n_pct > EMC_SUMMARY_MAX_PCT) return fail(ctx, EMC_ERR_INVALID, "emc_stats_summary: bad argument (1 <= n_pct <= 8)");
+    CK(cudaSetDevice(ctx->device));
+    for (int stage = 0; stage <= 14; ++stage)
+        if (int rc = summary_stage(ctx, out_dev, ld, n, percentiles, n_pct, stage, nullptr, nullptr, result)) return rc;
+    return EMC_OK;
+}
+
+/* the context's CUDA stream (cudaStream_t), for callers that enqueue their own work between stages (NCCL all-reduce) */
+EMC_EXPORT int emc_stream(emc_ctx *ctx, void **stream)
+{
+    if (!ctx || !stream) return fail(ctx, EMC_ERR_INVALID, "emc_stream: NULL argument");
+    *stream = (void *)ctx->stream;
     return EMC_OK;
 }
 

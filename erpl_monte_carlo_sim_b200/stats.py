@@ -67,6 +67,7 @@ class DeviceBackend:
         self.out_ptr = C.c_void_p(out_dev) if out_dev else None
         self.ld = int(ld) if ld is not None else 0
         self.distributed = _dist_active() if distributed is None else bool(distributed)
+        self.stream_ordered_collectives = True       # NCCL all-reduce can be enqueued on the engine's stream
         words = NSUM + 2 * NMM + 5 + N2 + 3 * MAXP * BINS
         base = C.c_void_p()
         engine._check(engine._lib.emc_scratch(engine._ctx, words * 8, C.byref(base)), "emc_scratch")
@@ -96,14 +97,37 @@ class DeviceBackend:
         return allv[:NSUM], allv[NSUM:NSUM + NMM], allv[NSUM + NMM:]
 
     def summary(self, percentiles):
-        """Single-GPU fast path: every pass chained on the device, one synchronisation (emc_stats_summary).
+        """Every pass chained on the device, one host synchronisation.  One GPU: emc_stats_summary.  Several GPUs: the same
+        chain stage by stage (emc_stats_summary_stage) with the small blocks all-reduced between stages ON THE ENGINE'S
+        STREAM (NCCL, stream-ordered: no host round trip either).
         Returns (sum, min, max, s2, val) with val[f][2j], val[f][2j+1] the lo / hi order statistic of percentile j."""
         e = self.e
         npct = len(percentiles)
         pct = (C.c_double * npct)(*[float(p) for p in percentiles])
         res = np.empty(32 + 3 * 2 * npct, np.float64)
-        e._check(e._lib.emc_stats_summary(e._ctx, self.out_ptr, self.ld, self.n, pct, npct, res.ctypes.data_as(C.POINTER(C.c_double))),
-                 "emc_stats_summary")
+        rp = res.ctypes.data_as(C.POINTER(C.c_double))
+        if self.distributed:
+            import torch
+            import torch.distributed as dist
+            sp = C.c_void_p()
+            e._check(e._lib.emc_stream(e._ctx, C.byref(sp)), "emc_stream")
+            dev = torch.device("cuda", e.device)
+            ext = torch.cuda.ExternalStream(sp.value, device=dev)
+            with torch.cuda.stream(ext):
+                for stage in range(15):
+                    bp, bw = C.c_void_p(), C.c_int64()
+                    e._check(e._lib.emc_stats_summary_stage(e._ctx, self.out_ptr, self.ld, self.n, pct, npct, stage, C.byref(bp),
+                                                            C.byref(bw), rp), "emc_stats_summary_stage")
+                    if bp.value:
+                        if stage == 0:
+                            for off, cnt, op in ((0, NSUM, dist.ReduceOp.SUM), (NSUM, NMM, dist.ReduceOp.MIN), (NSUM + NMM, NMM, dist.ReduceOp.MAX)):
+                                dist.all_reduce(torch.as_tensor(DeviceBlock(e, bp.value + 8 * off, cnt, np.float64), device=dev), op=op)
+                        elif stage == 1:
+                            dist.all_reduce(torch.as_tensor(DeviceBlock(e, bp.value, bw.value, np.float64), device=dev))
+                        else:
+                            dist.all_reduce(torch.as_tensor(DeviceBlock(e, bp.value, bw.value, np.uint64), device=dev).view(torch.int64))
+        else:
+            e._check(e._lib.emc_stats_summary(e._ctx, self.out_ptr, self.ld, self.n, pct, npct, rp), "emc_stats_summary")
         return (res[:NSUM], res[NSUM:NSUM + NMM], res[NSUM + NMM:NSUM + 2 * NMM], res[20:26],
                 res[32:].reshape(3, 2 * npct))
 
@@ -212,8 +236,8 @@ def radix_select(backend, field, ranks):
 
 def compute_statistics(backend, histogram_bins=0):
     fused = None
-    if hasattr(backend, "summary") and getattr(backend, "fused", True) and not getattr(backend, "distributed", True) \
-            and len(PERCENTILES) <= 8:
+    if hasattr(backend, "summary") and getattr(backend, "fused", True) and len(PERCENTILES) <= 8 \
+            and (not getattr(backend, "distributed", True) or getattr(backend, "stream_ordered_collectives", False)):
         fused = backend.summary(PERCENTILES)          # one stream-ordered chain on the device, one host sync
         s, mn, mx = fused[0], fused[1], fused[2]
     else:

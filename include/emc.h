@@ -314,6 +314,14 @@ int emc_stats_select_hist3(emc_ctx *ctx, const double *out_dev, int64_t ld, int6
  * whose blocks are all-reduced between passes. */
 int emc_stats_summary(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct,
                       double *result);
+/* The same chain one stage at a time, for several GPUs: every stage is only ENQUEUED on the context stream; after the
+ * stages that return a block (0: sum[14] | min[3] | max[3]; 1: s2[6]; 2, 4, .., 12: the digit histograms, uint64) the
+ * caller all-reduces that block across ranks on the same stream (emc_stream) and goes on; stage 14 copies the result
+ * (layout of emc_stats_summary, now over the whole job) and synchronises.  Stages 0..14 in order. */
+int emc_stats_summary_stage(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, const double *percentiles, int n_pct,
+                            int stage, void **block_dev, int64_t *block_words, double *result);
+/* the context's cudaStream_t */
+int emc_stream(emc_ctx *ctx, void **stream);
 
 /* fixed-bin histogram over the valid samples; field 0 apogee, 1 range, 2 flight_time, 3 landing x, 4 landing y */
 int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, double lo, double hi,
