@@ -2,21 +2,29 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|planar]
 
-A "step" is one pass of the hot path (rail phase + RK4 flight + summaries) over one batch of dispersed
-samples.  Default workload = BASELINE config C3: SolidMotor + sample_wind.csv altitude-resolved wind +
-stochastic perturbations, 100 000 host-seeded samples per GPU (weak scaling; rank r flies seeds
-r*S .. (r+1)*S-1).  One JSON line on stdout (rank 0).
+A "step" is one pass of the hot path (rail phase + RK4 flight + summaries + device statistics) over one batch of
+dispersed samples.  Default workload = BASELINE config C3: SolidMotor + sample_wind.csv altitude-resolved wind +
+stochastic perturbations, 100 000 host-seeded samples per GPU (weak scaling; rank r flies seeds r*S .. (r+1)*S-1).
+One JSON line on stdout (rank 0).
 
-  value   trajectories/s with the inputs resident in HBM (device-pointer entry of the C ABI)
-  e2e     same metric through the host-buffer entry emc_run_batch, pinned host buffers, H2D + D2H inside
-  roofline.bound = "fp64": achieved = RK4 steps/s x 1600 flop (SURVEY.md §8d canonical count) against the
-          DFMA peak measured in the same run (MEASURED_PEAKS.json has no FP64 entry)
-  cpu_baseline   the C oracle (port of the reference path) on this box's host cores, bounded sample
-  --impl reference   the same CPU port timed as its own arm (the Python reference cannot travel to the box)
+  value     trajectories/s with the inputs resident in HBM (device-pointer entry of the C ABI), statistics included
+  e2e       same step through the host-buffer entry emc_run_batch (pinned host buffers, H2D + kernels + D2H inside) with the
+            same statistics chain (all-reduced over NCCL for N > 1)
+  e2e_api   wall time of the drop-in call MonteCarloAnalyzer.run_monte_carlo(ic, n_samples = S x N) itself, sharded over the
+            ranks, for rng = numpy-device and philox (and host numpy draws on a bounded sample)
+  roofline.bound = "fp64": achieved = RK4 steps/s x 1600 flop (SURVEY.md §8d canonical count) against the DFMA peak
+            measured in the same run (MEASURED_PEAKS.json has no FP64 entry)
+  secondary at EVERY N: the planar launch->landing set W-B (100 k / GPU) against the 1e6 traj/s target on 8 GPUs, config
+            C4 (1.25 M / GPU, device dispersions, through run_monte_carlo), a 1 M-sample C3 batch, the downsampled batch
+            tape with its HBM GB/s — each with per-rank flight-kernel times
+  cpu_baseline   the C oracle (port of the reference path) on this box's host cores, bounded sample; plus
+            cpu_baseline.python_reference: the unmodified Python reference's own run_monte_carlo from baseline/_ref
+  --impl reference   the CPU port timed as its own arm (all host threads)
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -27,21 +35,29 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE flight-kernel launch on this workload (100 k C3 samples), from
-# `ncu --set full` (profiles/r1_flight_kernel_bench.txt): 32.28 MB + 0.54 MB.  Algorithmic bytes: 30.4 MB in + 30 MB out.
+# `ncu --set full` (profiles/): algorithmic bytes are 30.4 MB in + 30 MB out (the rail kernel writes part of the outputs).
 FLIGHT_KERNEL_DRAM_BYTES_100K = 32.82e6
 STATS_LAUNCHES_FUSED = 2 + 1 + 2 + 12   # the statistics chain: moments1 + finish, plan, moments2 + finish, 6 x (digit histogram + digit decision); NCCL kernels not counted
 FLOP_PER_STEP = 1600.0          # 4*348 + 203 ~ 1.6 kflop per accepted RK4 step
 CSV_ALT = np.array([0.0, 5000.0, 10000.0, 15000.0, 20000.0, 25000.0])                # sample_wind.csv:2-7
 CSV_WIND = np.array([[2.0, 0, 0], [5, 1, 0], [8, 2, 0], [10, 2, 0], [12, 3, 0], [15, 3, 0]], float)
+IC_C3 = {"position": [0.0, 0.0, 10.0], "velocity": [0.0, 0.0, 0.0], "attitude": [0.0, -np.pi / 2 + 0.02, 0.0],
+         "angular_velocity": [0.0, 0.0, 0.0]}
+IC_C4 = {"position": [0.0, 0.0, 0.0], "velocity": [0.0, 0.0, 0.0], "attitude": [0.0, -np.pi / 2 + 0.02, 0.0],
+         "angular_velocity": [0.0, 0.0, 0.0]}
+
+
+def c3_analyzer(device=None):
+    from erpl_monte_carlo_sim_b200 import MonteCarloAnalyzer, Rocket, SolidMotor, StandardAtmosphere, WindModel
+    mc = MonteCarloAnalyzer(Rocket(), SolidMotor(), StandardAtmosphere(), WindModel(), device=device)
+    mc.base_altitude_profile, mc.base_wind_profile = CSV_ALT, CSV_WIND.copy()
+    return mc
 
 
 def make_workload(name, n, first_seed):
     """Host-seeded dispersions of the named configuration -> (model dict, scalars, wind, description)."""
-    from erpl_monte_carlo_sim_b200 import (MonteCarloAnalyzer, Rocket, SolidMotor, StandardAtmosphere, WindModel, marshal)
-    mc = MonteCarloAnalyzer(Rocket(), SolidMotor(), StandardAtmosphere(), WindModel())
-    mc.base_altitude_profile, mc.base_wind_profile = CSV_ALT, CSV_WIND.copy()
-    ic = {"position": [0.0, 0.0, 10.0], "velocity": [0.0, 0.0, 0.0], "attitude": [0.0, -np.pi / 2 + 0.02, 0.0],
-          "angular_velocity": [0.0, 0.0, 0.0]}
+    from erpl_monte_carlo_sim_b200 import marshal
+    mc = c3_analyzer(device=0)
     disp = mc.draw_parameters(n, first_seed=first_seed)
     desc = "C3: SolidMotor + sample_wind.csv 6-knot wind + stochastic perturbations, reference default dispersions, vertical launch"
     if name == "planar":
@@ -50,7 +66,7 @@ def make_workload(name, n, first_seed):
         disp.omega[:, 0] = 0.0; disp.omega[:, 2] = 0.0
         disp.wind_direction[:] = np.where(disp.seed % 2 == 0, 0.0, np.pi)
         desc = "W-B planar projection of C3 (beta == 0): launch -> apogee -> parachute -> landing"
-    blk, wind, alts = mc.build_inputs(ic, disp)
+    blk, wind, alts = mc.build_inputs(IC_C3, disp)
     if name == "planar":
         wind[:, :, 1] = 0.0
     md = marshal.model_dict(mc.rocket, mc.motor, mc.atmosphere, mc._model_simulator(), alts)
@@ -99,30 +115,144 @@ def cpu_baseline(md, blk, wind, n_cpu, threads=0):
     t0 = time.perf_counter()
     out, iout = O.batch(md, sc, w, n_threads=cores, diagnostics=True)
     dt = time.perf_counter() - t0
+    ns, fn = iout[0].astype(np.int64), iout[3].astype(np.int64)
+    integrated = int(np.where(fn >= 0, np.minimum(fn, ns), ns).sum())       # steps up to the first NaN state: what the GPU integrates
     return {"value": n_cpu / dt, "unit": "trajectories/s", "cores": cores, "kind": "port",
             "sample": f"first {n_cpu} samples of rank 0's batch, oracle/emc_oracle.c (C port of the reference path, "
-                      f"pthreads), {int(iout[0].sum())} RK4 steps in {dt:.2f} s",
-            "steps_per_s": float(iout[0].sum() / dt)}, dt
+                      f"pthreads), {int(ns.sum())} RK4 steps in {dt:.2f} s",
+            "steps_per_s": float(ns.sum() / dt),
+            "steps_per_s_counting_only_pre_nan_steps": float(integrated / dt),
+            "note": "the port, like the reference, grinds a NaN trajectory to max_time (~57 k steps); the GPU integrates to the first "
+                    "all-NaN state and replays the time axis in closed form, so compare per-step rates on the pre-NaN count"}, dt
 
 
-def secondary_measurements(eng, opts, peak_tf):
-    """Not the headline: the same kernel (a) on a batch large enough that the drain of the work queue is amortised
-    (C4's per-GPU share is 1.25 M samples) and (b) on the planar W-B set whose flights really reach landing."""
+def python_reference_baseline(samples=0):
+    """The unmodified Python reference's own run_monte_carlo (monte_carlo.py:52-90) on this box's cores, in a process of
+    its own (its ProcessPoolExecutor forks; this one has not touched CUDA yet).  Needs baseline/_ref."""
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "pyref_bench.py")] + (["--samples", str(samples)] if samples else [])
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd="/tmp")
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        return json.loads(line[-1]) if line else {"unavailable": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # pragma: no cover
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+
+
+def gather_ranks(values, world, dev):
+    """[world][len(values)] list of every rank's numbers (NCCL all_gather of one small tensor)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(values, dtype=torch.float64, device=dev)
+    if world == 1:
+        return [t.tolist()]
+    buf = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(buf, t)
+    return [b.tolist() for b in buf]
+
+
+def secondary_measurements(eng, opts, peak_tf, rank, world, dev, barrier, n_planar, n_c4, n_c3_big):
+    """Not the headline, but the numbers the north star names, at THIS N: (a) W-B planar launch->landing (flights that really
+    reach landing), (b) config C4 through the drop-in API, sharded, device dispersions, NCCL statistics, (c) a C3 batch
+    large enough that the drained tail is amortised, (d) the downsampled batch tape with its HBM rate."""
+    from erpl_monte_carlo_sim_b200 import LiquidMotor, MonteCarloAnalyzer, Rocket, StandardAtmosphere, WindModel, _abi, stats as emc_stats
     out = {}
-    for key, workload, n in (("c3_1M_samples", "c3", 1_000_000), ("planar_launch_to_landing_100k", "planar", 100_000)):
-        md, blk, wind, desc = make_workload(workload, n, 0)
+
+    def kernel_line(desc, n, c, wall, extra=None):
+        per_rank = gather_ranks([c["flight_ms"], c["rail_ms"], float(c["rk4_steps"]), wall * 1e3], world, dev)
+        fl = max(r[0] for r in per_rank); steps = sum(r[2] for r in per_rank); w = max(r[3] for r in per_rank)
+        sps = steps / (fl * 1e-3)
+        d = {"workload": desc, "samples_per_gpu": n, "n_gpus": world,
+             "trajectories_per_s": n * world / (w * 1e-3), "trajectories_per_s_kernels_only": n * world / ((fl + max(r[1] for r in per_rank)) * 1e-3),
+             "rk4_steps_per_s": sps, "mean_rk4_steps_per_trajectory": steps / (n * world),
+             "fp64_roofline_frac": sps * FLOP_PER_STEP * 1e-12 / (peak_tf * world),
+             "flight_ms_per_rank": [round(r[0], 3) for r in per_rank], "wall_ms": w}
+        if extra:
+            d.update(extra)
+        return d
+
+    # (a) W-B: host-seeded planar set, resident in HBM; wall = kernels + device statistics (all-reduced)
+    if n_planar > 0:
+        import torch
+        md, blk, wind, desc = make_workload("planar", n_planar, rank * n_planar)
         eng.set_model(md)
+        d_blk = torch.from_numpy(blk).to(dev); d_wind = torch.from_numpy(wind).to(dev)
+        d_out = torch.empty((_abi.OUT_COUNT, n_planar), dtype=torch.float64, device=dev)
+        d_iout = torch.empty((_abi.IOUT_COUNT, n_planar), dtype=torch.int32, device=dev)
         best = None
-        for _ in range(2):
-            eng.run_batch(blk, wind, opts=opts)
+        for rep in range(2):
+            barrier(); t0 = time.perf_counter()
+            eng.run_batch_device(d_blk.data_ptr(), n_planar, d_wind.data_ptr(), wind.shape[1] * 3, d_out.data_ptr(), d_iout.data_ptr(), n_planar, n_planar, opts)
             c = eng.counters()
-            if best is None or c["flight_ms"] < best["flight_ms"]:
-                best = c
-        ms = best["flight_ms"] + best["rail_ms"]
-        sps = best["rk4_steps"] / (best["flight_ms"] * 1e-3)
-        out[key] = {"workload": desc, "samples": n, "trajectories_per_s_kernels_only": n / (ms * 1e-3), "rk4_steps_per_s": sps,
-                    "mean_rk4_steps_per_trajectory": best["rk4_steps"] / n, "fp64_roofline_frac": sps * FLOP_PER_STEP * 1e-12 / peak_tf}
+            st = emc_stats.device_statistics(eng, n_planar, out_dev=d_out.data_ptr(), ld=n_planar, distributed=(world > 1))
+            barrier(); wall = time.perf_counter() - t0
+            if best is None or wall < best[1]:
+                best = (c, wall, st)
+        out["planar_launch_to_landing"] = kernel_line(desc, n_planar, best[0], best[1], {
+            "target": "north star: >= 1e6 launch->landing trajectories/s on 8 x B200", "valid_flights": best[2]["n_samples"],
+            "apogee_mean_m": best[2]["apogee_altitude"]["mean"], "flight_time_mean_s": best[2]["flight_time"]["mean"]})
+        # (d) the same launch with the downsampled tape armed for EVERY 16th sample (stride 20 = 0.1 s)
+        if rank == 0 and world >= 1:
+            sel = np.arange(0, n_planar, 16, dtype=np.int64)
+            rows_cap = 60000 // 20 + 4
+            eng.tape_request(sel, 20, rows_cap)
+            eng.run_batch_device(d_blk.data_ptr(), n_planar, d_wind.data_ptr(), wind.shape[1] * 3, d_out.data_ptr(), d_iout.data_ptr(), n_planar, n_planar, opts)
+            ct = eng.counters()
+            nbytes = ct["tape_rows"] * 32.0
+            out["batch_tape"] = {"workload": "W-B planar, tape armed for every 16th sample, every 20th stored state (0.1 s) as {t, x, y, z}",
+                                 "taped_samples": int(sel.size), "rows": int(ct["tape_rows"]), "bytes": nbytes,
+                                 "flight_ms_with_tape": ct["flight_ms"], "flight_ms_without": best[0]["flight_ms"],
+                                 "hbm_write_GBps": nbytes / (ct["flight_ms"] * 1e-3) / 1e9,
+                                 "note": "the tape is a trickle against HBM (32-byte rows, one sector per row): it costs launch time only through the extra per-step test"}
+        del d_blk, d_wind, d_out, d_iout
+    # (b) C4 through the product API: LiquidMotor, default 100-knot stochastic wind, Philox dispersions on the device
+    if n_c4 > 0:
+        mc = MonteCarloAnalyzer(Rocket(), LiquidMotor(), StandardAtmosphere(), WindModel())
+        mc.rng = "philox"; mc.trajectory_samples = 0; mc.run_opts = opts
+        best = None
+        for rep in range(2):
+            barrier(); t0 = time.perf_counter()
+            an = mc.run_monte_carlo(IC_C4, n_samples=n_c4 * world)
+            barrier(); wall = time.perf_counter() - t0
+            c = eng_counters_of(mc)
+            if best is None or wall < best[1]:
+                best = (c, wall, an)
+        an = best[2]
+        out["c4"] = kernel_line("C4: LiquidMotor, default dispersions, 100-knot stochastic wind per sample, Philox draws on the device, "
+                                "MonteCarloAnalyzer.run_monte_carlo sharded over the ranks, NCCL-reduced statistics", n_c4, best[0], best[1], {
+            "api": "run_monte_carlo(ic, n_samples=%d), rng=philox" % (n_c4 * world), "n_valid": an["n_samples"], "n_outliers": an["n_outliers"],
+            "apogee_percentiles_m": an["apogee_altitude"]["percentiles"], "landing_ellipse": an["landing_ellipse"]})
+    # (c) a large C3 batch (device-regenerated numpy streams: no host loop)
+    if n_c3_big > 0:
+        mc = c3_analyzer()
+        mc.rng = "numpy-device"; mc.trajectory_samples = 0; mc.run_opts = opts
+        barrier(); t0 = time.perf_counter()
+        run = mc.run_batch_numpy_device(IC_C3, n_c3_big, first_seed=rank * n_c3_big)
+        barrier(); wall = time.perf_counter() - t0
+        out["c3_large_batch"] = kernel_line("C3, %d samples per GPU in one launch (reference MT19937 streams regenerated on the device)" % n_c3_big,
+                                            n_c3_big, eng_counters_of(mc), wall)
     return out
+
+
+def eng_counters_of(mc):
+    from erpl_monte_carlo_sim_b200.simulator import get_engine
+    return get_engine(mc._dev()).counters()
+
+
+def api_end_to_end(n_total, rank, world, barrier, opts):
+    """Wall time of the drop-in call itself: MonteCarloAnalyzer.run_monte_carlo(ic, n_samples) -> analysis dict."""
+    res = {}
+    for mode, n in (("numpy-device", n_total), ("philox", n_total), ("numpy", min(n_total, 8192 * world))):
+        mc = c3_analyzer()
+        mc.rng = mode; mc.host_rng_max = 1 << 40; mc.run_opts = opts
+        best = None
+        for rep in range(3 if mode != "numpy" else 1):
+            barrier(); t0 = time.perf_counter()
+            an = mc.run_monte_carlo(IC_C3, n_samples=n)
+            barrier(); dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        res[mode] = {"samples": n, "seconds": best, "trajectories_per_s": n / best, "n_valid": an["n_samples"],
+                     "trajectory_samples_taped": int(mc.last_run.tape_ids.size)}
+    return res
 
 
 def hbm_side(blk, wind, h_out, h_iout, flight_ms, world):
@@ -155,6 +285,8 @@ def reference_arm(a):
         vals.append(last["value"]); t_tot += dt
     v = float(n * a.steps / t_tot)
     last["value"] = v
+    if not a.no_python_reference:
+        last["python_reference"] = python_reference_baseline()
     print(json.dumps({"impl": "reference", "metric": "Monte Carlo trajectories/sec (launch->termination)", "value": v,
                       "unit": "trajectories/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                       "ms_per_step": t_tot / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -174,7 +306,11 @@ def main():
     ap.add_argument("--samples-per-gpu", type=int, default=100_000)
     ap.add_argument("--cpu-samples", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (larger batch, planar launch->landing set)")
+    ap.add_argument("--no-python-reference", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary measurements (W-B launch->landing, C4, large batch, tape) and e2e_api")
+    ap.add_argument("--planar-samples", type=int, default=100_000)
+    ap.add_argument("--c4-samples", type=int, default=1_250_000)
+    ap.add_argument("--c3-large", type=int, default=1_000_000)
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--refill-threshold", type=int, default=0)
@@ -184,12 +320,18 @@ def main():
     if a.impl == "reference":
         return reference_arm(a)
 
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    # the Python reference's own multiprocessing path, before this process touches CUDA (its pool forks)
+    pyref = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.no_python_reference:
+        pyref = python_reference_baseline()
+
     import torch
     import torch.distributed as dist
     from erpl_monte_carlo_sim_b200 import _abi, _lib, stats as emc_stats
+    from erpl_monte_carlo_sim_b200.simulator import get_engine
 
-    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
@@ -201,7 +343,7 @@ def main():
     dev = torch.device("cuda", local)
     n = a.samples_per_gpu
     md, blk, wind, desc = make_workload(a.workload, n, rank * n)
-    eng = _lib.Engine(local)
+    eng = get_engine(local)                            # the engine the drop-in classes of this process share
     eng.set_model(md)
     opts = _lib.run_opts(refill_threshold=a.refill_threshold, block_threads=a.block_threads, blocks_per_sm=a.blocks_per_sm,
                          cold_state_in_smem=a.cold_smem)
@@ -244,28 +386,44 @@ def main():
     wall = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)
 
-    # ---- end to end: host pinned buffers through emc_run_batch (H2D + kernels + D2H inside) ----
+    # ---- end to end: host pinned buffers through emc_run_batch (H2D + kernels + D2H inside) + the statistics chain ----
     p_blk = torch.from_numpy(blk).pin_memory(); p_wind = torch.from_numpy(wind).pin_memory()
     p_out = torch.empty((_abi.OUT_COUNT, n), dtype=torch.float64).pin_memory()
     p_iout = torch.empty((_abi.IOUT_COUNT, n), dtype=torch.int32).pin_memory()
     h_blk, h_wind, h_out, h_iout = p_blk.numpy(), p_wind.numpy(), p_out.numpy(), p_iout.numpy()
-    for _ in range(2):
+    e2e_stats = [None]
+
+    def step_e2e():
+        flush.zero_()
+        torch.cuda.synchronize()
         eng.run_batch(h_blk, h_wind, opts=opts, outputs=(h_out, h_iout))
+        e2e_stats[0] = emc_stats.device_statistics(eng, n, distributed=(world > 1))       # on the outputs still resident in HBM
+
+    for _ in range(2):
+        step_e2e()
     barrier()
     t1 = time.perf_counter()
     for _ in range(a.steps):
-        flush.zero_()
-        eng.run_batch(h_blk, h_wind, opts=opts, outputs=(h_out, h_iout))
+        step_e2e()
     barrier()
     wall_e2e = time.perf_counter() - t1
-    parity_hint = bool(np.array_equal(h_iout, d_iout.cpu().numpy()))
+    parity_hint = bool(np.array_equal(h_iout, d_iout.cpu().numpy())) and \
+        json.dumps(e2e_stats[0], sort_keys=True, default=float) == json.dumps(last_stats[0], sort_keys=True, default=float)
 
+    per_rank = gather_ranks([flight_ms / a.steps, rail_ms / a.steps], world, dev)
     tmax = torch.tensor([wall, wall_e2e, flight_ms, rail_ms], dtype=torch.float64, device=dev)
     tsum = torch.tensor([float(rk4), float(replay)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tsum)
     wall, wall_e2e, flight_ms, rail_ms = tmax.tolist()
     rk4_all, replay_all = tsum.tolist()
+
+    extras = api = None
+    if not a.no_extras and a.workload == "c3":
+        del d_blk, d_wind, flush
+        api = api_end_to_end(n * world, rank, world, barrier, opts)
+        extras = secondary_measurements(eng, opts, peak_tf, rank, world, dev, barrier, a.planar_samples, a.c4_samples, a.c3_large)
+
     if rank == 0:
         n_total = n * world
         ms_per_step = wall / a.steps * 1e3
@@ -282,7 +440,8 @@ def main():
                        "launch": {"block_threads": a.block_threads, "blocks_per_sm": a.blocks_per_sm, "refill_threshold": a.refill_threshold, "cold_smem": a.cold_smem}},
             "rk4_steps_per_s": steps_per_s, "mean_rk4_steps_per_trajectory": rk4_all / a.steps / n_total,
             "replayed_steps_per_trajectory": replay_all / a.steps / n_total,
-            "kernel_ms_per_step": {"flight": flight_ms / a.steps, "rail": rail_ms / a.steps},
+            "kernel_ms_per_step": {"flight": flight_ms / a.steps, "rail": rail_ms / a.steps,
+                                   "flight_per_rank": [round(r[0], 3) for r in per_rank]},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf * world, "unit": "TFLOP/s",
                          "frac": achieved_tf / (peak_tf * world),
                          "traffic": FLIGHT_KERNEL_DRAM_BYTES_100K if (a.workload == "c3" and n == 100_000) else None, "traffic_unit": "bytes/launch (ncu)",
@@ -290,16 +449,21 @@ def main():
                                  "(max over ranks); peak = in-run DFMA-chain microbenchmark (emc_fp64_peak) x n_gpus",
                          "hbm": hbm_side(blk, wind, h_out, h_iout, flight_ms / a.steps, world)},
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
-                    "h2d_bytes_per_step": int(blk.nbytes + wind.nbytes), "d2h_bytes_per_step": int(h_out.nbytes + h_iout.nbytes)},
+                    "h2d_bytes_per_step": int(blk.nbytes + wind.nbytes), "d2h_bytes_per_step": int(h_out.nbytes + h_iout.nbytes),
+                    "what": "emc_run_batch on pinned host buffers (H2D, rail + flight kernels, D2H of every summary) + the device statistics chain"},
             "gpu_launches": (2 + STATS_LAUNCHES_FUSED) * a.steps * world,
             "clocks": sampler.summary(),
             "statistics": {k: last_stats[0][k] for k in ("n_total", "n_samples", "n_outliers", "apogee_altitude", "range", "flight_time", "landing_ellipse")},
             "e2e_equals_resident": parity_hint,
         }
+        if api is not None:
+            line["e2e_api"] = api
         if not a.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(md, blk, wind, a.cpu_samples)
-        if not a.no_extras and world == 1 and a.workload == "c3":
-            line["secondary"] = secondary_measurements(eng, opts, peak_tf)
+            if pyref is not None:
+                line["cpu_baseline"]["python_reference"] = pyref
+        if extras is not None:
+            line["secondary"] = extras
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

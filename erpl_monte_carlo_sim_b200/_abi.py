@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CD_KNOTS = 16
 MAX_CP_KNOTS = 16
 MAX_THRUST_KNOTS = 32
@@ -31,6 +31,7 @@ OUT = {k: i for i, k in enumerate(OUT_FIELDS)}
 IOUT = {k: i for i, k in enumerate(IOUT_FIELDS)}
 IN_COUNT, OUT_COUNT, IOUT_COUNT = len(IN_FIELDS), len(OUT_FIELDS), len(IOUT_FIELDS)
 TAPE_WIDTH = 15
+BTAPE_WIDTH = 4
 SERIES_FIELDS = ["mass", "Ixx", "Iyy", "Izz", "center_of_mass", "euler_roll", "euler_pitch", "euler_yaw", "thrust", "drag",
                  "cd", "cl", "cm", "cp_location_dynamic", "stability_margin", "angle_of_attack", "sideslip_angle", "speed",
                  "mach", "dynamic_pressure"]
@@ -73,6 +74,7 @@ class EmcModel(C.Structure):
         ("yaw_damping", C.c_double), ("rail_length", C.c_double),
         ("has_wind", C.c_int32), ("n_wind", C.c_int32),
         ("wind_altitudes", _dp),
+        ("gamma", C.c_double),
     ]
 
 
@@ -106,7 +108,7 @@ class EmcDispersion(C.Structure):
 class EmcCounters(C.Structure):
     _fields_ = [("rk4_steps", C.c_int64), ("replay_steps", C.c_int64), ("rail_steps", C.c_int64),
                 ("refills", C.c_int64), ("kernel_launches", C.c_int64),
-                ("rail_ms", C.c_double), ("flight_ms", C.c_double)]
+                ("rail_ms", C.c_double), ("flight_ms", C.c_double), ("tape_rows", C.c_int64)]
 
 
 _MODEL_SCALARS = ["center_of_mass_dry", "Ixx_dry", "Iyy_dry", "diameter", "reference_area",
@@ -152,6 +154,7 @@ def pack_model(md: dict):
         raise ValueError(f"altitude_profile: {alts.size} knots exceed the engine limit of {MAX_WIND_KNOTS}")
     m.n_wind = int(alts.size) if m.has_wind else 0
     m.wind_altitudes = alts.ctypes.data_as(_dp) if alts.size else None
+    m.gamma = float(md.get("gamma", 1.4))
     return m, alts
 
 

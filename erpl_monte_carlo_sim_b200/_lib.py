@@ -29,7 +29,7 @@ class EmcError(RuntimeError):
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/emc_engine.cu for sm_100a into the in-tree libemc.so (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(CSRC, f) for f in ("emc_engine.cu", "emc_physics.cuh", "emc_model_build.h", "emc_stats.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))]
     srcs = [s for s in srcs if os.path.isfile(s)] + [os.path.join(os.path.dirname(PKG_DIR), "include", "emc.h")]
     if not force and os.path.isfile(SO_PATH) and os.path.getmtime(SO_PATH) >= max(os.path.getmtime(s) for s in srcs):
         return SO_PATH
@@ -108,6 +108,12 @@ def load():
     L.emc_resident_outputs.restype = C.c_int
     L.emc_upload_outputs.argtypes = [vp, vp, i64, i64]
     L.emc_upload_outputs.restype = C.c_int
+    L.emc_tape_request.argtypes = [vp, C.POINTER(C.c_int64), i64, C.c_int32, C.c_int32]
+    L.emc_tape_request.restype = C.c_int
+    L.emc_tape_fetch.argtypes = [vp, _dp, _ip]
+    L.emc_tape_fetch.restype = C.c_int
+    L.emc_tape_resident.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(C.c_int32)]
+    L.emc_tape_resident.restype = C.c_int
     for name in ("emc_scratch", "emc_copy_to_host", "emc_copy_to_device", "emc_stats_moments1", "emc_stats_moments2",
                  "emc_stats_select_hist", "emc_stats_linear_hist"):
         getattr(L, name).restype = C.c_int
@@ -259,11 +265,32 @@ class Engine:
                                               d.ctypes.data_as(_dp)), "emc_numpy_draws")
         return g, u, d
 
-    def run_batch_staged(self, n, opts=None):
-        outs, out, iout = _abi.outputs_alloc(n)
+    def run_batch_staged(self, n, opts=None, download=True):
+        """Fly the staged samples.  download=False leaves the outputs in HBM only (statistics run there; fetch them later
+        with fetch_outputs)."""
+        if download:
+            outs, out, iout = _abi.outputs_alloc(n)
+        else:
+            outs, out, iout = _abi.EmcOutputs(), None, None
+            outs.out, outs.iout, outs.ld = None, None, n
         self._check(self._lib.emc_run_batch_staged(self._ctx, n, C.byref(outs), C.byref(opts) if opts is not None else None),
                     "emc_run_batch_staged")
         return out, iout
+
+    # -- downsampled batch tape --------------------------------------------------------------------
+    def tape_request(self, samples, stride, max_rows):
+        """Arm the next run: record every `stride`-th stored state (+ the last) of the listed samples as {t, x, y, z} rows."""
+        idx = np.ascontiguousarray(samples, np.int64)
+        self._check(self._lib.emc_tape_request(self._ctx, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size, int(stride), int(max_rows)),
+                    "emc_tape_request")
+        self._tape_shape = (idx.size, int(max_rows))
+
+    def tape_fetch(self):
+        """(rows[n_sel][max_rows][4], n_rows[n_sel]) of the tape recorded by the last armed run."""
+        n_sel, max_rows = self._tape_shape
+        rows = np.empty((n_sel, max_rows, _abi.BTAPE_WIDTH), np.float64); cnt = np.empty(n_sel, np.int32)
+        self._check(self._lib.emc_tape_fetch(self._ctx, rows.ctypes.data_as(_dp), cnt.ctypes.data_as(_ip)), "emc_tape_fetch")
+        return rows, cnt
 
     def staged_inputs(self, n, want_wind=True):
         sc = np.empty((_abi.IN_COUNT, n), np.float64)

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <new>
 #include <string>
 
@@ -48,6 +49,8 @@ struct KernelArgs {
     unsigned long long *counters;      /* [0] rk4 steps [1] replays [2] rail steps [3] refills */
     double *tape; int64_t tape_cap; int64_t *tape_n;
     int32_t refill_threshold; int32_t nan_ff;
+    /* downsampled batch tape (emc_tape_request): slot of every sample (-1: not recorded), rows[n_sel][bt_max][4], counts */
+    const int32_t *bt_slot; double *bt_rows; int32_t *bt_count; int32_t bt_stride, bt_max;
 };
 
 /* Stage the run-constant tables into shared memory.  The tables are a STATIC __shared__ object and the wind
@@ -90,16 +93,24 @@ __global__ void __launch_bounds__(128) emc_rail_kernel(KernelArgs a)
  * the remembered table brackets) can live in shared memory instead of registers (COLD = 1): the
  * derivative then fits in fewer registers and more warps are resident to hide the FP64 latency.
  * The structs are padded to an odd number of 8-byte words, so lane-strided access is conflict-free. */
-struct ColdLaneRaw { Track K; Sample S; WindBracket WB; };
-struct alignas(8) ColdLane {
-    Track K; Sample S; WindBracket WB;
-    double pad_[((sizeof(ColdLaneRaw) / 8) % 2 == 1) ? 2 : 1];
-};
+struct alignas(8) ColdLaneRaw { Track K; Sample S; WindBracket WB; };
+template <bool PAD> struct ColdPad { double pad_; };
+template <> struct ColdPad<false> {};
+struct ColdLane : ColdLaneRaw, ColdPad<(sizeof(ColdLaneRaw) / 8) % 2 == 0> {};
 static_assert(sizeof(ColdLane) % 8 == 0 && (sizeof(ColdLane) / 8) % 2 == 1, "ColdLane must span an odd number of 8-byte words");
 
 /* Dynamic shared memory of the flight kernel: [28][BLOCK] state store (COLD == 2) followed by the wind altitude grid.
  * It is indexed directly (never through a pointer carved out of it), so the accesses are plain LDS/STS. */
 extern __shared__ double emc_dyn[];
+
+/* one row {t - t_rail, x, y, z} of the downsampled batch tape: a 32-byte store per lane (one sector) */
+__device__ __forceinline__ void bt_write(const KernelArgs &a, int32_t slot, int32_t row, double t, double x, double y, double z)
+{
+    if (row < a.bt_max) {
+        double4 *dst = reinterpret_cast<double4 *>(a.bt_rows + ((int64_t)slot * a.bt_max + row) * EMC_BTAPE_WIDTH);
+        *dst = make_double4(t, x, y, z);
+    }
+}
 
 template <int BLOCK>
 struct SharedStore {
@@ -124,7 +135,7 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
     ColdLane reg_lane;                     /* COLD = 0: plain registers */
     ColdLane &CL = COLD ? sh_cold[COLD ? threadIdx.x : 0] : reg_lane;
     Track &K = CL.K; Sample &S = CL.S; WindBracket &WB = CL.WB;
-    unsigned long long n_steps = 0, n_replay = 0, n_refill = 0;
+    unsigned long long n_steps = 0, n_replay = 0, n_refill = 0, n_tape = 0;
     const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
 
     for (;;) {
@@ -158,6 +169,11 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
                                 const double *sp = reinterpret_cast<const double *>(&s);
                                 for (int c = 0; c < 14; ++c) a.tape[1 + c] = sp[c];
                             }
+                            if (a.bt_slot) {
+                                const int32_t slot = a.bt_slot[idx];
+                                K.bt_slot = slot; K.bt_next = a.bt_stride;
+                                if (slot >= 0) bt_write(a, slot, 0, 0.0, s.x, s.y, s.z);
+                            }
                             active = true;
                             ++n_refill;
                         }
@@ -180,12 +196,24 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
                     row[0] = K.t;
                     for (int c = 0; c < 14; ++c) row[1 + c] = st.s(c);
                 }
+                if (a.bt_slot && K.bt_slot >= 0 && K.n_steps == K.bt_next) {       /* every bt_stride-th stored state */
+                    bt_write(a, K.bt_slot, K.n_steps / a.bt_stride, K.t - K.t_rail, st.s(0), st.s(1), st.s(2));
+                    K.bt_next += a.bt_stride;
+                }
             }
             if (retired) {
                 n_replay += (unsigned long long)rep;
                 State s; store_get(st, s);
                 write_flight_outputs(K, s, a.out + idx, a.iout + idx, a.old);
                 if (a.tape_n) *a.tape_n = (int64_t)K.n_steps + 1 - rep;
+                if (a.bt_slot && K.bt_slot >= 0) {
+                    /* the last integrated state closes the trajectory (a fast-forwarded NaN tail is not recorded) */
+                    const int32_t last = K.n_steps - (int32_t)rep;
+                    int32_t rows = last / a.bt_stride + 1;
+                    if (rep == 0 && last % a.bt_stride != 0) { bt_write(a, K.bt_slot, rows, K.t - K.t_rail, s.x, s.y, s.z); ++rows; }
+                    a.bt_count[K.bt_slot] = rows;
+                    n_tape += (unsigned long long)(rows < a.bt_max ? rows : a.bt_max);
+                }
                 active = false;
             }
         }
@@ -194,11 +222,13 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
         n_steps += __shfl_down_sync(FULL, n_steps, o);
         n_replay += __shfl_down_sync(FULL, n_replay, o);
         n_refill += __shfl_down_sync(FULL, n_refill, o);
+        n_tape += __shfl_down_sync(FULL, n_tape, o);
     }
     if (lane == 0) {
         if (n_steps) atomicAdd(a.counters + 0, n_steps);
         if (n_replay) atomicAdd(a.counters + 1, n_replay);
         if (n_refill) atomicAdd(a.counters + 3, n_refill);
+        if (n_tape) atomicAdd(a.counters + 7, n_tape);
     }
 }
 
@@ -272,6 +302,14 @@ __global__ void __launch_bounds__(128) emc_component_kernel(int comp, int64_t n,
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* batch tape: sample index -> row block (later entries of a duplicated index win; indices outside the batch are ignored) */
+__global__ void emc_tape_map_kernel(const int64_t *list, int64_t n_sel, int64_t n, int32_t *slot)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_sel && list[k] >= 0 && list[k] < n) slot[list[k]] = (int32_t)k;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 __global__ void emc_math_kernel(int op, int64_t n, const double *x, const double *y, double *out)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,7 +361,8 @@ struct emc_ctx {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     bool has_model = false;
     emc_model model;              /* raw copy (wind_altitudes pointer is NOT valid after set_model) */
-    DevModel dmodel;
+    DevModel dmodel;              /* host copies of what c_model / c_tables must hold while this context launches */
+    DevTables dtables;
     double *d_wind_alt = nullptr;
     unsigned long long *d_ctrl = nullptr;   /* [0] queue head, [1..4] counters, [5] tape_n */
     /* staging buffers for the host-buffer entry points (grown on demand) */
@@ -339,11 +378,27 @@ struct emc_ctx {
     double *d_draws = nullptr; size_t cap_draws = 0;  /* caller-supplied draws */
     int64_t staged_n = 0; int staged_knots = 0;
     int64_t last_n = 0;                       /* samples held by d_out/d_iout after the last host-buffer run */
+    /* one-sample paths (tape, series, derivative/debug seams) have their own small output block, so they never touch the
+     * resident outputs of the last batch */
+    double *d_out1 = nullptr; int32_t *d_iout1 = nullptr;
+    /* downsampled batch tape (emc_tape_request) */
+    int32_t *d_bt_slot = nullptr; size_t cap_bt_slot = 0;
+    double *d_bt_rows = nullptr; size_t cap_bt_rows = 0;
+    int32_t *d_bt_count = nullptr; size_t cap_bt_count = 0;
+    int64_t *d_bt_list = nullptr; size_t cap_bt_list = 0;
+    int64_t bt_n_sel = 0; int32_t bt_stride = 0, bt_max = 0;
+    bool bt_armed = false;                    /* a request waits for the next run */
+    int64_t bt_have = 0;                      /* n_sel of the tape the last armed run left in d_bt_rows */
     emc_counters counters;
     std::string err;
 };
 
 static thread_local std::string g_create_err;
+
+/* c_model / c_tables are per-device globals shared by every context on that device: remember which context uploaded
+ * last and re-upload (after draining the device) when another one is about to launch. */
+static std::mutex g_owner_mu;
+static emc_ctx *g_owner[64] = { nullptr };
 
 static int fail(emc_ctx *c, int code, const std::string &msg)
 {
@@ -388,7 +443,7 @@ EMC_EXPORT int emc_create(emc_ctx **out, int device)
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctrl, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctrl, 16 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         std::string m = std::string("emc_create: ") + cudaGetErrorString(e);
         delete ctx;
@@ -403,11 +458,30 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
     if (!ctx) return EMC_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    {
+        std::lock_guard<std::mutex> lk(g_owner_mu);
+        if (ctx->device >= 0 && ctx->device < 64 && g_owner[ctx->device] == ctx) g_owner[ctx->device] = nullptr;
+    }
+    cudaFree(ctx->d_out1); cudaFree(ctx->d_iout1); cudaFree(ctx->d_bt_slot); cudaFree(ctx->d_bt_rows); cudaFree(ctx->d_bt_count); cudaFree(ctx->d_bt_list);
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
     cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_summary); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+    return EMC_OK;
+}
+
+/* Make this context's run constants the ones in the device's __constant__ bank.  Called before every launch that reads
+ * c_model / c_tables; a no-op while the same context keeps launching. */
+static int make_resident(emc_ctx *ctx)
+{
+    if (ctx->device < 0 || ctx->device >= 64) return fail(ctx, EMC_ERR_INVALID, "device index beyond the ownership table");
+    std::lock_guard<std::mutex> lk(g_owner_mu);
+    if (g_owner[ctx->device] == ctx) return EMC_OK;
+    CK(cudaDeviceSynchronize());               /* kernels of the previous owner may still be reading its constants */
+    CK(cudaMemcpyToSymbol(c_model, &ctx->dmodel, sizeof(DevModel)));
+    CK(cudaMemcpyToSymbol(c_tables, &ctx->dtables, sizeof(DevTables)));
+    g_owner[ctx->device] = ctx;
     return EMC_OK;
 }
 
@@ -419,8 +493,13 @@ EMC_EXPORT int emc_set_model(emc_ctx *ctx, const emc_model *model)
     DevModel D; DevTables T;
     build_dev_model(*model, D, T);
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpyToSymbol(c_model, &D, sizeof D));
-    CK(cudaMemcpyToSymbol(c_tables, &T, sizeof T));
+    ctx->dmodel = D; ctx->dtables = T;
+    {
+        std::lock_guard<std::mutex> lk(g_owner_mu);
+        if (g_owner[ctx->device] == ctx) g_owner[ctx->device] = nullptr;     /* force the upload below */
+    }
+    ctx->has_model = false;
+    if (int rc = make_resident(ctx)) return rc;
     cudaFree(ctx->d_wind_alt); ctx->d_wind_alt = nullptr;
     if (D.has_wind) {
         CK(cudaMalloc(&ctx->d_wind_alt, sizeof(double) * D.n_wind));
@@ -428,7 +507,6 @@ EMC_EXPORT int emc_set_model(emc_ctx *ctx, const emc_model *model)
     }
     ctx->model = *model;
     ctx->model.wind_altitudes = nullptr;
-    ctx->dmodel = D;
     ctx->has_model = true;
     return EMC_OK;
 }
@@ -491,9 +569,22 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     if (a.tape) a.tape_n = reinterpret_cast<int64_t *>(ctx->d_ctrl + 5);
     if (!ctx->dmodel.has_wind) { a.wind = nullptr; a.wind_stride = 0; }
     const size_t smem = smem_bytes(ctx->dmodel.n_wind);
-    CK(cudaMemsetAsync(ctx->d_ctrl, 0, 8 * sizeof(unsigned long long), ctx->stream));
+    if (int rc = make_resident(ctx)) return rc;
+    CK(cudaMemsetAsync(ctx->d_ctrl, 0, 16 * sizeof(unsigned long long), ctx->stream));
     memset(&ctx->counters, 0, sizeof ctx->counters);
     if (a.n == 0) return EMC_OK;
+    if (ctx->bt_armed && !a.tape) {
+        /* consume the tape request: slot map of this batch (-1 everywhere, then the listed samples), cleared counts */
+        ctx->bt_armed = false; ctx->bt_have = 0;
+        CK(grow(&ctx->d_bt_slot, &ctx->cap_bt_slot, (size_t)a.n));
+        CK(cudaMemsetAsync(ctx->d_bt_slot, 0xff, sizeof(int32_t) * (size_t)a.n, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_bt_count, 0, sizeof(int32_t) * (size_t)ctx->bt_n_sel, ctx->stream));
+        emc_tape_map_kernel<<<(unsigned)((ctx->bt_n_sel + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_bt_list, ctx->bt_n_sel, a.n, ctx->d_bt_slot);
+        CK(cudaGetLastError());
+        a.bt_slot = ctx->d_bt_slot; a.bt_rows = ctx->d_bt_rows; a.bt_count = ctx->d_bt_count;
+        a.bt_stride = ctx->bt_stride; a.bt_max = ctx->bt_max;
+        ctx->bt_have = ctx->bt_n_sel;
+    }
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     {
         int64_t grid = (a.n + 127) / 128;
@@ -529,13 +620,14 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
 
 static int finish_counters(emc_ctx *ctx)
 {
-    unsigned long long h[8];
+    unsigned long long h[16];
     CK(cudaMemcpyAsync(h, ctx->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->counters.rk4_steps = (int64_t)h[1];
     ctx->counters.replay_steps = (int64_t)h[2];
     ctx->counters.rail_steps = (int64_t)h[3];
     ctx->counters.refills = (int64_t)h[4];
+    ctx->counters.tape_rows = (int64_t)h[8];
     float ms = 0.f;
     if (ctx->counters.kernel_launches) {
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->counters.rail_ms = ms;
@@ -557,9 +649,13 @@ EMC_EXPORT int emc_run_batch_device(emc_ctx *ctx, const emc_inputs *in, int64_t 
     return finish_counters(ctx);
 }
 
-static int upload_inputs(emc_ctx *ctx, const emc_inputs *in, int64_t n, KernelArgs &a)
+/* batch = true: the run owns the context's resident output block; false (tape, series, debug seams): outputs, if any, go
+ * to the one-sample block so that the resident outputs of the last batch stay valid.  Either way the context's input
+ * staging area is overwritten, which invalidates inputs staged by emc_generate_inputs. */
+static int upload_inputs(emc_ctx *ctx, const emc_inputs *in, int64_t n, KernelArgs &a, bool batch = true)
 {
     const size_t ns = (size_t)EMC_IN_COUNT * (size_t)n;
+    ctx->staged_n = 0;
     CK(grow(&ctx->d_scalars, &ctx->cap_scalars, ns));
     /* compact the leading dimension to n on the way up (one contiguous copy when it already is n) */
     if (in->ld == n) CK(cudaMemcpyAsync(ctx->d_scalars, in->scalars, sizeof(double) * ns, cudaMemcpyHostToDevice, ctx->stream));
@@ -583,22 +679,33 @@ static int upload_inputs(emc_ctx *ctx, const emc_inputs *in, int64_t n, KernelAr
         }
         a.wind = ctx->d_wind;
     }
+    a.n = n;
+    if (!batch) {
+        if (n == 1) {
+            if (!ctx->d_out1) CK(cudaMalloc(&ctx->d_out1, sizeof(double) * EMC_OUT_COUNT));
+            if (!ctx->d_iout1) CK(cudaMalloc(&ctx->d_iout1, sizeof(int32_t) * EMC_IOUT_COUNT));
+            a.out = ctx->d_out1; a.iout = ctx->d_iout1; a.old = 1;
+        }
+        return EMC_OK;
+    }
+    if ((size_t)EMC_OUT_COUNT * (size_t)n > ctx->cap_out || (size_t)EMC_IOUT_COUNT * (size_t)n > ctx->cap_iout) ctx->last_n = 0;
     CK(grow(&ctx->d_out, &ctx->cap_out, (size_t)EMC_OUT_COUNT * (size_t)n));
     CK(grow(&ctx->d_iout, &ctx->cap_iout, (size_t)EMC_IOUT_COUNT * (size_t)n));
-    a.out = ctx->d_out; a.iout = ctx->d_iout; a.old = n; a.n = n;
+    a.out = ctx->d_out; a.iout = ctx->d_iout; a.old = n;
+    ctx->last_n = 0;                          /* set again by the caller once the run has completed */
     return EMC_OK;
 }
 
-static int download_outputs(emc_ctx *ctx, const emc_outputs *out, int64_t n)
+static int download_outputs(emc_ctx *ctx, const emc_outputs *out, int64_t n, const double *d_out, const int32_t *d_iout)
 {
     if (out->ld == n) {
-        CK(cudaMemcpyAsync(out->out, ctx->d_out, sizeof(double) * (size_t)EMC_OUT_COUNT * n, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(out->iout, ctx->d_iout, sizeof(int32_t) * (size_t)EMC_IOUT_COUNT * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out->out, d_out, sizeof(double) * (size_t)EMC_OUT_COUNT * n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out->iout, d_iout, sizeof(int32_t) * (size_t)EMC_IOUT_COUNT * n, cudaMemcpyDeviceToHost, ctx->stream));
         return EMC_OK;
     }
-    CK(cudaMemcpy2DAsync(out->out, sizeof(double) * out->ld, ctx->d_out, sizeof(double) * n, sizeof(double) * n,
+    CK(cudaMemcpy2DAsync(out->out, sizeof(double) * out->ld, d_out, sizeof(double) * n, sizeof(double) * n,
                          EMC_OUT_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpy2DAsync(out->iout, sizeof(int32_t) * out->ld, ctx->d_iout, sizeof(int32_t) * n, sizeof(int32_t) * n,
+    CK(cudaMemcpy2DAsync(out->iout, sizeof(int32_t) * out->ld, d_iout, sizeof(int32_t) * n, sizeof(int32_t) * n,
                          EMC_IOUT_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
     return EMC_OK;
 }
@@ -613,9 +720,10 @@ EMC_EXPORT int emc_run_batch(emc_ctx *ctx, const emc_inputs *in, int64_t n, cons
     memset(&a, 0, sizeof a);
     if (int rc = upload_inputs(ctx, in, n, a)) return rc;
     if (int rc = run_device(ctx, a, opts)) return rc;
-    if (int rc = download_outputs(ctx, out, n)) return rc;
+    if (int rc = download_outputs(ctx, out, n, ctx->d_out, ctx->d_iout)) return rc;
+    if (int rc = finish_counters(ctx)) return rc;
     ctx->last_n = n;
-    return finish_counters(ctx);
+    return EMC_OK;
 }
 
 EMC_EXPORT int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_outputs *out, double *tape, int64_t cap,
@@ -626,14 +734,14 @@ EMC_EXPORT int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_output
     CK(cudaSetDevice(ctx->device));
     KernelArgs a;
     memset(&a, 0, sizeof a);
-    if (int rc = upload_inputs(ctx, in, 1, a)) return rc;
+    if (int rc = upload_inputs(ctx, in, 1, a, false)) return rc;
     CK(grow(&ctx->d_tape, &ctx->cap_tape, (size_t)cap * EMC_TAPE_WIDTH));
     a.tape = ctx->d_tape; a.tape_cap = cap;
     emc_run_opts o = { 1, 64, 1, 0, 0 };    /* every state is integrated: no fast-forward on the tape path */
     if (int rc = run_device(ctx, a, &o)) return rc;
-    if (int rc = download_outputs(ctx, out, 1)) return rc;
+    if (int rc = download_outputs(ctx, out, 1, ctx->d_out1, ctx->d_iout1)) return rc;
     if (int rc = finish_counters(ctx)) return rc;
-    unsigned long long h[8];
+    unsigned long long h[16];
     CK(cudaMemcpy(h, ctx->d_ctrl, sizeof h, cudaMemcpyDeviceToHost));
     const int64_t ns = (int64_t)h[5];
     *n_states = ns;
@@ -651,7 +759,8 @@ EMC_EXPORT int emc_extract_series(emc_ctx *ctx, const emc_inputs *in, const doub
     CK(cudaSetDevice(ctx->device));
     KernelArgs a;
     memset(&a, 0, sizeof a);
-    if (int rc = upload_inputs(ctx, in, 1, a)) return rc;
+    if (int rc = upload_inputs(ctx, in, 1, a, false)) return rc;
+    if (int rc = make_resident(ctx)) return rc;
     a.wind_alt = ctx->d_wind_alt;
     if (!ctx->dmodel.has_wind) { a.wind = nullptr; a.wind_stride = 0; }
     CK(grow(&ctx->d_tape, &ctx->cap_tape, (size_t)n_states * EMC_TAPE_WIDTH));
@@ -676,7 +785,8 @@ EMC_EXPORT int emc_derivative_debug(emc_ctx *ctx, const emc_inputs *in, int64_t 
     CK(cudaSetDevice(ctx->device));
     KernelArgs a;
     memset(&a, 0, sizeof a);
-    if (int rc = upload_inputs(ctx, in, n, a)) return rc;
+    if (int rc = upload_inputs(ctx, in, n, a, false)) return rc;
+    if (int rc = make_resident(ctx)) return rc;
     a.wind_alt = ctx->d_wind_alt;
     if (!ctx->dmodel.has_wind) { a.wind = nullptr; a.wind_stride = 0; }
     double *d_t = nullptr, *d_s = nullptr, *d_k = nullptr; int32_t *d_c = nullptr;
@@ -810,19 +920,21 @@ EMC_EXPORT int emc_run_batch_staged(emc_ctx *ctx, int64_t n, const emc_outputs *
     if (n < 0 || n > ctx->staged_n) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: n exceeds the staged samples");
     if (ctx->dmodel.has_wind && ctx->staged_knots != ctx->dmodel.n_wind) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: staged wind tables do not match the model's altitude grid");
     if (n == 0) return EMC_OK;
-    if (!out->out || !out->iout || out->ld < n) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: output buffers");
+    if ((out->out || out->iout) && (!out->out || !out->iout || out->ld < n)) return fail(ctx, EMC_ERR_INVALID, "emc_run_batch_staged: output buffers");
     CK(cudaSetDevice(ctx->device));
     KernelArgs a;
     memset(&a, 0, sizeof a);
     a.scalars = ctx->d_scalars; a.ld = ctx->staged_n;
     a.wind = ctx->dmodel.has_wind ? ctx->d_wind : nullptr; a.wind_stride = (int64_t)ctx->staged_knots * 3;
+    ctx->last_n = 0;
     CK(grow(&ctx->d_out, &ctx->cap_out, (size_t)EMC_OUT_COUNT * (size_t)n));
     CK(grow(&ctx->d_iout, &ctx->cap_iout, (size_t)EMC_IOUT_COUNT * (size_t)n));
     a.out = ctx->d_out; a.iout = ctx->d_iout; a.old = n; a.n = n;
     if (int rc = run_device(ctx, a, opts)) return rc;
-    if (int rc = download_outputs(ctx, out, n)) return rc;
+    if (out->out && out->iout) { if (int rc = download_outputs(ctx, out, n, ctx->d_out, ctx->d_iout)) return rc; }
+    if (int rc = finish_counters(ctx)) return rc;
     ctx->last_n = n;
-    return finish_counters(ctx);
+    return EMC_OK;
 }
 
 EMC_EXPORT int emc_staged_inputs(emc_ctx *ctx, int64_t n, double *scalars_host, double *wind_host)
@@ -891,6 +1003,44 @@ EMC_EXPORT int emc_resident_outputs(emc_ctx *ctx, double **out_dev, int64_t *ld)
     return EMC_OK;
 }
 
+/* ---------------------------------------------------------------------------------------------------
+ *  downsampled batch tape (reference monte_carlo.py:296-302 'trajectory')
+ * ------------------------------------------------------------------------------------------------- */
+EMC_EXPORT int emc_tape_request(emc_ctx *ctx, const int64_t *samples, int64_t n_sel, int32_t stride, int32_t max_rows)
+{
+    if (!ctx) return EMC_ERR_INVALID;
+    if (n_sel == 0 || !samples) { ctx->bt_armed = false; return EMC_OK; }     /* clears a pending request */
+    if (n_sel < 0 || n_sel > 0x7fffffffLL || stride < 1 || max_rows < 2) return fail(ctx, EMC_ERR_INVALID, "emc_tape_request: n_sel / stride >= 1 / max_rows >= 2");
+    CK(cudaSetDevice(ctx->device));
+    CK(grow(&ctx->d_bt_list, &ctx->cap_bt_list, (size_t)n_sel));
+    CK(grow(&ctx->d_bt_count, &ctx->cap_bt_count, (size_t)n_sel));
+    CK(grow(&ctx->d_bt_rows, &ctx->cap_bt_rows, (size_t)n_sel * (size_t)max_rows * EMC_BTAPE_WIDTH));
+    CK(cudaMemcpyAsync(ctx->d_bt_list, samples, sizeof(int64_t) * (size_t)n_sel, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->bt_n_sel = n_sel; ctx->bt_stride = stride; ctx->bt_max = max_rows;
+    ctx->bt_armed = true; ctx->bt_have = 0;
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_tape_fetch(emc_ctx *ctx, double *rows, int32_t *n_rows)
+{
+    if (!ctx || !rows || !n_rows) return fail(ctx, EMC_ERR_INVALID, "emc_tape_fetch: NULL argument");
+    if (ctx->bt_have <= 0) return fail(ctx, EMC_ERR_INVALID, "emc_tape_fetch: no run has recorded a tape since the last emc_tape_request");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(rows, ctx->d_bt_rows, sizeof(double) * (size_t)ctx->bt_have * (size_t)ctx->bt_max * EMC_BTAPE_WIDTH, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(n_rows, ctx->d_bt_count, sizeof(int32_t) * (size_t)ctx->bt_have, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
+EMC_EXPORT int emc_tape_resident(emc_ctx *ctx, double **rows_dev, int32_t **n_rows_dev, int64_t *n_sel, int32_t *max_rows)
+{
+    if (!ctx || !rows_dev || !n_rows_dev || !n_sel || !max_rows) return fail(ctx, EMC_ERR_INVALID, "emc_tape_resident: NULL argument");
+    if (ctx->bt_have <= 0) return fail(ctx, EMC_ERR_INVALID, "emc_tape_resident: no recorded tape");
+    *rows_dev = ctx->d_bt_rows; *n_rows_dev = ctx->d_bt_count; *n_sel = ctx->bt_have; *max_rows = ctx->bt_max;
+    return EMC_OK;
+}
+
 EMC_EXPORT int emc_upload_outputs(emc_ctx *ctx, const double *out_host, int64_t ld, int64_t n)
 {
     if (!ctx || !out_host || n < 0 || ld < n) return fail(ctx, EMC_ERR_INVALID, "emc_upload_outputs: bad argument");
@@ -907,6 +1057,10 @@ EMC_EXPORT int emc_upload_outputs(emc_ctx *ctx, const double *out_host, int64_t 
 static int stats_source(emc_ctx *ctx, const double *&out_dev, int64_t &ld, int64_t n)
 {
     if (!ctx || n < 0) return fail(ctx, EMC_ERR_INVALID, "emc_stats: bad argument");
+    if (n == 0 && !out_dev) {                 /* an empty shard of a multi-GPU job still takes part in the reductions */
+        out_dev = reinterpret_cast<const double *>(ctx->d_ctrl); ld = 0;
+        return EMC_OK;
+    }
     if (!out_dev) {
         if (!ctx->d_out || ctx->last_n < n || ctx->last_n == 0) return fail(ctx, EMC_ERR_INVALID, "emc_stats: no resident outputs of a previous emc_run_batch");
         out_dev = ctx->d_out; ld = ctx->last_n;
@@ -1110,6 +1264,7 @@ EMC_EXPORT int emc_component_debug(emc_ctx *ctx, int component, int64_t n, const
     if (!ctx->has_model) return fail(ctx, EMC_ERR_NO_MODEL, "emc_set_model has not been called");
     if (n == 0) return EMC_OK;
     CK(cudaSetDevice(ctx->device));
+    if (int rc = make_resident(ctx)) return rc;
     const size_t ni = (size_t)n_in[component] * n, no = (size_t)n_out[component] * n;
     CK(grow(&ctx->d_scratch, &ctx->cap_scratch, (ni + no) * sizeof(double)));
     double *d_in = reinterpret_cast<double *>(ctx->d_scratch), *d_out = d_in + ni;

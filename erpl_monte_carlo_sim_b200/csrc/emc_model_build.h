@@ -145,6 +145,8 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
     D.p25 = D.p20 * exp(-g * 5000.0 / (R * m.stratosphere_temp));                     /* :72-75 */
     D.expo_25 = g / (R * 0.0028);                                                     /* :76,81 */
     D.R_gas = R; D.g0 = g;
+    D.mach_k = (R == 287.053) ? 1.0 / 1.4 : R / (1.4 * 287.053);                      /* utils.py:152-157 */
+    D.gamma = (m.gamma > 0.0) ? m.gamma : 1.4;                                        /* environment.py:19,96 */
     {
         /* p0*(1 - a z)^e, a = L/T0, about zc: p0*(1 - a zc)^e * (1 - ap zeta)^e with ap = a zh/(1 - a zc); binomial series
          * c_k = c_{k-1} * (e - k + 1)/k * (-ap).  Used on [-2 km, troposphere_height] when the series has converged to

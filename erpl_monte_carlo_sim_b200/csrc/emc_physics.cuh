@@ -76,6 +76,8 @@ struct DevModel {
     double p20, p25;     /* :56-62, :72-75 */
     double expo_25;      /* g/(R*0.0028)                   :81 */
     double R_gas, g0;
+    double mach_k;       /* R_gas/(1.4*287.053): utils.mach_number hardcodes gamma and R (utils.py:152-157) whatever the atmosphere holds */
+    double gamma;        /* atmosphere.gamma: speed_of_sound of get_properties only (environment.py:96) */
     /* troposphere pressure as ONE polynomial: p0*(1 - L z/T0)^(g/(R L)) expanded about the middle of [tp_lo, tp_hi]
      * (binomial series in zeta = (z - tp_zc)*tp_inv_zh, |zeta| <= 1, truncation < 1e-18 relative; built in long double
      * by build_dev_model).  Replaces exp(e*log(T/T0)) where nearly every sounding-rocket step is flown; an atmosphere
@@ -496,7 +498,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double vby = r01 * ux + r11 * uy + r21 * uz;
     const double vbz = r02 * ux + r12 * uy + r22 * uz;
     const double v2 = ux * ux + uy * uy + uz * uz;
-    const double mach2 = v2 * (inv_RT * K_MISC[7]);         /* (|v|/sqrt(1.4*R*T))^2, utils.py:152-157 */
+    const double mach2 = v2 * (inv_RT * M.mach_k);           /* (|v|/sqrt(1.4*287.053*T))^2, utils.py:152-157 */
     const double qdyn = 0.5 * rho * v2;
 
     /* :359-363 thrust along body x */
@@ -630,6 +632,7 @@ struct Track {
     bool chute, apogee_detected, burnout_found;
     bool finishing;   /* loop ended: one more stage-0 pass exports the last stored state's diagnostics */
     int32_t replay;   /* NaN fast-forward mode (0 none, 1 all-NaN, 2 altitude-NaN ballistic): t is replayed to max_time */
+    int32_t bt_slot, bt_next;   /* batch tape: row block of this sample (-1: not recorded) and the next stored-state index to record */
 };
 
 EMC_HD void track_init(Track &K, const State &s, double t_rail)
@@ -641,6 +644,7 @@ EMC_HD void track_init(Track &K, const State &s, double t_rail)
     K.burnout_time = 0.0; K.burnout_found = false;
     K.chute_time = NAN; K.chute = false; K.apogee_detected = false;
     K.n_steps = 0; K.term = EMC_TERM_NONE; K.finishing = false; K.replay = 0;
+    K.bt_slot = -1; K.bt_next = 0;
     K.max_mach2 = -INFINITY; K.max_q = -INFINITY; K.max_v2 = -INFINITY; K.max_om = -INFINITY;
     K.min_stab = INFINITY; K.max_stab = -INFINITY; K.max_aoa = -INFINITY;
 }
@@ -1022,7 +1026,7 @@ EMC_HD int rail_phase(const DevModel &M, const DevTables &Tb, const double *wind
         double speed = vx * dx + vy * dy + vz * dz;            /* :75 */
         const double rx = dx * speed - w[0], ry = dy * speed - w[1], rz = dz * speed - w[2];
         const double rel_speed = rx * dx + ry * dy + rz * dz;  /* :80 */
-        const double mach = fast_sqrt((rx * rx + ry * ry + rz * rz) * (inv_RT * (1.0 / 1.4)));
+        const double mach = fast_sqrt((rx * rx + ry * ry + rz * rz) * (inv_RT * M.mach_k));
         const int jd = brk_find(Tb.m_lo, Tb.m_hi, M.n_mb, WB.j_m, mach);
         WB.j_m = jd;
         const double dm = mach - Tb.cd_x0[jd];
@@ -1114,7 +1118,7 @@ EMC_HD void component_eval(const DevModel &M, const DevTables &Tb, int comp, con
     if (comp == 0) {
         double T, inv_RT, p;
         atmosphere(M, in[0], T, inv_RT, p);
-        out[0] = T; out[ld] = p; out[2 * ld] = p * inv_RT; out[3 * ld] = sqrt(1.4 * M.R_gas * T); out[4 * ld] = gravity(M, in[0]);
+        out[0] = T; out[ld] = p; out[2 * ld] = p * inv_RT; out[3 * ld] = sqrt(M.gamma * M.R_gas * T); out[4 * ld] = gravity(M, in[0]);
     } else if (comp == 1) {
         const double pf = in[0], dry = in[ld], prop = in[2 * ld];
         const double mp = prop * pf, mass = dry + mp;
@@ -1181,7 +1185,7 @@ EMC_HD void series_state(const DevModel &M, const DevTables &Tb, const double *w
     const double r20 = qx * z2 - qw * y2, r21 = qy * z2 + qw * x2, r22 = 1.0 - (qx * x2 + qy * y2);
     const double vbx = r00 * ux + r10 * uy + r20 * uz, vby = r01 * ux + r11 * uy + r21 * uz, vbz = r02 * ux + r12 * uy + r22 * uz;
     const double v2 = ux * ux + uy * uy + uz * uz;
-    const double mach2 = v2 * (inv_RT * K_MISC[7]);
+    const double mach2 = v2 * (inv_RT * M.mach_k);
     double mach = fast_sqrt(mach2);
     const double mach_c = (mach > 1e300) ? 1e300 : mach;
     const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);

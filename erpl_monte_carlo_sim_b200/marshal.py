@@ -37,6 +37,7 @@ def model_dict(rocket, motor, atmosphere, sim, altitude_profile=None) -> dict:
         temperature_lapse_rate=f(atmosphere.temperature_lapse_rate), gas_constant=f(atmosphere.gas_constant),
         gravity=f(atmosphere.gravity), troposphere_height=f(atmosphere.troposphere_height),
         stratosphere_height=f(atmosphere.stratosphere_height), stratosphere_temp=f(atmosphere.stratosphere_temp),
+        gamma=f(getattr(atmosphere, "gamma", 1.4)),
         max_time=f(sim.max_time), dt_initial=f(sim.dt_initial), pitch_damping=f(sim.pitch_damping),
         yaw_damping=f(sim.yaw_damping), rail_length=f(getattr(sim, "rail_length", RAIL_LENGTH)),
         has_wind=0 if altitude_profile is None else 1,

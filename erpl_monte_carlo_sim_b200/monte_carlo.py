@@ -62,6 +62,14 @@ class DispersionSet:
             d.density_multiplier[i] = p["density_multiplier"]; d.seed[i] = p["random_seed"]
         return d
 
+    def take(self, ids):
+        ids = np.asarray(ids, np.int64)
+        d = DispersionSet(ids.size)
+        for k in ("pos", "vel", "att", "omega", "mass_multiplier", "thrust_multiplier", "wind_speed",
+                  "wind_direction", "density_multiplier", "seed"):
+            setattr(d, k, getattr(self, k)[ids])
+        return d
+
     def slice(self, lo, hi):
         d = DispersionSet(hi - lo)
         for k in ("pos", "vel", "att", "omega", "mass_multiplier", "thrust_multiplier", "wind_speed",
@@ -70,39 +78,114 @@ class DispersionSet:
         return d
 
 
+class SampleDict(dict):
+    """One sample's result dict.  The reference attaches 'trajectory' = {time, altitude, position(n,3)} to every result
+    (monte_carlo.py:296-302); here it is served on first access from the downsampled tape the flight kernel recorded
+    (BatchRun.trajectory), so building 1e5 result dicts does not move 1e5 time series."""
+
+    def __init__(self, data, run, i):
+        super().__init__(data)
+        self._run, self._i = run, i
+
+    def __missing__(self, key):
+        if key == "trajectory":
+            self["trajectory"] = t = self._run.trajectory(self._i)
+            return t
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return key == "trajectory" or dict.__contains__(self, key)
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
 class SampleResults(Sequence):
     """`analysis['results']` / `analysis['outliers']`: one dict per sample, built on access from the
     engine's SoA summary (the reference materialises every time series of every sample in a list)."""
 
-    def __init__(self, owner, ids, reasons=None):
-        self._owner, self._ids, self._reasons = owner, np.asarray(ids, np.int64), reasons
+    def __init__(self, owner, ids, with_reasons=False):
+        self._owner, self._ids, self._with_reasons = owner, np.asarray(ids, np.int64), with_reasons
 
     def __len__(self):
         return len(self._ids)
+
+    @property
+    def sample_indices(self):
+        """Indices (into the rank-local batch) of the samples in this list."""
+        return self._ids
 
     def __getitem__(self, k):
         if isinstance(k, slice):
             return [self[i] for i in range(*k.indices(len(self)))]
         i = int(self._ids[k])
         d = self._owner.sample_result(i)
-        if self._reasons is not None:
-            d["outlier_reasons"] = self._reasons[k]
+        if self._with_reasons:
+            d["outlier_reasons"] = MonteCarloAnalyzer._outlier_reasons(d["apogee_altitude"], d["range"], d["flight_time"])
         return d
 
 
 class BatchRun:
-    """Everything one Monte Carlo batch produced: dispersions, inputs summary and the SoA outputs."""
+    """Everything one Monte Carlo batch produced on this rank: dispersions, inputs and the SoA outputs.  `disp` and
+    `scalars` may be given as zero-argument callables: the device-generated modes fetch them only when somebody looks."""
 
-    def __init__(self, analyzer, base_ic, disp, out, iout, altitude_profile, scalars, outputs_resident=False):
-        self.analyzer, self.base_ic, self.disp = analyzer, base_ic, disp
-        self.out, self.iout, self.altitude_profile, self.scalars = out, iout, altitude_profile, scalars
+    def __init__(self, analyzer, base_ic, disp, out, iout, altitude_profile, scalars, outputs_resident=False, first_id=0):
+        self.analyzer, self.base_ic, self._disp = analyzer, base_ic, disp
+        self.out, self.iout, self.altitude_profile, self._scalars = out, iout, altitude_profile, scalars
         self.outputs_resident = outputs_resident      # the engine still holds these outputs in HBM (single chunk)
+        self.first_id = int(first_id)                 # global index (= seed) of local sample 0: rank r of a sharded run
+        self.n = out.shape[1]
+        self.tape_ids = np.zeros(0, np.int64)         # local samples whose downsampled trajectory was recorded
+        self.tape_rows = np.zeros((0, 2, _abi.BTAPE_WIDTH)); self.tape_count = np.zeros(0, np.int32); self.tape_stride = 0
+        self._tape_pos = {}
+
+    @property
+    def disp(self):
+        if callable(self._disp):
+            self._disp = self._disp()
+        return self._disp
+
+    @property
+    def scalars(self):
+        if callable(self._scalars):
+            self._scalars = self._scalars()
+        return self._scalars
+
+    def add_tape(self, ids, rows, count, stride):
+        ids = np.asarray(ids, np.int64)
+        if self.tape_ids.size and rows.shape[1] != self.tape_rows.shape[1]:
+            m = max(rows.shape[1], self.tape_rows.shape[1])
+            pad = lambda r: np.concatenate([r, np.full((r.shape[0], m - r.shape[1], r.shape[2]), np.nan)], axis=1)
+            rows, self.tape_rows = pad(rows), pad(self.tape_rows)
+        base = self.tape_ids.size
+        self.tape_ids = np.concatenate([self.tape_ids, ids])
+        self.tape_rows = rows if base == 0 else np.concatenate([self.tape_rows, rows])
+        self.tape_count = np.concatenate([self.tape_count, np.asarray(count, np.int32)])
+        self.tape_stride = stride
+        for k, i in enumerate(ids):
+            self._tape_pos[int(i)] = base + k
+
+    def ensure_trajectories(self, ids):
+        """Record the downsampled trajectories of local samples `ids` that the run did not tape, as ONE extra batch."""
+        missing = [int(i) for i in ids if int(i) not in self._tape_pos]
+        if missing:
+            self.analyzer._tape_samples(self, missing)
+
+    def trajectory(self, i):
+        """{'time', 'altitude', 'position' (m,3)} of local sample i from the kernel's downsampled tape (every
+        `trajectory_stride`-th stored state and the last one; time since rail exit as in the reference)."""
+        if int(i) not in self._tape_pos:
+            self.ensure_trajectories([i])
+        k = self._tape_pos[int(i)]
+        m = int(min(self.tape_count[k], self.tape_rows.shape[1]))
+        r = self.tape_rows[k, :m]
+        return {"time": r[:, 0].copy(), "altitude": r[:, 3].copy(), "position": r[:, 1:4].copy()}
 
     def sample_result(self, i):
         O = _abi.OUT
         o = self.out[:, i]
         d = {
-            "simulation_id": i, "parameters": self.disp.as_dict(i),
+            "simulation_id": self.first_id + i, "parameters": self.disp.as_dict(i),
             "apogee_altitude": o[O["apogee_altitude"]], "apogee_time": o[O["apogee_time"]],
             "range": o[O["range"]], "flight_time": o[O["flight_time"]],
             "rail_exit_time": o[O["rail_exit_time"]],
@@ -114,15 +197,21 @@ class BatchRun:
             "wind_at_exit": o[O["wind_at_exit_u"]:O["wind_at_exit_w"] + 1].copy(),
         }
         d.update(summary_extras(self.out, self.iout, i))
-        return d
+        return SampleDict(d, self, i)
 
     def full_result(self, i):
-        """Re-fly sample i with the tape on: the complete `simulate_flight` dict incl. time series."""
+        """Re-fly local sample i with the full tape on: the complete `simulate_flight` dict incl. every time series."""
         return self.analyzer.resimulate(self.base_ic, self.disp.as_dict(i))
 
 
+def shard_range(n, rank, world):
+    """Contiguous sample-index range [lo, hi) of rank `rank` among `world` ranks: the GPU-side counterpart of the
+    reference's process-pool fan-out (monte_carlo.py:63-83).  Ranges tile [0, n) exactly, sizes differ by at most one."""
+    return rank * n // world, (rank + 1) * n // world
+
+
 class MonteCarloAnalyzer:
-    def __init__(self, rocket, motor, atmosphere, wind_model, device: int = 0):
+    def __init__(self, rocket, motor, atmosphere, wind_model, device=None):
         self.rocket = rocket
         self.motor = motor
         self.atmosphere = atmosphere
@@ -141,16 +230,44 @@ class MonteCarloAnalyzer:
             "wind_direction_range": [0.0, 2 * np.pi],
             "atmospheric_density_uncertainty": 0.05,
         }
-        self.device = device
-        self.chunk_size = 1 << 16
+        self.device = device              # None: cuda:LOCAL_RANK inside a torch.distributed job, else cuda:0
+        self.chunk_size = 1 << 21         # samples per kernel launch (C4's 1.25 M per GPU is one launch)
         self.run_opts = None
         self.histogram_bins = 0
         # "numpy": the reference's own MT19937 streams drawn on the host (bit-matched inputs)
         # "numpy-device": the same streams regenerated on the GPU (same bits up to the last place of log/sqrt)
         # "philox": counter-based draws on the GPU (same distribution and stream structure)
-        self.rng = "numpy"
+        # "auto": "numpy" up to host_rng_max samples, "numpy-device" beyond (no per-sample host loop on large runs)
+        self.rng = "auto"
+        self.host_rng_max = 4096
         self.philox_seed = 0
+        # the reference stores the whole trajectory of every sample (monte_carlo.py:296-302); the engine records a
+        # downsampled tape {t, x, y, z} of the first `trajectory_samples` samples of a run while they fly (every
+        # `trajectory_stride`-th stored state = 0.1 s, plus the last one); any other sample is taped on demand
+        self.trajectory_samples = 64
+        self.trajectory_stride = 20
+        # inside an initialised torch.distributed job the samples are sharded over the ranks (rank r flies the seeds
+        # shard_range(n, r, world)) and the statistics are all-reduced over NCCL; False: every rank flies all n samples
+        self.shard = True
         self.last_run = None
+
+    def _dev(self):
+        if self.device is not None:
+            return int(self.device)
+        return int(os.environ.get("LOCAL_RANK", "0")) if stats._dist_active() else 0
+
+    def _rank_world(self):
+        if self.shard and stats._dist_active():
+            import torch.distributed as dist
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    def _rng_mode(self, n):
+        if self.rng == "auto":
+            return "numpy" if n <= self.host_rng_max else "numpy-device"
+        if self.rng not in ("numpy", "numpy-device", "philox"):
+            raise ValueError(f"MonteCarloAnalyzer.rng = {self.rng!r}: expected auto, numpy, numpy-device or philox")
+        return self.rng
 
     # ------------------------------------------------------------------------------------------
     # dispersion draws (host-seeded: the reference's own NumPy streams)
@@ -320,7 +437,7 @@ class MonteCarloAnalyzer:
 
     def numpy_device_parameters(self, n, first_seed=0) -> DispersionSet:
         """draw_parameters() from the MT19937 streams the device regenerates (no per-sample host loop)."""
-        g, u, dens = get_engine(self.device).numpy_draws(first_seed, n, 15)
+        g, u, dens = get_engine(self._dev()).numpy_draws(first_seed, n, 15)
         g[:, 14] = dens
         return self._parameters_from_draws(g, u, np.arange(first_seed, first_seed + n, dtype=np.uint64))
 
@@ -337,69 +454,148 @@ class MonteCarloAnalyzer:
         d.seed[:] = idx.astype(np.int64)
         return d
 
-    def run_batch_numpy_device(self, initial_conditions, n, first_seed=0) -> BatchRun:
+    def run_batch_numpy_device(self, initial_conditions, n, first_seed=0, tape_ids=None) -> BatchRun:
         """Host-seeded semantics without the host: MT19937(seed = sample index) and NumPy's legacy Gaussian regenerated,
         perturbed and flown on the GPU."""
-        return self.run_batch_philox(initial_conditions, n, first_index=first_seed, numpy_streams=True)
+        return self.run_batch_philox(initial_conditions, n, first_index=first_seed, numpy_streams=True, tape_ids=tape_ids)
 
-    def run_batch_philox(self, initial_conditions, n, first_index=0, numpy_streams=False) -> BatchRun:
+    def _tape_rows(self):
+        """Row capacity of one taped trajectory: every stride-th stored state up to max_time, plus the end points."""
+        sim = self._model_simulator()
+        dt = min(0.005, float(sim.dt_initial))
+        return int(np.ceil(max(float(sim.max_time), 0.0) / dt / max(int(self.trajectory_stride), 1))) + 4
+
+    def _chunk_tape_ids(self, lo, hi, want):
+        """Chunk-local indices of the samples in [lo, hi) that are to be taped during the run."""
+        if want is not None:
+            w = np.asarray(want, np.int64)
+            return w[(w >= lo) & (w < hi)] - lo
+        return np.arange(lo, min(hi, max(int(self.trajectory_samples), 0)), dtype=np.int64) - lo
+
+    def run_batch_philox(self, initial_conditions, n, first_index=0, numpy_streams=False, tape_ids=None) -> BatchRun:
         """Draw, perturb and fly n samples entirely on the GPU (no host input generation, no input upload)."""
-        eng = get_engine(self.device)
+        eng = get_engine(self._dev())
         alts = self._altitude_grid()
         eng.set_model(marshal.model_dict(self.rocket, self.motor, self.atmosphere, self._model_simulator(), alts))
         disp_struct = self.dispersion_struct(initial_conditions)
-        out = np.empty((_abi.OUT_COUNT, n)); iout = np.empty((_abi.IOUT_COUNT, n), np.int32); scal = np.empty((_abi.IN_COUNT, n))
-        for lo in range(0, n, self.chunk_size):
+        single = n <= self.chunk_size
+        out = None if single else np.empty((_abi.OUT_COUNT, n))
+        iout = None if single else np.empty((_abi.IOUT_COUNT, n), np.int32)
+        taped = []
+        stride, rows_cap = max(int(self.trajectory_stride), 1), self._tape_rows()
+        for lo in range(0, max(n, 1), self.chunk_size):
             hi = min(n, lo + self.chunk_size)
             if numpy_streams:
                 eng.generate_inputs_numpy(disp_struct, first_index + lo, hi - lo)
             else:
                 eng.generate_inputs(disp_struct, self.philox_seed, first_index + lo, hi - lo)
+            ids = self._chunk_tape_ids(lo, hi, tape_ids)
+            if ids.size:
+                eng.tape_request(ids, stride, rows_cap)
             o, io = eng.run_batch_staged(hi - lo, opts=self.run_opts)
-            out[:, lo:hi] = o; iout[:, lo:hi] = io
-            scal[:, lo:hi] = eng.staged_inputs(hi - lo, want_wind=False)[0]
-        params = self.numpy_device_parameters(n, first_index) if numpy_streams else self.philox_parameters(n, first_index)
-        self.last_run = BatchRun(self, dict(initial_conditions), params, out, iout, alts, scal, outputs_resident=(n <= self.chunk_size))
-        return self.last_run
+            if single:
+                out, iout = o, io
+            else:
+                out[:, lo:hi] = o; iout[:, lo:hi] = io
+            if ids.size:
+                taped.append((ids + lo,) + eng.tape_fetch())
+
+        def params():
+            return self.numpy_device_parameters(n, first_index) if numpy_streams else self.philox_parameters(n, first_index)
+
+        def scalars():
+            sc = np.empty((_abi.IN_COUNT, n))
+            for lo in range(0, n, self.chunk_size):
+                hi = min(n, lo + self.chunk_size)
+                if numpy_streams:
+                    eng.generate_inputs_numpy(disp_struct, first_index + lo, hi - lo)
+                else:
+                    eng.generate_inputs(disp_struct, self.philox_seed, first_index + lo, hi - lo)
+                sc[:, lo:hi] = eng.staged_inputs(hi - lo, want_wind=False)[0]
+            return sc
+
+        run = BatchRun(self, dict(initial_conditions), params, out, iout, alts, scalars, outputs_resident=single, first_id=first_index)
+        run.mode = "numpy-device" if numpy_streams else "philox"
+        for ids, rows, cnt in taped:
+            run.add_tape(ids, rows, cnt, stride)
+        self.last_run = run
+        return run
 
     def _model_simulator(self):
-        return FlightSimulator(self.rocket, self.motor, self.atmosphere, self.wind_model, device=self.device)
+        return FlightSimulator(self.rocket, self.motor, self.atmosphere, self.wind_model, device=self._dev())
 
     # ------------------------------------------------------------------------------------------
     # running
     # ------------------------------------------------------------------------------------------
-    def run_batch(self, initial_conditions, disp: DispersionSet) -> BatchRun:
-        eng = get_engine(self.device)
+    def run_batch(self, initial_conditions, disp: DispersionSet, first_id=0, tape_ids=None) -> BatchRun:
+        eng = get_engine(self._dev())
         alts = self._altitude_grid()
         md = marshal.model_dict(self.rocket, self.motor, self.atmosphere, self._model_simulator(), alts)
         eng.set_model(md)
         n = disp.n
         out = np.empty((_abi.OUT_COUNT, n)); iout = np.empty((_abi.IOUT_COUNT, n), np.int32)
         scal = np.empty((_abi.IN_COUNT, n))
+        taped = []
+        stride, rows_cap = max(int(self.trajectory_stride), 1), self._tape_rows()
         for lo in range(0, n, self.chunk_size):
             hi = min(n, lo + self.chunk_size)
             blk, wind, _ = self.build_inputs(initial_conditions, disp.slice(lo, hi))
+            ids = self._chunk_tape_ids(lo, hi, tape_ids)
+            if ids.size:
+                eng.tape_request(ids, stride, rows_cap)
             o, io = eng.run_batch(blk, wind, opts=self.run_opts)
             out[:, lo:hi] = o; iout[:, lo:hi] = io; scal[:, lo:hi] = blk
-        self.last_run = BatchRun(self, dict(initial_conditions), disp, out, iout, alts, scal, outputs_resident=(n <= self.chunk_size))
-        return self.last_run
+            if ids.size:
+                taped.append((ids + lo,) + eng.tape_fetch())
+        run = BatchRun(self, dict(initial_conditions), disp, out, iout, alts, scal, outputs_resident=(n <= self.chunk_size), first_id=first_id)
+        run.mode = "numpy"
+        for ids, rows, cnt in taped:
+            run.add_tape(ids, rows, cnt, stride)
+        self.last_run = run
+        return run
+
+    def _tape_samples(self, run: BatchRun, ids):
+        """Tape local samples `ids` of a finished run: one extra batch with the tape armed for them.  Host-seeded runs
+        re-fly exactly those samples; device-generated runs regenerate and re-fly the index span that covers them."""
+        ids = np.unique(np.asarray(ids, np.int64))
+        keep_last = self.last_run
+        if getattr(run, "mode", "numpy") == "numpy":
+            sub = self.run_batch(run.base_ic, run.disp.take(ids), tape_ids=np.arange(ids.size))
+            run.add_tape(ids, sub.tape_rows, sub.tape_count, sub.tape_stride)
+        else:
+            # clusters of ids closer than 4096 apart are regenerated as one span
+            cuts = np.flatnonzero(np.diff(ids) > 4096) + 1
+            for grp in np.split(ids, cuts):
+                lo, hi = int(grp[0]), int(grp[-1]) + 1
+                sub = self.run_batch_philox(run.base_ic, hi - lo, first_index=run.first_id + lo,
+                                            numpy_streams=(run.mode == "numpy-device"), tape_ids=grp - lo)
+                run.add_tape(grp, sub.tape_rows, sub.tape_count, sub.tape_stride)
+        run.outputs_resident = False               # the engine's resident block now belongs to the extra batch
+        self.last_run = keep_last
 
     def run_monte_carlo(self, initial_conditions, n_samples=1000, n_processes=None, optimized=False):
-        """n_processes is accepted for signature compatibility; the batch runs on the GPU."""
+        """n_processes is accepted for signature compatibility; the batch runs on the GPU.  Inside an initialised
+        torch.distributed job the samples are sharded over the ranks (the fan-out of monte_carlo.py:63-83): every rank
+        returns the statistics of the WHOLE job and the result lists of its own shard."""
         if optimized:
             return self.run_optimized_monte_carlo(initial_conditions, n_samples)
-        if self.rng == "philox":
-            return self._analyze_run(self.run_batch_philox(initial_conditions, n_samples))
-        if self.rng == "numpy-device":
-            return self._analyze_run(self.run_batch_numpy_device(initial_conditions, n_samples))
-        disp = self.draw_parameters(n_samples)
-        run = self.run_batch(initial_conditions, disp)
+        rank, world = self._rank_world()
+        lo, hi = shard_range(n_samples, rank, world)
+        mode = self._rng_mode(n_samples)
+        if mode == "philox":
+            run = self.run_batch_philox(initial_conditions, hi - lo, first_index=lo)
+        elif mode == "numpy-device":
+            run = self.run_batch_numpy_device(initial_conditions, hi - lo, first_seed=lo)
+        else:
+            run = self.run_batch(initial_conditions, self.draw_parameters(hi - lo, first_seed=lo), first_id=lo)
         return self._analyze_run(run)
 
     def run_optimized_monte_carlo(self, initial_conditions, n_samples=1000, chunk_size=None):
         t0 = time.time()
-        disp = self.draw_parameters(n_samples, optimized=True)
-        run = self.run_batch(initial_conditions, disp)
+        rank, world = self._rank_world()
+        lo, hi = shard_range(n_samples, rank, world)
+        disp = self.draw_parameters(n_samples, optimized=True)          # one sequential stream (seed 42): draw all, keep the shard
+        run = self.run_batch(initial_conditions, disp.slice(lo, hi) if world > 1 else disp, first_id=lo)
         analysis = self._analyze_run(run)
         elapsed = time.time() - t0
         analysis["performance"] = {"total_time": elapsed, "simulations_per_second": n_samples / elapsed,
@@ -411,7 +607,7 @@ class MonteCarloAnalyzer:
         `n_dispersions` dispersed samples (common random numbers, seeds 0..n-1) as ONE batch; per point the statistics
         are reduced on the device and the tail is extracted the way the reference's scripts do it by hand: the sample of
         maximum apogee (find_max_apogee.py:7-17) with its outlier diagnostics (analyze_outlier.py:18-25)."""
-        eng = get_engine(self.device)
+        eng = get_engine(self._dev())
         alts = self._altitude_grid()
         eng.set_model(marshal.model_dict(self.rocket, self.motor, self.atmosphere, self._model_simulator(), alts))
         disp = self.draw_parameters(n_dispersions)
@@ -559,35 +755,154 @@ class MonteCarloAnalyzer:
 
     def _analyze_run(self, run: BatchRun):
         """Statistics of a batch: outlier classification, moments, landing ellipse and exact percentiles are reduced
-        on the GPU (stats.device_statistics; NCCL all-reduce between the passes in a multi-GPU job)."""
+        on the GPU (stats.device_statistics; NCCL all-reduce between the passes in a multi-GPU job, where `run` is this
+        rank's shard and the statistics cover every rank's samples)."""
         O = _abi.OUT
-        if run.disp.n == 0:
+        rank, world = self._rank_world()
+        if run.n == 0 and world == 1:
             raise ValueError("No valid simulation results")
-        eng = get_engine(self.device)
-        if not run.outputs_resident:
+        eng = get_engine(self._dev())
+        if not run.outputs_resident and run.n > 0:
             eng.upload_outputs(run.out)
-        st = stats.device_statistics(eng, run.disp.n, histogram_bins=self.histogram_bins)
+        st = stats.device_statistics(eng, run.n, histogram_bins=self.histogram_bins, distributed=(world > 1))
+        if st["n_total"] == 0:
+            raise ValueError("No valid simulation results")
         if st["n_samples"] == 0:
             raise ValueError("No physically reasonable simulation results after outlier filtering")
         ap, rg, ft = run.out[O["apogee_altitude"]], run.out[O["range"]], run.out[O["flight_time"]]
         bad = self.outlier_mask(ap, rg, ft)                       # per-sample membership for the lazy result lists
         valid_ids, out_ids = np.flatnonzero(~bad), np.flatnonzero(bad)
         d = run.disp
-        ranges = {}
+        keys, lo, hi = [], [], []
         for key, arr in (("initial_position_offset", d.pos), ("initial_velocity_offset", d.vel),
                          ("initial_attitude_offset", d.att), ("initial_angular_velocity_offset", d.omega),
                          ("mass_multiplier", d.mass_multiplier), ("thrust_multiplier", d.thrust_multiplier),
                          ("wind_speed", d.wind_speed), ("wind_direction", d.wind_direction),
                          ("density_multiplier", d.density_multiplier), ("random_seed", d.seed.astype(float))):
-            sel = arr[valid_ids]
-            ranges[key] = {"min": sel.min(axis=0).tolist(), "max": sel.max(axis=0).tolist()}
-        reasons = [self._outlier_reasons(ap[i], rg[i], ft[i]) for i in out_ids] if out_ids.size <= 100000 else None
+            sel = arr[valid_ids].reshape(valid_ids.size, -1)
+            keys.append((key, arr.ndim > 1, sel.shape[1]))
+            lo.append(sel.min(axis=0) if valid_ids.size else np.full(sel.shape[1], np.inf))
+            hi.append(sel.max(axis=0) if valid_ids.size else np.full(sel.shape[1], -np.inf))
+        lo, hi = np.concatenate(lo), np.concatenate(hi)
+        if world > 1:
+            lo, hi = stats.allreduce_minmax(eng, lo, hi)
+        ranges, k = {}, 0
+        for key, is_vec, width in keys:
+            a, b = lo[k:k + width], hi[k:k + width]
+            ranges[key] = {"min": a.tolist(), "max": b.tolist()} if is_vec else {"min": float(a[0]), "max": float(b[0])}
+            k += width
         analysis = {"n_samples": st["n_samples"], "n_failed": 0, "n_outliers": st["n_outliers"],
                     "apogee_altitude": st["apogee_altitude"], "range": st["range"], "flight_time": st["flight_time"],
-                    "results": SampleResults(run, valid_ids), "outliers": SampleResults(run, out_ids, reasons),
+                    "results": SampleResults(run, valid_ids), "outliers": SampleResults(run, out_ids, with_reasons=True),
                     "parameter_ranges_observed": ranges,
                     # engine extras (not in the reference's dict): device-reduced landing ellipse, reasons, histograms
                     "landing_ellipse": st["landing_ellipse"], "outlier_reason_counts": st["outlier_reasons"]}
+        if world > 1:
+            analysis["shard"] = {"rank": rank, "world_size": world, "first_sample": run.first_id, "n_local": run.n}
         if "histograms" in st:
             analysis["histograms"] = st["histograms"]
         return analysis
+
+    # ------------------------------------------------------------------------------------------
+    # plots (monte_carlo.py:562-707): host-only matplotlib code on the analysis dict
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _pyplot():
+        try:
+            import matplotlib
+            matplotlib.use("Agg", force=False)
+            import matplotlib.pyplot as plt
+        except ImportError as e:                                  # the reference imports it at module top (monte_carlo.py:6)
+            raise ImportError("MonteCarloAnalyzer.plot_* need matplotlib (the reference lists it in requirements.txt)") from e
+        return plt
+
+    @staticmethod
+    def _metric_arrays(results):
+        """apogee / range / flight time of a result list as arrays (straight from the SoA block when it is ours)."""
+        if isinstance(results, SampleResults):
+            o, ids, O = results._owner.out, results._ids, _abi.OUT
+            return o[O["apogee_altitude"], ids], o[O["range"], ids], o[O["flight_time"], ids]
+        return (np.array([r["apogee_altitude"] for r in results], float), np.array([r["range"] for r in results], float),
+                np.array([r["flight_time"] for r in results], float))
+
+    def plot_results(self, analysis, save_plots=True):
+        """Histograms of apogee, range, flight time and the range-vs-apogee scatter (monte_carlo.py:562-633)."""
+        plt = self._pyplot()
+        output_dir = None
+        _, axes = plt.subplots(2, 2, figsize=(12, 10))
+        ap, rg, ft = self._metric_arrays(analysis["results"])
+        for ax, vals, label, title in ((axes[0, 0], ap, "Apogee Altitude (m)", "Apogee Altitude Distribution"),
+                                       (axes[0, 1], rg, "Range (m)", "Range Distribution"),
+                                       (axes[1, 0], ft, "Flight Time (s)", "Flight Time Distribution")):
+            ax.hist(vals[np.isfinite(vals)], bins=50, alpha=0.7, edgecolor="black")
+            ax.set_xlabel(label); ax.set_ylabel("Frequency"); ax.set_title(title); ax.grid(True, alpha=0.3)
+        ok = np.isfinite(ap) & np.isfinite(rg)
+        axes[1, 1].scatter(ap[ok], rg[ok], alpha=0.6, s=10)
+        axes[1, 1].set_xlabel("Apogee Altitude (m)"); axes[1, 1].set_ylabel("Range (m)")
+        axes[1, 1].set_title("Range vs Apogee Altitude"); axes[1, 1].grid(True, alpha=0.3)
+        plt.tight_layout()
+        if save_plots:
+            output_dir = self._create_output_directory()
+            plot_path = os.path.join(output_dir, "monte_carlo_distributions.png")
+            plt.savefig(plot_path, dpi=300, bbox_inches="tight")
+            print(f"Plots saved to: {plot_path}")
+            self._save_report(analysis, output_dir)
+            print(f"Report saved to: {output_dir}")
+        print("\nMonte Carlo Analysis Results:")
+        print(f"Number of valid simulations: {analysis['n_samples']}")
+        print(f"Number of failed simulations: {analysis['n_failed']}")
+        print(f"Number of outlier simulations: {analysis['n_outliers']}")
+        for key, title in (("apogee_altitude", "Apogee Altitude"), ("range", "Range")):
+            st = analysis[key]
+            print(f"\n{title} Statistics:")
+            print(f"  Mean: {st['mean']:.1f} m")
+            print(f"  Standard Deviation: {st['std']:.1f} m")
+            print(f"  95% Confidence Interval: [{st['percentiles'][0]:.1f}, {st['percentiles'][4]:.1f}] m")
+        return output_dir
+
+    def _cloud(self, analysis, max_trajectories):
+        """The first max_trajectories results with their trajectories; what the run did not tape is taped as ONE batch."""
+        results = analysis["results"]
+        if isinstance(results, SampleResults):
+            results._owner.ensure_trajectories(results._ids[:max_trajectories])
+        return results[:max_trajectories]
+
+    def plot_trajectory_cloud(self, analysis, save_plots=True, max_trajectories=50):
+        """Altitude-vs-time and ground-track clouds (monte_carlo.py:635-677)."""
+        plt = self._pyplot()
+        _, (ax1, ax2) = plt.subplots(1, 2, figsize=(15, 6))
+        trajectories = self._cloud(analysis, max_trajectories)
+        for result in trajectories:
+            if "trajectory" in result:
+                tr = result["trajectory"]
+                ax1.plot(tr["time"], tr["altitude"], alpha=0.3, linewidth=0.5, color="blue")
+                if "position" in tr:
+                    ax2.plot(tr["position"][:, 0], tr["position"][:, 1], alpha=0.3, linewidth=0.5, color="red")
+        ax1.set_xlabel("Time (s)"); ax1.set_ylabel("Altitude (m)")
+        ax1.set_title(f"Trajectory Cloud - Altitude vs Time\n({len(trajectories)} trajectories)"); ax1.grid(True, alpha=0.3)
+        ax2.set_xlabel("East Position (m)"); ax2.set_ylabel("North Position (m)")
+        ax2.set_title(f"Ground Track Cloud\n({len(trajectories)} trajectories)"); ax2.grid(True, alpha=0.3); ax2.axis("equal")
+        plt.tight_layout()
+        if save_plots:
+            output_dir = self._create_output_directory()
+            plot_path = os.path.join(output_dir, "monte_carlo_trajectories.png")
+            plt.savefig(plot_path, dpi=300, bbox_inches="tight")
+            print(f"Trajectory plots saved to: {plot_path}")
+
+    def plot_trajectory_cloud_3d(self, analysis, save_plots=True, max_trajectories=50):
+        """3-D trajectory cloud (monte_carlo.py:679-707)."""
+        plt = self._pyplot()
+        fig = plt.figure(figsize=(10, 8))
+        ax = fig.add_subplot(111, projection="3d")
+        trajectories = self._cloud(analysis, max_trajectories)
+        for result in trajectories:
+            if "trajectory" in result and "position" in result["trajectory"]:
+                pos = result["trajectory"]["position"]
+                ax.plot(pos[:, 0], pos[:, 1], pos[:, 2], alpha=0.3, linewidth=0.5)
+        ax.set_xlabel("East Position (m)"); ax.set_ylabel("North Position (m)"); ax.set_zlabel("Altitude (m)")
+        ax.set_title(f"3D Trajectory Cloud ({len(trajectories)} trajectories)"); ax.grid(True, alpha=0.3)
+        if save_plots:
+            output_dir = self._create_output_directory()
+            plot_path = os.path.join(output_dir, "monte_carlo_trajectories_3d.png")
+            plt.savefig(plot_path, dpi=300, bbox_inches="tight")
+            print(f"3D trajectory plot saved to: {plot_path}")

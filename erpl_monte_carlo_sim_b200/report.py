@@ -46,12 +46,12 @@ def save_report(analyzer, analysis, output_dir, max_samples=1000):
 
     sims = os.path.join(output_dir, "simulation_results")
     os.makedirs(sims, exist_ok=True)
-    run = analyzer.last_run
     results = analysis.get("results", [])
+    run = getattr(results, "_owner", None) or analyzer.last_run      # the run that produced THIS analysis
     for k in range(min(len(results), max_samples)):
         brief = results[k]
         sim_id = brief.get("simulation_id", k)
-        full = run.full_result(int(sim_id)) if run is not None else brief
+        full = run.full_result(int(sim_id) - run.first_id) if run is not None else brief
         full["simulation_id"] = sim_id
         with open(os.path.join(sims, f"sim_{sim_id}.json"), "w") as fh:
             json.dump(to_serializable(full), fh)

@@ -175,6 +175,17 @@ class DeviceBackend:
         return bh.get().astype(np.int64)
 
 
+def allreduce_minmax(engine, lo, hi):
+    """Element-wise min of `lo` and max of `hi` over the ranks of the initialised process group (NCCL on the engine's GPU,
+    gloo on the host)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", engine.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+    a, b = torch.as_tensor(np.ascontiguousarray(lo), device=dev), torch.as_tensor(np.ascontiguousarray(hi), device=dev)
+    dist.all_reduce(a, op=dist.ReduceOp.MIN); dist.all_reduce(b, op=dist.ReduceOp.MAX)
+    return a.cpu().numpy(), b.cpu().numpy()
+
+
 def ordered_keys(v):
     """Order-preserving map float64 -> uint64 (the device kernel's `ordered_key`)."""
     b = np.asarray(v, np.float64).view(np.uint64)

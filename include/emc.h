@@ -12,7 +12,10 @@
  *  - plain C: pointers, sizes, doubles and 32/64-bit integers only; no exceptions cross the ABI.
  *  - every function returns 0 on success or a negative emc_status; emc_last_error() gives text.
  *  - the library copies what it needs; the caller keeps ownership of every buffer it passes.
- *  - calls on one context are serialised by the caller; a context owns one CUDA device.
+ *  - calls on one context are serialised by the caller; a context owns one CUDA device.  Several contexts may share a
+ *    device: the run constants live in per-device __constant__ memory and are re-uploaded whenever the context that
+ *    launches is not the one that uploaded last (the device is synchronised at that switch), so contexts never see each
+ *    other's model; calls on DIFFERENT contexts of one device must not overlap in time.
  *  - all arithmetic is IEEE-754 binary64 (the reference's Python floats / NumPy float64).
  *  - there is NO CPU implementation behind these symbols: without a CUDA device emc_create fails.
  */
@@ -25,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EMC_ABI_VERSION 1
+#define EMC_ABI_VERSION 2
 
 /* ---- limits of the run-constant tables (rocket.py:43-53, motor.py:31-41) ---- */
 #define EMC_MAX_CD_KNOTS 16
@@ -77,6 +80,10 @@ typedef struct emc_model {
     int32_t has_wind;                 /* 0: wind_profile/altitude_profile were None (simulator.py:333) */
     int32_t n_wind;                   /* knots in the altitude grid (<= EMC_MAX_WIND_KNOTS) */
     const double *wind_altitudes;     /* [n_wind], host pointer, copied by emc_set_model */
+    /* ABI 2 (appended): atmosphere.gamma, read only by get_properties' speed_of_sound (environment.py:96); the Mach number
+     * of the flight path uses the literals 1.4 and 287.053 of utils.mach_number (utils.py:152-157) whatever the
+     * atmosphere object holds.  0 = 1.4. */
+    double gamma;
 } emc_model;
 
 /* ---- per-sample inputs: one field-major block  scalars[EMC_IN_COUNT][ld] ---- */
@@ -171,6 +178,7 @@ typedef struct emc_counters {
     int64_t refills;          /* work-queue fetches */
     int64_t kernel_launches;  /* kernels launched by the call */
     double rail_ms, flight_ms;/* device time of the two kernels (CUDA events on the context stream) */
+    int64_t tape_rows;        /* ABI 2: rows stored by an armed batch tape (emc_tape_request) */
 } emc_counters;
 
 int emc_abi_version(void);
@@ -191,6 +199,21 @@ int emc_run_batch_device(emc_ctx *ctx, const emc_inputs *in_dev, int64_t n, cons
 /* One sample with every stored state written to tape[cap][EMC_TAPE_WIDTH] (simulator.py:212-231). */
 int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_outputs *out,
                  double *tape, int64_t cap, int64_t *n_states);
+
+/* ---- downsampled trajectory tape of a batch (reference monte_carlo.py:296-302: every result of a Monte Carlo run
+ *      carries 'trajectory' = {time, altitude, position}; plot_trajectory_cloud(_3d) :635-707 read it) -------------
+ * Arms the NEXT emc_run_batch / emc_run_batch_device / emc_run_batch_staged of this context: for every listed sample the
+ * flight kernel stores the stored states 0, stride, 2*stride, ... (state 0 = rail exit, simulator.py:212-214) and the last
+ * integrated one as rows {t - t_rail, x, y, z} (the reference's shifted time axis, simulator.py:464) into HBM while it
+ * flies — nothing is re-flown.  Rows past max_rows are counted but not stored; a trajectory that is fast-forwarded as
+ * all-NaN (emc_run_opts.nan_fast_forward) stops recording at the fast-forward point.  The request is consumed by that
+ * run; emc_tape_fetch then copies rows[n_sel][max_rows][EMC_BTAPE_WIDTH] and n_rows[n_sel] to the host. */
+#define EMC_BTAPE_WIDTH 4
+int emc_tape_request(emc_ctx *ctx, const int64_t *samples /*host [n_sel], indices into the next batch*/, int64_t n_sel,
+                     int32_t stride, int32_t max_rows);
+int emc_tape_fetch(emc_ctx *ctx, double *rows /*host [n_sel][max_rows][4]*/, int32_t *n_rows /*host [n_sel]*/);
+/* device pointers of the tape of the last armed run (rows_dev [n_sel][max_rows][4], n_rows_dev [n_sel]) and its size */
+int emc_tape_resident(emc_ctx *ctx, double **rows_dev, int32_t **n_rows_dev, int64_t *n_sel, int32_t *max_rows);
 
 /* ---- device-side dispersion draws (reference monte_carlo.py:156-201,225-288; motor.py:95-125,171-186;
  *      environment.py:125-200,218-265) -------------------------------------------------------------------
