@@ -51,6 +51,8 @@ struct KernelArgs {
     int32_t refill_threshold; int32_t nan_ff;
     /* downsampled batch tape (emc_tape_request): slot of every sample (-1: not recorded), rows[n_sel][bt_max][4], counts */
     const int32_t *bt_slot; double *bt_rows; int32_t *bt_count; int32_t bt_stride, bt_max;
+    /* once-per-step bookkeeping of the 16-warp variant: [TC_DCOUNT][gcold_ld] doubles, [TI_ICOUNT][gcold_ld] ints */
+    double *gcold_d; int32_t *gcold_i; int64_t gcold_ld;
 };
 
 /* Stage the run-constant tables into shared memory.  The tables are a STATIC __shared__ object and the wind
@@ -90,16 +92,30 @@ __global__ void __launch_bounds__(128) emc_rail_kernel(KernelArgs a)
 
 /* ------------------------------------------------------------------------------------------------ */
 /* Per-lane state that is touched once per step or per derivative (event bookkeeping, sample constants,
- * the remembered table brackets) can live in shared memory instead of registers (COLD = 1): the
+ * the remembered table brackets) can live in shared memory instead of registers (COLD >= 1): the
  * derivative then fits in fewer registers and more warps are resident to hide the FP64 latency.
- * The structs are padded to an odd number of 8-byte words, so lane-strided access is conflict-free. */
-struct alignas(8) ColdLaneRaw { Track K; Sample S; WindBracket WB; };
+ * The structs span an odd number of 8-byte words, so lane-strided access is conflict-free.
+ * COLD == 3 keeps only the HOT half of the bookkeeping here; the once-per-step half (running maxima, event times,
+ * tape cursor) goes to global memory, field-major over the resident lanes (GlobalCold): 200 B + 224 B of state store
+ * per lane let 512 lanes (16 warps) share an SM. */
+struct alignas(8) ColdLaneFull { TrackHot K; TrackCold C; Sample S; WindBracket WB; };
+struct alignas(8) ColdLaneHot { TrackHot K; Sample S; WindBracket WB; };
 template <bool PAD> struct ColdPad { double pad_; };
 template <> struct ColdPad<false> {};
-struct ColdLane : ColdLaneRaw, ColdPad<(sizeof(ColdLaneRaw) / 8) % 2 == 0> {};
-static_assert(sizeof(ColdLane) % 8 == 0 && (sizeof(ColdLane) / 8) % 2 == 1, "ColdLane must span an odd number of 8-byte words");
+template <class Raw> struct Padded : Raw, ColdPad<(sizeof(Raw) / 8) % 2 == 0> {};
+static_assert(sizeof(Padded<ColdLaneFull>) % 8 == 0 && (sizeof(Padded<ColdLaneFull>) / 8) % 2 == 1, "lane state must span an odd number of 8-byte words");
+static_assert(sizeof(Padded<ColdLaneHot>) % 8 == 0 && (sizeof(Padded<ColdLaneHot>) / 8) % 2 == 1, "lane state must span an odd number of 8-byte words");
 
-/* Dynamic shared memory of the flight kernel: [28][BLOCK] state store (COLD == 2) followed by the wind altitude grid.
+/* cold bookkeeping in global memory: d[field][lane], i[field][lane], lane = resident lane of the grid */
+struct GlobalCold {
+    double *d; int32_t *i; int64_t ld;
+    __device__ __forceinline__ double getd(int f) const { return d[f * ld]; }
+    __device__ __forceinline__ void setd(int f, double v) const { d[f * ld] = v; }
+    __device__ __forceinline__ int32_t geti(int f) const { return i[f * ld]; }
+    __device__ __forceinline__ void seti(int f, int32_t v) const { i[f * ld] = v; }
+};
+
+/* Dynamic shared memory of the flight kernel: [28][BLOCK] state store (COLD >= 2) followed by the wind altitude grid.
  * It is indexed directly (never through a pointer carved out of it), so the accesses are plain LDS/STS. */
 extern __shared__ double emc_dyn[];
 
@@ -120,21 +136,18 @@ struct SharedStore {
     __device__ __forceinline__ void set_acc(int i, double v) { emc_dyn[(14 + i) * BLOCK + threadIdx.x] = v; }
 };
 
-template <int BLOCK, int COLD, class Store>
-__device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *alt)
+/* the persistent loop, generic over where the lane state lives: K/S/WB are references (registers or shared memory),
+ * C is the accessor of the cold bookkeeping */
+template <int BLOCK, class Store, class CA, int MK, int WK>
+__device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables &Tb, const double *alt,
+                                            TrackHot &K, const CA &C, Sample &S, WindBracket &WB)
 {
-    __shared__ DevTables Tb;
-    __shared__ ColdLane sh_cold[COLD ? BLOCK : 1];
-    stage_tables(Tb, alt, a);
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
 
     bool active = false, drained = false;
     int64_t idx = -1;
     Store st;
-    ColdLane reg_lane;                     /* COLD = 0: plain registers */
-    ColdLane &CL = COLD ? sh_cold[COLD ? threadIdx.x : 0] : reg_lane;
-    Track &K = CL.K; Sample &S = CL.S; WindBracket &WB = CL.WB;
     unsigned long long n_steps = 0, n_replay = 0, n_refill = 0, n_tape = 0;
     const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
 
@@ -161,7 +174,7 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
                             State s;
                             load_flight_state(S, a.scalars + idx, a.ld, a.out + idx, a.old, s, t_rail);
                             store_put(st, s);
-                            track_init(K, s, t_rail);
+                            track_init(K, C, s, t_rail);
                             wind_bracket_reset(WB);
                             if (!(K.t < c_model.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
                             if (a.tape && a.tape_cap > 0) {
@@ -171,7 +184,7 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
                             }
                             if (a.bt_slot) {
                                 const int32_t slot = a.bt_slot[idx];
-                                K.bt_slot = slot; K.bt_next = a.bt_stride;
+                                C.seti(TI_BT_SLOT, slot); C.seti(TI_BT_NEXT, a.bt_stride);
                                 if (slot >= 0) bt_write(a, slot, 0, 0.0, s.x, s.y, s.z);
                             }
                             active = true;
@@ -188,7 +201,7 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
         }
         if (active) {
             bool stepped; int64_t rep = 0;
-            const bool retired = lane_advance(c_model, Tb, alt, S, WB, K, st, a.nan_ff != 0, stepped, rep);
+            const bool retired = lane_advance<Store, CA, MK, WK>(c_model, Tb, alt, S, WB, K, C, st, a.nan_ff != 0, stepped, rep);
             if (stepped) {
                 ++n_steps;
                 if (a.tape && (int64_t)K.n_steps < a.tape_cap) {
@@ -196,23 +209,29 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
                     row[0] = K.t;
                     for (int c = 0; c < 14; ++c) row[1 + c] = st.s(c);
                 }
-                if (a.bt_slot && K.bt_slot >= 0 && K.n_steps == K.bt_next) {       /* every bt_stride-th stored state */
-                    bt_write(a, K.bt_slot, K.n_steps / a.bt_stride, K.t - K.t_rail, st.s(0), st.s(1), st.s(2));
-                    K.bt_next += a.bt_stride;
+                if (a.bt_slot) {                                            /* every bt_stride-th stored state */
+                    const int32_t slot = C.geti(TI_BT_SLOT);
+                    if (slot >= 0 && K.n_steps == C.geti(TI_BT_NEXT)) {
+                        bt_write(a, slot, K.n_steps / a.bt_stride, K.t - K.t_rail, st.s(0), st.s(1), st.s(2));
+                        C.seti(TI_BT_NEXT, K.n_steps + a.bt_stride);
+                    }
                 }
             }
             if (retired) {
                 n_replay += (unsigned long long)rep;
                 State s; store_get(st, s);
-                write_flight_outputs(K, s, a.out + idx, a.iout + idx, a.old);
+                write_flight_outputs(K, C, s, a.out + idx, a.iout + idx, a.old);
                 if (a.tape_n) *a.tape_n = (int64_t)K.n_steps + 1 - rep;
-                if (a.bt_slot && K.bt_slot >= 0) {
-                    /* the last integrated state closes the trajectory (a fast-forwarded NaN tail is not recorded) */
-                    const int32_t last = K.n_steps - (int32_t)rep;
-                    int32_t rows = last / a.bt_stride + 1;
-                    if (rep == 0 && last % a.bt_stride != 0) { bt_write(a, K.bt_slot, rows, K.t - K.t_rail, s.x, s.y, s.z); ++rows; }
-                    a.bt_count[K.bt_slot] = rows;
-                    n_tape += (unsigned long long)(rows < a.bt_max ? rows : a.bt_max);
+                if (a.bt_slot) {
+                    const int32_t slot = C.geti(TI_BT_SLOT);
+                    if (slot >= 0) {
+                        /* the last integrated state closes the trajectory (a fast-forwarded NaN tail is not recorded) */
+                        const int32_t last = K.n_steps - (int32_t)rep;
+                        int32_t rows = last / a.bt_stride + 1;
+                        if (rep == 0 && last % a.bt_stride != 0) { bt_write(a, slot, rows, K.t - K.t_rail, s.x, s.y, s.z); ++rows; }
+                        a.bt_count[slot] = rows;
+                        n_tape += (unsigned long long)(rows < a.bt_max ? rows : a.bt_max);
+                    }
                 }
                 active = false;
             }
@@ -232,20 +251,42 @@ __device__ __forceinline__ void flight_body_impl(const KernelArgs &a, double *al
     }
 }
 
-/* COLD: 0 everything in registers; 1 event bookkeeping / sample constants / brackets in shared memory;
- *       2 additionally the base state and the RK4 accumulator (SharedStore) */
-template <int BLOCK, int COLD>
+/* COLD: 0 everything in registers; 1 bookkeeping / sample constants / brackets in shared memory; 2 additionally the base
+ *       state and the RK4 accumulator (SharedStore); 3 as 2 with the once-per-step half of the bookkeeping in global memory.
+ * MK / WK: the motor kind and the presence of a wind table compiled in (-1: read from the model) */
+template <int BLOCK, int COLD, int MK, int WK>
 __device__ __forceinline__ void flight_body(const KernelArgs &a)
 {
-    if (COLD == 2) flight_body_impl<BLOCK, 1, SharedStore<BLOCK>>(a, emc_dyn + 28 * BLOCK);
-    else flight_body_impl<BLOCK, (COLD != 0), RegStore>(a, emc_dyn);
+    __shared__ DevTables Tb;
+    if constexpr (COLD == 3) {
+        /* dynamic shared memory: [28][BLOCK] state store | BLOCK hot lane records | wind altitude grid (static shared
+         * memory stops at 48 KB) */
+        constexpr int HOT_WORDS = sizeof(Padded<ColdLaneHot>) / 8;
+        Padded<ColdLaneHot> *sh_hot = reinterpret_cast<Padded<ColdLaneHot> *>(emc_dyn + 28 * BLOCK);
+        double *alt = emc_dyn + (28 + HOT_WORDS) * BLOCK;
+        stage_tables(Tb, alt, a);
+        Padded<ColdLaneHot> &CL = sh_hot[threadIdx.x];
+        const int64_t gl = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+        const GlobalCold C = { a.gcold_d + gl, a.gcold_i + gl, a.gcold_ld };
+        flight_loop<BLOCK, SharedStore<BLOCK>, GlobalCold, MK, WK>(a, Tb, alt, CL.K, C, CL.S, CL.WB);
+    } else if constexpr (COLD >= 1) {
+        __shared__ Padded<ColdLaneFull> sh_cold[BLOCK];
+        double *alt = (COLD == 2) ? emc_dyn + 28 * BLOCK : emc_dyn;
+        stage_tables(Tb, alt, a);
+        Padded<ColdLaneFull> &CL = sh_cold[threadIdx.x];
+        const ColdStruct C(CL.C);
+        if constexpr (COLD == 2) flight_loop<BLOCK, SharedStore<BLOCK>, ColdStruct, MK, WK>(a, Tb, alt, CL.K, C, CL.S, CL.WB);
+        else flight_loop<BLOCK, RegStore, ColdStruct, MK, WK>(a, Tb, alt, CL.K, C, CL.S, CL.WB);
+    } else {
+        stage_tables(Tb, emc_dyn, a);
+        ColdLaneFull CL;
+        const ColdStruct C(CL.C);
+        flight_loop<BLOCK, RegStore, ColdStruct, MK, WK>(a, Tb, emc_dyn, CL.K, C, CL.S, CL.WB);
+    }
 }
 
-template <int BLOCK, int MINB, int COLD>
-__global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a) { flight_body<BLOCK, COLD>(a); }
-
-/* 14 warps/SM: 64-thread blocks capped at 144 registers (launch bounds alone round down to 128) */
-__global__ void __maxnreg__(144) emc_flight_kernel_r144(KernelArgs a) { flight_body<64, 1>(a); }
+template <int BLOCK, int MINB, int COLD, int MK = -1, int WK = -1>
+__global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a) { flight_body<BLOCK, COLD, MK, WK>(a); }
 
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const double *t, const double *state,
@@ -386,6 +427,7 @@ struct emc_ctx {
     double *d_bt_rows = nullptr; size_t cap_bt_rows = 0;
     int32_t *d_bt_count = nullptr; size_t cap_bt_count = 0;
     int64_t *d_bt_list = nullptr; size_t cap_bt_list = 0;
+    unsigned char *d_gcold = nullptr; size_t cap_gcold = 0;     /* GlobalCold arrays of the 16-warp kernel */
     int64_t bt_n_sel = 0; int32_t bt_stride = 0, bt_max = 0;
     bool bt_armed = false;                    /* a request waits for the next run */
     int64_t bt_have = 0;                      /* n_sel of the tape the last armed run left in d_bt_rows */
@@ -462,7 +504,7 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
         std::lock_guard<std::mutex> lk(g_owner_mu);
         if (ctx->device >= 0 && ctx->device < 64 && g_owner[ctx->device] == ctx) g_owner[ctx->device] = nullptr;
     }
-    cudaFree(ctx->d_out1); cudaFree(ctx->d_iout1); cudaFree(ctx->d_bt_slot); cudaFree(ctx->d_bt_rows); cudaFree(ctx->d_bt_count); cudaFree(ctx->d_bt_list);
+    cudaFree(ctx->d_out1); cudaFree(ctx->d_iout1); cudaFree(ctx->d_bt_slot); cudaFree(ctx->d_bt_rows); cudaFree(ctx->d_bt_count); cudaFree(ctx->d_bt_list); cudaFree(ctx->d_gcold);
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
     cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_summary); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -557,6 +599,17 @@ static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem,
     return launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD>, BLOCK, a, smem, blocks_per_sm_req);
 }
 
+/* the production instances: motor kind and wind-table presence compiled in */
+template <int BLOCK, int MINB, int COLD>
+static cudaError_t launch_flight_cfg(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
+{
+    const bool solid = ctx->dmodel.motor_kind == EMC_MOTOR_SOLID, wind = ctx->dmodel.has_wind != 0;
+    if (solid) return wind ? launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD, 1, 1>, BLOCK, a, smem, blocks_per_sm_req)
+                           : launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD, 1, 0>, BLOCK, a, smem, blocks_per_sm_req);
+    return wind ? launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD, 0, 1>, BLOCK, a, smem, blocks_per_sm_req)
+                : launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD, 0, 0>, BLOCK, a, smem, blocks_per_sm_req);
+}
+
 /* all pointers in `a` are device pointers */
 static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
 {
@@ -601,17 +654,21 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     cudaError_t e;
     const bool cold = o.cold_state_in_smem >= 0;
     const bool store = o.cold_state_in_smem == 0 || o.cold_state_in_smem >= 2;   /* default: base state + RK4 accumulator in shared memory as well */
-    if (bt == 64 && bps == 7) e = launch_kernel(ctx, emc_flight_kernel_r144, 64, a, smem, bps);
-    else if (bt == 64 && bps == 8) e = launch_flight<64, 8, 1>(ctx, a, smem, bps);
-    else if (bt == 96 && bps == 4) e = launch_flight<96, 4, 1>(ctx, a, smem, bps);
-    else if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
-    else if (bt == 256) e = launch_flight<256, 1, 0>(ctx, a, smem, bps);
-    else if (bt == 128 && bps == 3 && store) e = launch_flight<128, 3, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
-    else if (bt == 128 && bps == 4 && store) e = launch_flight<128, 4, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
+    if (bt == 256 && bps == 2) {
+        /* 16 warps per SM: 2 blocks x 256 lanes at 128 registers; the once-per-step bookkeeping lives in global memory */
+        const int64_t lanes = (int64_t)ctx->sm_count * 2048;
+        CK(grow(&ctx->d_gcold, &ctx->cap_gcold, (size_t)lanes * (TC_DCOUNT * sizeof(double) + TI_ICOUNT * sizeof(int32_t))));
+        a.gcold_d = reinterpret_cast<double *>(ctx->d_gcold);
+        a.gcold_i = reinterpret_cast<int32_t *>(ctx->d_gcold + (size_t)lanes * TC_DCOUNT * sizeof(double));
+        a.gcold_ld = lanes;
+        e = launch_flight_cfg<256, 2, 3>(ctx, a, smem + (28 * sizeof(double) + sizeof(Padded<ColdLaneHot>)) * 256, bps);
+    }
+    else if (bt == 128 && bps == 3 && store) e = launch_flight_cfg<128, 3, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
+    else if (bt == 128 && bps == 4 && store) e = launch_flight_cfg<128, 4, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
     else if (bt == 128 && bps == 3) e = cold ? launch_flight<128, 3, 1>(ctx, a, smem, bps) : launch_flight<128, 3, 0>(ctx, a, smem, bps);
-    else if (bt == 128 && bps >= 4) e = cold ? launch_flight<128, 4, 1>(ctx, a, smem, bps) : launch_flight<128, 4, 0>(ctx, a, smem, bps);
-    else if (bt == 128) e = cold ? launch_flight<128, 1, 1>(ctx, a, smem, bps) : launch_flight<128, 1, 0>(ctx, a, smem, bps);
-    else return fail(ctx, EMC_ERR_INVALID, "block_threads must be 64, 96 (with 4 blocks/SM), 128 or 256");
+    else if (bt == 128) e = launch_flight<128, 1, 0>(ctx, a, smem, bps);
+    else if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
+    else return fail(ctx, EMC_ERR_INVALID, "block_threads must be 64, 128 or 256 (with 2 blocks per SM)");
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("flight kernel launch: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->counters.kernel_launches = 2;

@@ -213,6 +213,24 @@ EMC_HD double ll2d(long long b)
 #endif
 }
 
+/* Degree-16 polynomial c[0..16] in x as two interleaved Horner chains (even / odd coefficients).  Estrin's scheme (5
+ * dependent levels instead of 9, +3 multiplications) was measured SLOWER on the B200 (round 2, profiles/): with three
+ * warps per scheduler the kernel follows the FP64-pipe instruction count, not the depth of the chain. */
+EMC_HD double poly16(const double *c, double x)
+{
+    const double x2 = x * x;
+    double pe = c[16], po = c[15];
+    pe = fma(pe, x2, c[14]);  po = fma(po, x2, c[13]);
+    pe = fma(pe, x2, c[12]);  po = fma(po, x2, c[11]);
+    pe = fma(pe, x2, c[10]);  po = fma(po, x2, c[9]);
+    pe = fma(pe, x2, c[8]);   po = fma(po, x2, c[7]);
+    pe = fma(pe, x2, c[6]);   po = fma(po, x2, c[5]);
+    pe = fma(pe, x2, c[4]);   po = fma(po, x2, c[3]);
+    pe = fma(pe, x2, c[2]);   po = fma(po, x2, c[1]);
+    pe = fma(pe, x2, c[0]);
+    return fma(po, x, pe);
+}
+
 /* exp(x) = 2^k * (1 + r + r^2 Q(r)), k = rint(x/ln2), |r| <= ln2/2; Q: degree-10 minimax
  * (tools/fit_minimax.py exp 10, 6e-20).  Straight-line code: the atmosphere calls it once per
  * derivative for every layer (environment.py:42-45,59-62,66-69,90). */
@@ -274,7 +292,8 @@ EMC_HD double fast_atan2(double y, double x)
     double t = num * fast_rcp(den);
     t = (den == 0.0) ? 0.0 : t;                          /* atan2(0, 0) = 0 (0 * rcp(0) is NaN); NaN stays NaN */
     const double u = t * t, u2 = u * u;
-    /* two interleaved Horner chains (even / odd coefficients) for instruction-level parallelism */
+    /* two interleaved Horner chains (even / odd coefficients).  A shorter polynomial for |t| <= 1/4 behind a per-lane
+     * branch was measured slower (round 2): the branch diverges inside warps that hold a tumbling flight. */
     double pe = K_ATAN[18], po = K_ATAN[17];
     pe = fma(pe, u2, K_ATAN[16]);  po = fma(po, u2, K_ATAN[15]);
     pe = fma(pe, u2, K_ATAN[14]);  po = fma(po, u2, K_ATAN[13]);
@@ -312,17 +331,7 @@ EMC_HD void atmosphere(const DevModel &M, double z, int &j_atm, double &T, doubl
     if (EMC_LIKELY(z >= M.tp_lo && z <= M.tp_hi)) {          /* troposphere (environment.py:28-33): T linear, p by the series above */
         T = M.T0 - M.lapse * z;
         inv_RT = fast_rcp(M.R_gas * T);
-        const double zeta = (z - M.tp_zc) * M.tp_inv_zh, z2 = zeta * zeta;
-        double pe = M.tp_c[16], po = M.tp_c[15];
-        pe = fma(pe, z2, M.tp_c[14]);  po = fma(po, z2, M.tp_c[13]);
-        pe = fma(pe, z2, M.tp_c[12]);  po = fma(po, z2, M.tp_c[11]);
-        pe = fma(pe, z2, M.tp_c[10]);  po = fma(po, z2, M.tp_c[9]);
-        pe = fma(pe, z2, M.tp_c[8]);   po = fma(po, z2, M.tp_c[7]);
-        pe = fma(pe, z2, M.tp_c[6]);   po = fma(po, z2, M.tp_c[5]);
-        pe = fma(pe, z2, M.tp_c[4]);   po = fma(po, z2, M.tp_c[3]);
-        pe = fma(pe, z2, M.tp_c[2]);   po = fma(po, z2, M.tp_c[1]);
-        pe = fma(pe, z2, M.tp_c[0]);
-        p = fma(po, zeta, pe);
+        p = poly16(M.tp_c, (z - M.tp_zc) * M.tp_inv_zh);
         return;
     }
     if (M.n_atm > 0) {                          /* upper layers (environment.py:35-103) by segment polynomial */
@@ -338,18 +347,7 @@ EMC_HD void atmosphere(const DevModel &M, double z, int &j_atm, double &T, doubl
             T = py_min(T, M.at_tmax[j]);
             T = py_max(T, M.at_tmin[j]);
             inv_RT = fast_rcp(M.R_gas * T);
-            const double *c = M.at_c[j];
-            const double zeta = (z - M.at_zc[j]) * M.at_izh[j], z2 = zeta * zeta;
-            double pe = c[16], po = c[15];
-            pe = fma(pe, z2, c[14]);  po = fma(po, z2, c[13]);
-            pe = fma(pe, z2, c[12]);  po = fma(po, z2, c[11]);
-            pe = fma(pe, z2, c[10]);  po = fma(po, z2, c[9]);
-            pe = fma(pe, z2, c[8]);   po = fma(po, z2, c[7]);
-            pe = fma(pe, z2, c[6]);   po = fma(po, z2, c[5]);
-            pe = fma(pe, z2, c[4]);   po = fma(po, z2, c[3]);
-            pe = fma(pe, z2, c[2]);   po = fma(po, z2, c[1]);
-            pe = fma(pe, z2, c[0]);
-            p = fma(po, zeta, pe);
+            p = poly16(M.at_c[j], (z - M.at_zc[j]) * M.at_izh[j]);
             return;
         }
     }
@@ -392,6 +390,11 @@ EMC_HD double gravity(const DevModel &M, double z)
     return M.g0 * (r * r);
 }
 
+/* Compile-time knowledge of the run (flight kernel instances): MK = 0 liquid, 1 solid; WK = 0 no wind table, 1 wind
+ * table; -1 = read the flag from the model at run time (test seam, rail / series / debug kernels). */
+template <int MK> EMC_HD bool cfg_solid(const DevModel &M) { return MK < 0 ? (M.motor_kind == EMC_MOTOR_SOLID) : (MK == 1); }
+template <int WK> EMC_HD bool cfg_wind(const DevModel &M) { return WK < 0 ? (M.has_wind != 0) : (WK == 1); }
+
 /* ---------------- wind table (environment.py:267-276 -> three np.interp on one grid) ------------- */
 EMC_HD void wind_bracket_load(const DevModel &M, const double *alt, const double *w, double z, WindBracket &B)
 {
@@ -425,9 +428,10 @@ EMC_HD void wind_bracket_load(const DevModel &M, const double *alt, const double
     }
 }
 
+template <int WK = -1>
 EMC_HD void wind_at(const DevModel &M, const double *alt, const Sample &S, double z, WindBracket &B, double w[3])
 {
-    if (!M.has_wind) { w[0] = w[1] = w[2] = 0.0; return; }
+    if (!cfg_wind<WK>(M)) { w[0] = w[1] = w[2] = 0.0; return; }
     if (!(z >= B.lo && z < B.hi)) wind_bracket_load(M, alt, S.wind, z, B);
     double dz = z - B.x0;
     w[0] = B.s[0] * dz + B.f0[0];
@@ -436,10 +440,11 @@ EMC_HD void wind_at(const DevModel &M, const double *alt, const Sample &S, doubl
 }
 
 /* ---------------- thrust (motor.py:54-76, 152-156), caller has checked pf>0 && t<=burn ---------- */
-EMC_HD double thrust_at(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, double p)
+/* thrust inside the burn window (the caller has established 0 <= t <= burn_time) */
+template <int MK = -1>
+EMC_HD double thrust_core(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, double p)
 {
-    if (t < 0.0 || t > S.burn_time) return 0.0;
-    if (M.motor_kind == EMC_MOTOR_SOLID) {
+    if (cfg_solid<MK>(M)) {
         const int j = brk_find(Tb.th_lo, Tb.th_hi, M.n_thrust + 1, C.j_th, t);
         C.j_th = j;
         const double f = fma(Tb.th_s[j], t - Tb.th_x0[j], Tb.th_f[j]) * S.thrust_a;
@@ -448,11 +453,29 @@ EMC_HD double thrust_at(const DevModel &M, const DevTables &Tb, const Sample &S,
     return S.thrust_a - S.nozzle_area * p;
 }
 
+template <int MK = -1>
+EMC_HD double thrust_at(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, double p)
+{
+    if (t < 0.0 || t > S.burn_time) return 0.0;
+    return thrust_core<MK>(M, Tb, S, C, t, p);
+}
+
+/* t < 0 for a time value (never NaN, never -0): the sign bit, tested off the FP64 pipe */
+EMC_HD bool time_negative(double t)
+{
+#if defined(__CUDA_ARCH__)
+    return __double2hiint(t) < 0;
+#else
+    return t < 0.0;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------------
  * The derivative, simulator.py:295-460.
  *   chute      : sticky parachute flag (self.parachute_deployed), may be latched by any stage (F12)
  *   want_diag  : stage 0 only — export Mach^2, q_inf, |alpha|, stability margin of this state
  * ---------------------------------------------------------------------------------------------- */
+template <int MK = -1, int WK = -1>
 EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
                        WindBracket &WB, double t, const State &s, bool &chute, double &chute_time,
                        State &k, bool want_diag, Diag &dg)
@@ -490,7 +513,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     atmosphere(M, s.z, WB.j_atm, T, inv_RT, p);
     const double rho = p * inv_RT;
     double w[3];
-    wind_at(M, wind_alt, S, s.z, WB, w);
+    wind_at<WK>(M, wind_alt, S, s.z, WB, w);
 
     /* :341-352 */
     const double ux = s.vx - w[0], uy = s.vy - w[1], uz = s.vz - w[2];
@@ -502,7 +525,7 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double qdyn = 0.5 * rho * v2;
 
     /* :359-363 thrust along body x */
-    double fbx = burning ? thrust_at(M, Tb, S, WB, t, p) : 0.0;
+    double fbx = (burning && !time_negative(t)) ? thrust_core<MK>(M, Tb, S, WB, t, p) : 0.0;   /* motor.py:55,153: 0 outside [0, burn_time] */
     double fby = 0.0, fbz = 0.0;
     double mx = 0.0, my = 0.0, mz = 0.0;
 
@@ -590,9 +613,9 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double g = gravity(M, s.z);
     const double fix = r00 * fbx + r01 * fby + r02 * fbz;
     const double fiy = r10 * fbx + r11 * fby + r12 * fbz;
-    const double fiz = r20 * fbx + r21 * fby + r22 * fbz - mass * g;
+    const double fiz = r20 * fbx + r21 * fby + r22 * fbz;
     k.x = s.vx; k.y = s.vy; k.z = s.vz;
-    k.vx = fix * inv_m; k.vy = fiy * inv_m; k.vz = fiz * inv_m;
+    k.vx = fix * inv_m; k.vy = fiy * inv_m; k.vz = fma(fiz, inv_m, -g);      /* (F_z - m g)/m */
 
     /* :431-436  Euler equations with Izz == Iyy (rocket.py:127); Ixx, Iyy > 0 */
     const double inv_Iyy = fast_rcp(Iyy);
@@ -601,13 +624,13 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     k.wy = (Iyy > 0.0) ? (my - (Ixx - Iyy) * s.wz * s.wx) * inv_Iyy : 0.0;
     k.wz = (Iyy > 0.0) ? (mz - (Iyy - Ixx) * s.wx * s.wy) * inv_Iyy : 0.0;
 
-    /* :439  q_dot = 0.5 * q (x) (0,w) - 0.5*(q.q - 1)*q on the unit quaternion, utils.py:114-121 */
-    const double ne = (qw * qw + qx * qx + qy * qy + qz * qz) - 1.0;
-    const double hc = 0.5 * ne;
-    k.q0 = 0.5 * (-qx * s.wx - qy * s.wy - qz * s.wz) - hc * qw;
-    k.q1 = 0.5 * (qw * s.wx + qy * s.wz - qz * s.wy) - hc * qx;
-    k.q2 = 0.5 * (qw * s.wy - qx * s.wz + qz * s.wx) - hc * qy;
-    k.q3 = 0.5 * (qw * s.wz + qx * s.wy - qy * s.wx) - hc * qz;
+    /* :439  q_dot = 0.5 * q (x) (0,w) - 0.5*(q.q - 1)*q, utils.py:114-121.  q was normalised above, so q.q - 1 is a
+     * rounding residue (<= 3e-16): its term is 1e-16 of q_dot and, times dt, 1e-3 ulp of q — dropped (a non-finite q
+     * makes every product below non-finite as well, so the NaN behaviour is the same). */
+    k.q0 = 0.5 * (-qx * s.wx - qy * s.wy - qz * s.wz);
+    k.q1 = 0.5 * (qw * s.wx + qy * s.wz - qz * s.wy);
+    k.q2 = 0.5 * (qw * s.wy - qx * s.wz + qz * s.wx);
+    k.q3 = 0.5 * (qw * s.wz + qx * s.wy - qy * s.wx);
 
     /* :442-450 propellant; the 10 ms taper test pf/|rate| < 0.01 is written as pf < 0.01*|rate|
      * (the two branches are continuous at the boundary) */
@@ -622,68 +645,91 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
 /* ------------------------------------------------------------------------------------------------
  * Flight bookkeeping: everything the loop of simulator.py:216-264 and the summary of :474-494 need
  * ---------------------------------------------------------------------------------------------- */
-struct Track {
+/* HOT part: read or written in every stage / every step — registers or shared memory. */
+struct TrackHot {
     double t, t_rail;
-    double apogee_alt, apogee_t;      /* running np.argmax(altitudes), :488 */
-    double apogee_time_latch, max_coast;  /* :247-257 */
-    double burnout_time, chute_time;
-    double max_mach2, max_q, max_v2, max_om, min_stab, max_stab, max_aoa;
-    int32_t n_steps, apogee_index, first_nan, term;
+    double apogee_alt;                /* running np.argmax(altitudes), :488 */
+    int32_t n_steps, first_nan;
     bool chute, apogee_detected, burnout_found;
     bool finishing;   /* loop ended: one more stage-0 pass exports the last stored state's diagnostics */
-    int32_t replay;   /* NaN fast-forward mode (0 none, 1 all-NaN, 2 altitude-NaN ballistic): t is replayed to max_time */
-    int32_t bt_slot, bt_next;   /* batch tape: row block of this sample (-1: not recorded) and the next stored-state index to record */
+    int8_t replay;    /* NaN fast-forward mode (0 none, 1 all-NaN, 2 altitude-NaN ballistic): t is replayed to max_time */
+    int8_t term;      /* emc_termination */
 };
+/* COLD part: touched once per step at most (running maxima, event times, tape cursor).  The flight kernel may keep it
+ * in global memory, field-major over the resident lanes (coalesced, L2-resident), to fit 16 warps per SM into the
+ * shared memory; everything else keeps it next to the hot part.  Access goes through a small accessor (ColdStruct
+ * here, GlobalCold in emc_engine.cu) with compile-time field indices. */
+enum { TC_APOGEE_T = 0, TC_LATCH, TC_MAX_COAST,         /* :488-490, :247-257 */
+       TC_BURNOUT_TIME, TC_CHUTE_TIME,
+       TC_MAX_MACH2, TC_MAX_Q, TC_MAX_V2, TC_MAX_OM, TC_MIN_STAB, TC_MAX_STAB, TC_MAX_AOA, TC_DCOUNT };
+enum { TI_APOGEE_INDEX = 0, TI_BT_SLOT, TI_BT_NEXT, TI_ICOUNT };   /* BT_*: batch tape row block (-1: not recorded), next stored-state index to record */
+struct TrackCold { double d[TC_DCOUNT]; int32_t i[TI_ICOUNT]; };
+struct ColdStruct {
+    TrackCold &c;
+    EMC_HD explicit ColdStruct(TrackCold &r) : c(r) {}
+    EMC_HD double getd(int f) const { return c.d[f]; }
+    EMC_HD void setd(int f, double v) const { c.d[f] = v; }
+    EMC_HD int32_t geti(int f) const { return c.i[f]; }
+    EMC_HD void seti(int f, int32_t v) const { c.i[f] = v; }
+};
+struct Track { TrackHot h; TrackCold c; };      /* both parts side by side (test seam, register / shared-memory variants) */
 
-EMC_HD void track_init(Track &K, const State &s, double t_rail)
+template <class CA>
+EMC_HD void track_init(TrackHot &K, const CA &C, const State &s, double t_rail)
 {
     K.t = t_rail; K.t_rail = t_rail;
-    K.apogee_alt = s.z; K.apogee_t = t_rail; K.apogee_index = 0;
+    K.apogee_alt = s.z; C.setd(TC_APOGEE_T, t_rail); C.seti(TI_APOGEE_INDEX, 0);
     K.first_nan = (s.z != s.z) ? 0 : -1;
-    K.apogee_time_latch = 0.0; K.max_coast = 0.0;
-    K.burnout_time = 0.0; K.burnout_found = false;
-    K.chute_time = NAN; K.chute = false; K.apogee_detected = false;
+    C.setd(TC_LATCH, 0.0); C.setd(TC_MAX_COAST, 0.0);
+    C.setd(TC_BURNOUT_TIME, 0.0); K.burnout_found = false;
+    C.setd(TC_CHUTE_TIME, NAN); K.chute = false; K.apogee_detected = false;
     K.n_steps = 0; K.term = EMC_TERM_NONE; K.finishing = false; K.replay = 0;
-    K.bt_slot = -1; K.bt_next = 0;
-    K.max_mach2 = -INFINITY; K.max_q = -INFINITY; K.max_v2 = -INFINITY; K.max_om = -INFINITY;
-    K.min_stab = INFINITY; K.max_stab = -INFINITY; K.max_aoa = -INFINITY;
+    C.seti(TI_BT_SLOT, -1); C.seti(TI_BT_NEXT, 0);
+    C.setd(TC_MAX_MACH2, -INFINITY); C.setd(TC_MAX_Q, -INFINITY); C.setd(TC_MAX_V2, -INFINITY); C.setd(TC_MAX_OM, -INFINITY);
+    C.setd(TC_MIN_STAB, INFINITY); C.setd(TC_MAX_STAB, -INFINITY); C.setd(TC_MAX_AOA, -INFINITY);
 }
 
+/* running np.max / np.min of one cold field: NaN propagates and sticks (a NaN maximum fails both tests) */
+template <class CA> EMC_HD void cold_max(const CA &C, int f, double v) { const double m = C.getd(f); if (v > m || v != v) C.setd(f, v); }
+template <class CA> EMC_HD void cold_min(const CA &C, int f, double v) { const double m = C.getd(f); if (v < m || v != v) C.setd(f, v); }
+
 /* diagnostics of a stored state (stage 0 of the next step, or the final extra evaluation) */
-EMC_HD void track_diag(Track &K, const State &s, const Diag &d)
+template <class CA>
+EMC_HD void track_diag(const CA &C, const State &s, const Diag &d)
 {
-    np_max_acc(K.max_mach2, d.mach2);
-    np_max_acc(K.max_q, d.qdyn);
-    np_max_acc(K.max_v2, s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);
+    cold_max(C, TC_MAX_MACH2, d.mach2);
+    cold_max(C, TC_MAX_Q, d.qdyn);
+    cold_max(C, TC_MAX_V2, s.vx * s.vx + s.vy * s.vy + s.vz * s.vz);
     double om = fabs(s.wx);
     np_max_acc(om, fabs(s.wy));
     np_max_acc(om, fabs(s.wz));
-    np_max_acc(K.max_om, om);
-    np_min_acc(K.min_stab, d.stab);
-    np_max_acc(K.max_stab, d.stab);
-    np_max_acc(K.max_aoa, d.abs_aoa);
+    cold_max(C, TC_MAX_OM, om);
+    cold_min(C, TC_MIN_STAB, d.stab);
+    cold_max(C, TC_MAX_STAB, d.stab);
+    cold_max(C, TC_MAX_AOA, d.abs_aoa);
 }
 
 /* After an accepted step: t already advanced, s is the new stored state (:229-264).
  * Returns true when the loop of :216 ends (break or guard). */
-EMC_HD bool track_post_step(const DevModel &M, const Sample &S, Track &K, const State &s)
+template <class CA>
+EMC_HD bool track_post_step(const DevModel &M, const Sample &S, TrackHot &K, const CA &C, const State &s)
 {
     K.n_steps += 1;
     const double z = s.z, vz = s.vz;
     if (!(K.apogee_alt != K.apogee_alt) && ((z != z) || z > K.apogee_alt)) {
-        K.apogee_alt = z; K.apogee_index = K.n_steps; K.apogee_t = K.t;
+        K.apogee_alt = z; C.seti(TI_APOGEE_INDEX, K.n_steps); C.setd(TC_APOGEE_T, K.t);
     }
     if (K.first_nan < 0 && (z != z)) K.first_nan = K.n_steps;
-    if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
+    if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; C.setd(TC_BURNOUT_TIME, K.t - K.t_rail); }
     if (z <= 0.5 && vz <= 0.0) { K.term = EMC_TERM_GROUND; return true; }
     if (z > 100000.0) { K.term = EMC_TERM_ALTITUDE; return true; }
     if (z > 1000.0 && vz < 0.0 && !K.apogee_detected) {
         K.apogee_detected = true;
-        K.apogee_time_latch = K.t;
-        K.max_coast = (z > 50000.0) ? 60.0 : ((z > 25000.0) ? 120.0 : 300.0);
+        C.setd(TC_LATCH, K.t);
+        C.setd(TC_MAX_COAST, (z > 50000.0) ? 60.0 : ((z > 25000.0) ? 120.0 : 300.0));
     }
     if (K.apogee_detected && z > 25000.0) {
-        if (K.t - K.apogee_time_latch > K.max_coast) { K.term = EMC_TERM_COAST; return true; }
+        if (K.t - C.getd(TC_LATCH) > C.getd(TC_MAX_COAST)) { K.term = EMC_TERM_COAST; return true; }
     }
     if (!(K.t < M.max_time)) { K.term = EMC_TERM_MAX_TIME; return true; }
     return false;
@@ -725,9 +771,9 @@ EMC_HD void store_get(const Store &st, State &s)
  * same quantities at the same state).  A lane whose loop has ended (K.finishing) runs stage 0 only,
  * for the diagnostics of its last stored state, with the sticky flag protected: the reference never
  * evaluates the derivative there.  Returns true if a full step was taken. */
-template <class Store>
+template <class Store, class CA, int MK = -1, int WK = -1>
 EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
-                     WindBracket &WB, Track &K, Store &st)
+                     WindBracket &WB, TrackHot &K, const CA &C, Store &st)
 {
     State ys, k;
     double *y = reinterpret_cast<double *>(&ys);
@@ -739,15 +785,15 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
     /* the sticky parachute flag (F12) is carried in registers through the four stages and written back once */
     const bool chute_keep = K.chute;
     bool chute = chute_keep;
-    double chute_time = K.chute_time;
+    double chute_time = 0.0;                        /* only read back when a stage of THIS step latches the flag */
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int stage = 0; stage < 4; ++stage) {
         const double ts = K.t + ((stage == 0) ? 0.0 : ((stage == 3) ? M.dt : M.half_dt));   /* warp-uniform offset */
-        derivative(M, Tb, wind_alt, S, WB, ts, ys, chute, chute_time, k, stage == 0, dg);
+        derivative<MK, WK>(M, Tb, wind_alt, S, WB, ts, ys, chute, chute_time, k, stage == 0, dg);
         if (stage == 0) {
-            track_diag(K, ys, dg);                      /* ys == s at stage 0 */
+            track_diag(C, ys, dg);                      /* ys == s at stage 0 */
             if (fin) return false;                      /* diagnostic pass only: a latch by this evaluation is dropped */
         }
         if (stage < 3) {
@@ -781,7 +827,7 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
     const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
     if (n2 > 1e-24) { const double rn = fast_rsqrt(n2); st.set_s(6, q0 * rn); st.set_s(7, q1 * rn); st.set_s(8, q2 * rn); st.set_s(9, q3 * rn); }
     else { st.set_s(6, 1.0); st.set_s(7, 0.0); st.set_s(8, 0.0); st.set_s(9, 0.0); }
-    if (chute != chute_keep) { K.chute = true; K.chute_time = chute_time; }
+    if (chute != chute_keep) { K.chute = true; C.setd(TC_CHUTE_TIME, chute_time); }
     K.t += M.dt;
     return true;
 }
@@ -802,7 +848,7 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
  * category parity). */
 EMC_HD bool finite_d(double v) { return fabs(v) <= 1.7976931348623157e308; }
 
-EMC_HD int nan_mode(const DevModel &M, const Sample &S, const Track &K, const State &s)
+EMC_HD int nan_mode(const DevModel &M, const Sample &S, const TrackHot &K, const State &s)
 {
     if (!((s.z != s.z) && (s.vz != s.vz))) return 0;
     if (!(K.t + 2.0 * M.dt < M.max_time)) return 0;          /* too close to the guard: just integrate */
@@ -817,12 +863,13 @@ EMC_HD int nan_mode(const DevModel &M, const Sample &S, const Track &K, const St
 }
 
 /* Plain replay of `t += dt` (:229) with the burnout-index test of :479-480 (reads only the time). */
-EMC_HD int64_t replay_time_loop(const DevModel &M, const Sample &S, Track &K, int64_t max_iter)
+template <class CA>
+EMC_HD int64_t replay_time_loop(const DevModel &M, const Sample &S, TrackHot &K, const CA &C, int64_t max_iter)
 {
     int64_t n = 0;
     while (K.t < M.max_time && n < max_iter) {
         K.t += M.dt; K.n_steps += 1; ++n;
-        if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; K.burnout_time = K.t - K.t_rail; }
+        if (!K.burnout_found && (K.t - K.t_rail) > S.burn_time) { K.burnout_found = true; C.setd(TC_BURNOUT_TIME, K.t - K.t_rail); }
     }
     return n;
 }
@@ -854,7 +901,8 @@ EMC_HD int exponent_d(double v)    /* floor(log2(v)) for normal positive v */
  * binade edge is taken as a real floating-point addition.  Mode 2 also advances x, y by
  * n * (dt/6 * acc): 1e-16-level difference to the step-by-step sum, far inside the parity bar.
  */
-EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K, State &s)
+template <class CA>
+EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, TrackHot &K, const CA &C, State &s)
 {
     int64_t n = 0;
     const double t_begin = K.t;
@@ -886,7 +934,7 @@ EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K, State &
         }
         if (seg < 1) {            /* binade crossing, tie, or degenerate operands: one real step */
             if (!(t1 > t)) { break; }                         /* dt no longer advances t (reference would spin) */
-            n += replay_time_loop(M, S, K, 1);
+            n += replay_time_loop(M, S, K, C, 1);
             continue;
         }
         if (!K.burnout_found && (S.burn_time == S.burn_time)) {
@@ -895,7 +943,7 @@ EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K, State &
             long long j = (est < 1.0) ? 1 : ((est > (double)seg) ? seg : (long long)est);
             while (j > 1 && ((t + (double)(j - 1) * d) - K.t_rail) > S.burn_time) --j;
             while (j <= seg && !(((t + (double)j * d) - K.t_rail) > S.burn_time)) ++j;
-            if (j <= seg) { K.burnout_found = true; K.burnout_time = (t + (double)j * d) - K.t_rail; }
+            if (j <= seg) { K.burnout_found = true; C.setd(TC_BURNOUT_TIME, (t + (double)j * d) - K.t_rail); }
         }
         K.t = t + (double)seg * d;                            /* exact */
         K.n_steps += (int32_t)seg;
@@ -915,47 +963,48 @@ EMC_HD int64_t replay_time(const DevModel &M, const Sample &S, Track &K, State &
 /* One scheduling quantum of a lane, shared by the flight kernel and the test seam: a full RK4 step
  * plus the event logic, or the closing diagnostics pass.  Returns true when the lane retires (its
  * outputs are final).  `stepped` reports whether a stored state was produced (tape). */
-template <class Store>
+template <class Store, class CA, int MK = -1, int WK = -1>
 EMC_HD bool lane_advance(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
-                         WindBracket &WB, Track &K, Store &st, bool nan_ff, bool &stepped, int64_t &replayed)
+                         WindBracket &WB, TrackHot &K, const CA &C, Store &st, bool nan_ff, bool &stepped, int64_t &replayed)
 {
-    stepped = rk4_step(M, Tb, wind_alt, S, WB, K, st);
+    stepped = rk4_step<Store, CA, MK, WK>(M, Tb, wind_alt, S, WB, K, C, st);
     if (!stepped) {                       /* closing pass done */
         if (K.replay) {
             State s; store_get(st, s);
-            replayed += replay_time(M, S, K, s);
+            replayed += replay_time(M, S, K, C, s);
             st.set_s(0, s.x); st.set_s(1, s.y);
         }
         return true;
     }
     State s; store_get(st, s);
-    bool done = track_post_step(M, S, K, s);
-    if (!done && nan_ff) { K.replay = nan_mode(M, S, K, s); done = (K.replay != 0); }
+    bool done = track_post_step(M, S, K, C, s);
+    if (!done && nan_ff) { K.replay = (int8_t)nan_mode(M, S, K, s); done = (K.replay != 0); }
     K.finishing = done;
     return false;
 }
 
 /* write the flight part of the summary (strided SoA column) */
-EMC_HD void write_flight_outputs(const Track &K, const State &s, double *out, int32_t *iout, int64_t ld)
+template <class CA>
+EMC_HD void write_flight_outputs(const TrackHot &K, const CA &C, const State &s, double *out, int32_t *iout, int64_t ld)
 {
     out[EMC_OUT_APOGEE_ALTITUDE * ld] = K.apogee_alt;
-    out[EMC_OUT_APOGEE_TIME * ld] = K.apogee_t - K.t_rail;
+    out[EMC_OUT_APOGEE_TIME * ld] = C.getd(TC_APOGEE_T) - K.t_rail;
     out[EMC_OUT_RANGE * ld] = sqrt(s.x * s.x + s.y * s.y);
     out[EMC_OUT_FLIGHT_TIME * ld] = K.t - K.t_rail;
     out[EMC_OUT_FINAL_X * ld] = s.x; out[EMC_OUT_FINAL_Y * ld] = s.y; out[EMC_OUT_FINAL_Z * ld] = s.z;
     out[EMC_OUT_FINAL_VX * ld] = s.vx; out[EMC_OUT_FINAL_VY * ld] = s.vy; out[EMC_OUT_FINAL_VZ * ld] = s.vz;
-    out[EMC_OUT_MAX_MACH * ld] = sqrt(K.max_mach2);
-    out[EMC_OUT_MAX_Q * ld] = K.max_q;
-    out[EMC_OUT_MAX_SPEED * ld] = sqrt(K.max_v2);
-    out[EMC_OUT_MAX_ABS_OMEGA * ld] = K.max_om;
-    out[EMC_OUT_MIN_STABILITY * ld] = K.min_stab;
-    out[EMC_OUT_MAX_STABILITY * ld] = K.max_stab;
-    out[EMC_OUT_MAX_ABS_AOA * ld] = K.max_aoa;
-    out[EMC_OUT_BURNOUT_TIME * ld] = K.burnout_time;
-    out[EMC_OUT_CHUTE_TIME * ld] = K.chute_time;
+    out[EMC_OUT_MAX_MACH * ld] = sqrt(C.getd(TC_MAX_MACH2));
+    out[EMC_OUT_MAX_Q * ld] = C.getd(TC_MAX_Q);
+    out[EMC_OUT_MAX_SPEED * ld] = sqrt(C.getd(TC_MAX_V2));
+    out[EMC_OUT_MAX_ABS_OMEGA * ld] = C.getd(TC_MAX_OM);
+    out[EMC_OUT_MIN_STABILITY * ld] = C.getd(TC_MIN_STAB);
+    out[EMC_OUT_MAX_STABILITY * ld] = C.getd(TC_MAX_STAB);
+    out[EMC_OUT_MAX_ABS_AOA * ld] = C.getd(TC_MAX_AOA);
+    out[EMC_OUT_BURNOUT_TIME * ld] = C.getd(TC_BURNOUT_TIME);
+    out[EMC_OUT_CHUTE_TIME * ld] = C.getd(TC_CHUTE_TIME);
     iout[EMC_IOUT_N_STEPS * ld] = K.n_steps;
     iout[EMC_IOUT_TERMINATION * ld] = K.term;
-    iout[EMC_IOUT_APOGEE_INDEX * ld] = K.apogee_index;
+    iout[EMC_IOUT_APOGEE_INDEX * ld] = C.geti(TI_APOGEE_INDEX);
     iout[EMC_IOUT_FIRST_NAN_STEP * ld] = K.first_nan;
 }
 

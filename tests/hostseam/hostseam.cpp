@@ -51,7 +51,8 @@ int hs_batch(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outp
         iout[EMC_IOUT_RAIL_STEPS * o->ld] = rail_phase(D, T, m->wind_altitudes, S, col, in->ld, out, o->ld);
         State s; double t_rail;
         load_flight_state(S, col, in->ld, out, o->ld, s, t_rail);
-        Track K; track_init(K, s, t_rail);
+        Track TK; TrackHot &K = TK.h; const ColdStruct C(TK.c);
+        track_init(K, C, s, t_rail);
         RegStore st; store_put(st, s);
         WindBracket WB; wind_bracket_reset(WB);
         int64_t ns = 1, replayed = 0;
@@ -59,7 +60,7 @@ int hs_batch(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outp
         if (!(K.t < D.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
         for (;;) {
             bool stepped;
-            bool retired = lane_advance(D, T, m->wind_altitudes, S, WB, K, st, nan_fast_forward != 0, stepped, replayed);
+            bool retired = lane_advance(D, T, m->wind_altitudes, S, WB, K, C, st, nan_fast_forward != 0, stepped, replayed);
             store_get(st, s);
             if (stepped) {
                 if (tape && ns < tape_cap) { tape[ns * EMC_TAPE_WIDTH] = K.t; memcpy(tape + ns * EMC_TAPE_WIDTH + 1, &s, sizeof s); }
@@ -67,7 +68,7 @@ int hs_batch(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outp
             }
             if (retired) break;
         }
-        write_flight_outputs(K, s, out, iout, o->ld);
+        write_flight_outputs(K, C, s, out, iout, o->ld);
         if (n_states) *n_states = ns;
     }
     return 0;
@@ -82,10 +83,11 @@ int hs_replay(double t0, double t_rail, double dt, double max_time, double burn_
     D.dt = dt; D.max_time = max_time; D.dt_over_6 = dt / 6.0;
     Sample S; memset(&S, 0, sizeof S); S.burn_time = burn_time;
     State s; memset(&s, 0, sizeof s);
-    Track K; track_init(K, s, t_rail);
+    Track TK; TrackHot &K = TK.h; const ColdStruct C(TK.c);
+    track_init(K, C, s, t_rail);
     K.t = t0; K.replay = 1;
-    int64_t n = closed_form ? replay_time(D, S, K, s) : replay_time_loop(D, S, K, (int64_t)1 << 40);
-    out[0] = (double)n; out[1] = K.t; out[2] = K.burnout_time; out[3] = K.burnout_found ? 1.0 : 0.0; out[4] = (double)K.n_steps;
+    int64_t n = closed_form ? replay_time(D, S, K, C, s) : replay_time_loop(D, S, K, C, (int64_t)1 << 40);
+    out[0] = (double)n; out[1] = K.t; out[2] = C.getd(TC_BURNOUT_TIME); out[3] = K.burnout_found ? 1.0 : 0.0; out[4] = (double)K.n_steps;
     return 0;
 }
 

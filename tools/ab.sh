@@ -1,6 +1,5 @@
 #!/bin/bash
-# developer tool (GPU box): headline numbers of the current build: C3 100k, C3 1M, planar 100k
-for args in "--samples-per-gpu 100000" "--samples-per-gpu 1000000" "--workload planar --samples-per-gpu 100000"; do
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras $args "$@" 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print(d['config']['workload'][:12], d['config']['samples_per_gpu'], 'traj/s', round(d['value']), 'Gsteps/s', round(d['rk4_steps_per_s']/1e9,3))"
-done
+# developer tool (GPU box): compare builds of libemc.so placed under variants/ (and the in-tree one)
+# usage: tools/ab.sh [lib.so ...]   (EMC_AB_OPTS='{"blocks_per_sm":4,"block_threads":128}' selects launch options)
+libs="$@"; [ -z "$libs" ] && libs="erpl_monte_carlo_sim_b200/libemc.so $(ls variants/*.so 2>/dev/null)"
+for l in $libs; do EMC_LIB=$PWD/$l python tools/ab_one.py 2>&1 | tail -1; done
