@@ -89,7 +89,8 @@ class EmcOutputs(C.Structure):
 
 class EmcRunOpts(C.Structure):
     _fields_ = [("refill_threshold", C.c_int32), ("block_threads", C.c_int32),
-                ("blocks_per_sm", C.c_int32), ("nan_fast_forward", C.c_int32), ("cold_state_in_smem", C.c_int32)]
+                ("blocks_per_sm", C.c_int32), ("nan_fast_forward", C.c_int32), ("cold_state_in_smem", C.c_int32),
+                ("flags", C.c_int32)]
 
 
 class EmcDispersion(C.Structure):
@@ -108,7 +109,7 @@ class EmcDispersion(C.Structure):
 class EmcCounters(C.Structure):
     _fields_ = [("rk4_steps", C.c_int64), ("replay_steps", C.c_int64), ("rail_steps", C.c_int64),
                 ("refills", C.c_int64), ("kernel_launches", C.c_int64),
-                ("rail_ms", C.c_double), ("flight_ms", C.c_double), ("tape_rows", C.c_int64)]
+                ("rail_ms", C.c_double), ("flight_ms", C.c_double), ("tape_rows", C.c_int64), ("handovers", C.c_int64)]
 
 
 _MODEL_SCALARS = ["center_of_mass_dry", "Ixx_dry", "Iyy_dry", "diameter", "reference_area",

@@ -53,6 +53,7 @@ struct KernelArgs {
     const int32_t *bt_slot; double *bt_rows; int32_t *bt_count; int32_t bt_stride, bt_max;
     /* once-per-step bookkeeping of the 16-warp variant: [TC_DCOUNT][gcold_ld] doubles, [TI_ICOUNT][gcold_ld] ints */
     double *gcold_d; int32_t *gcold_i; int64_t gcold_ld;
+    int32_t sm_count, compact;         /* tail compaction (shared-memory variant): collector choice, on/off */
 };
 
 /* Stage the run-constant tables into shared memory.  The tables are a STATIC __shared__ object and the wind
@@ -128,28 +129,60 @@ __device__ __forceinline__ void bt_write(const KernelArgs &a, int32_t slot, int3
     }
 }
 
+/* base state + RK4 accumulator of this thread's lane record (a column of the [28][BLOCK] block at the start of emc_dyn) */
 template <int BLOCK>
 struct SharedStore {
     __device__ __forceinline__ double s(int i) const { return emc_dyn[i * BLOCK + threadIdx.x]; }
     __device__ __forceinline__ void set_s(int i, double v) { emc_dyn[i * BLOCK + threadIdx.x] = v; }
     __device__ __forceinline__ double acc(int i) const { return emc_dyn[(14 + i) * BLOCK + threadIdx.x]; }
     __device__ __forceinline__ void set_acc(int i, double v) { emc_dyn[(14 + i) * BLOCK + threadIdx.x] = v; }
+    __device__ __forceinline__ void adopt(int src) {                      /* take over another record's column */
+#pragma unroll
+        for (int i = 0; i < 28; ++i) emc_dyn[i * BLOCK + threadIdx.x] = emc_dyn[i * BLOCK + src];
+    }
+};
+struct RegStoreLane : RegStore { __device__ __forceinline__ void adopt(int) {} };
+
+/* Tail compaction (north star: "retired with warp ballot/compaction").  Once the work queue is empty the warps of a
+ * block thin out: a warp that still flies ONE trajectory costs its scheduler as many issue slots as a full one, and an
+ * SM whose 12 warps each hold a straggler runs every one of them at the loaded step latency.  All per-trajectory state
+ * of the shared-memory variants lives in the lane RECORD (hot/cold bookkeeping, sample constants, brackets, state
+ * store column); a thread only holds {active, sample index}.  So a sparse warp can hand its trajectories to the
+ * block's collector warp by posting their record numbers on a board and exit; the collector's idle lanes adopt them.  `reserved` bounds collector lanes in use + posted: a donation is made only if it fits, so a posted
+ * trajectory is adopted at the collector's next iteration.  The arithmetic of a trajectory does not depend on the lane
+ * that integrates it: outputs are bit-identical with and without compaction (tests/).
+ * (First version: records addressed through a slot number, no copy — the indirection cost 7 % of the step latency
+ * everywhere.  Now the adopting lane COPIES the 536 bytes of the record into its own slot, once per hand-over, and the
+ * steady-state code is the plain thread-indexed one.) */
+template <int BLOCK>
+struct CompactBoard {
+    int reserved;                 /* collector lanes active or promised; starts at 32 (closed) until the collector drains */
+    int posted;                   /* slots written to `slots` (reservation cursor) */
+    int ready;                    /* slots whose records are visible (release counter) */
+    int exited;                   /* warps other than the collector that have left the loop */
+    short slots[BLOCK];
 };
 
-/* the persistent loop, generic over where the lane state lives: K/S/WB are references (registers or shared memory),
- * C is the accessor of the cold bookkeeping */
-template <int BLOCK, class Store, class CA, int MK, int WK>
-__device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables &Tb, const double *alt,
-                                            TrackHot &K, const CA &C, Sample &S, WindBracket &WB)
+/* the persistent loop, generic over where the lane records live (REC: registers or shared memory) and the cold accessor */
+template <int BLOCK, class Store, bool COMPACT, int MK, int WK, class LANES>
+__device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables &Tb, const double *alt, LANES lanes,
+                                            CompactBoard<BLOCK> *board)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned FULL = 0xffffffffu;
+    constexpr int NW = BLOCK / 32;
 
     bool active = false, drained = false;
-    int64_t idx = -1;
     Store st;
+    int64_t idx = -1;
     unsigned long long n_steps = 0, n_replay = 0, n_refill = 0, n_tape = 0;
     const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
+    /* compaction roles: blocks that share an SM (ids differ by the SM count) pick collectors on different schedulers */
+    const int warp = threadIdx.x >> 5;
+    const bool compact = COMPACT;
+    const bool collector = compact && (warp == (int)((blockIdx.x / (unsigned)a.sm_count) % NW));
+    bool opened = false;          /* collector: `reserved` switched from "closed" to its own lane count */
+    int taken = 0, last_cnt = 33; /* collector: board entries adopted; donor: active count at the last donation attempt */
 
     for (;;) {
         /* ---- retire/refill: ONE ballot per iteration in the steady state; idle lanes are ranked with
@@ -169,12 +202,16 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                         const int64_t my = (int64_t)base + __popc(idle & ((1u << lane) - 1u));
                         if (my < a.n) {
                             idx = my;
+                            auto &R = lanes.rec(threadIdx.x);
+                            TrackHot &K = R.K; Sample &S = R.S; WindBracket &WB = R.WB;
+                            const auto C = lanes.cold(threadIdx.x);
                             load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
                             double t_rail;
                             State s;
                             load_flight_state(S, a.scalars + idx, a.ld, a.out + idx, a.old, s, t_rail);
                             store_put(st, s);
                             track_init(K, C, s, t_rail);
+                            if (COMPACT) C.seti(TI_SAMPLE, (int32_t)idx);
                             wind_bracket_reset(WB);
                             if (!(K.t < c_model.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
                             if (a.tape && a.tape_cap > 0) {
@@ -194,14 +231,75 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                     act = __ballot_sync(FULL, active);
                 }
             }
+            if (compact && drained) {
+                const int cnt = __popc(act);
+                if (collector) {
+                    if (!opened) {                       /* open the board: from "closed" (32) down to the lanes in use */
+                        if (lane == 0) atomicSub(&board->reserved, 32 - cnt);
+                        opened = true;
+                    } else if (cnt < last_cnt && lane == 0) {
+                        atomicSub(&board->reserved, last_cnt - cnt);        /* own trajectories that retired */
+                    }
+                    int rdy = 0;
+                    if (lane == 0) rdy = *reinterpret_cast<volatile int *>(&board->ready);
+                    rdy = __shfl_sync(FULL, rdy, 0);
+                    int k = rdy - taken;
+                    if (k > 0) {                         /* adopt: the reservation guarantees that the idle lanes suffice */
+                        const unsigned idle = ~act;
+                        const int rank = __popc(idle & ((1u << lane) - 1u));
+                        if (!active && rank < k) {
+                            __threadfence_block();
+                            const int src = board->slots[taken + rank];
+                            lanes.adopt(threadIdx.x, src);       /* record + state-store column into this lane's slot */
+                            st.adopt(src);
+                            idx = lanes.cold(threadIdx.x).geti(TI_SAMPLE);
+                            active = true;
+                            atomicAdd(a.counters + 8, 1ull);
+                        }
+                        taken += k;
+                        act = __ballot_sync(FULL, active);
+                    }
+                    last_cnt = __popc(act);
+                    if (act == 0u) {
+                        /* leave only after every other warp has left and everything it posted has been adopted */
+                        int ex = 0, po = 0;
+                        if (lane == 0) { ex = *reinterpret_cast<volatile int *>(&board->exited); po = *reinterpret_cast<volatile int *>(&board->posted); }
+                        ex = __shfl_sync(FULL, ex, 0); po = __shfl_sync(FULL, po, 0);
+                        if (ex == NW - 1 && po == taken) break;
+                        __nanosleep(256);                /* wait for the other warps without taking their issue slots */
+                        continue;
+                    }
+                } else if (cnt > 0 && cnt <= 16 && cnt < last_cnt) {
+                    /* donor: try once per change of the active count */
+                    last_cnt = cnt;
+                    int ok = 0, pos = 0;
+                    if (lane == 0) {
+                        const int r = atomicAdd(&board->reserved, cnt);
+                        if (r + cnt <= 32) { ok = 1; pos = atomicAdd(&board->posted, cnt); }
+                        else atomicSub(&board->reserved, cnt);
+                    }
+                    ok = __shfl_sync(FULL, ok, 0); pos = __shfl_sync(FULL, pos, 0);
+                    if (ok) {
+                        if (active) board->slots[pos + __popc(act & ((1u << lane) - 1u))] = (short)threadIdx.x;
+                        __threadfence_block();
+                        __syncwarp();
+                        if (lane == 0) atomicAdd(&board->ready, cnt);
+                        active = false;
+                        act = 0u;
+                    }
+                }
+            }
             if (act == 0u) {
                 if (drained) break;
                 continue;
             }
         }
         if (active) {
+            auto &R = lanes.rec(threadIdx.x);
+            TrackHot &K = R.K; Sample &S = R.S; WindBracket &WB = R.WB;
+            const auto C = lanes.cold(threadIdx.x);
             bool stepped; int64_t rep = 0;
-            const bool retired = lane_advance<Store, CA, MK, WK>(c_model, Tb, alt, S, WB, K, C, st, a.nan_ff != 0, stepped, rep);
+            const bool retired = lane_advance<Store, decltype(C), MK, WK>(c_model, Tb, alt, S, WB, K, C, st, a.nan_ff != 0, stepped, rep);
             if (stepped) {
                 ++n_steps;
                 if (a.tape && (int64_t)K.n_steps < a.tape_cap) {
@@ -237,6 +335,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
             }
         }
     }
+    if (compact && !collector && lane == 0) atomicAdd(&board->exited, 1);
     for (int o = 16; o > 0; o >>= 1) {
         n_steps += __shfl_down_sync(FULL, n_steps, o);
         n_replay += __shfl_down_sync(FULL, n_replay, o);
@@ -251,8 +350,35 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
     }
 }
 
+/* where the lane records live */
+template <class REC> struct SmemLanesFull {          /* hot + cold halves side by side in shared memory */
+    REC *recs;
+    __device__ __forceinline__ REC &rec(int slot) const { return recs[slot]; }
+    __device__ __forceinline__ ColdStruct cold(int slot) const { return ColdStruct(recs[slot].C); }
+    __device__ __forceinline__ void adopt(int dst, int src) const {
+        const double *s = reinterpret_cast<const double *>(&recs[src]);
+        double *d = reinterpret_cast<double *>(&recs[dst]);
+#pragma unroll
+        for (int w = 0; w < (int)(sizeof(REC) / 8); ++w) d[w] = s[w];
+    }
+};
+template <class REC> struct SmemLanesHot {           /* hot half in shared memory, cold half in global memory */
+    REC *recs; double *gd; int32_t *gi; int64_t ld;
+    __device__ __forceinline__ REC &rec(int slot) const { return recs[slot]; }
+    __device__ __forceinline__ GlobalCold cold(int slot) const { return GlobalCold{ gd + slot, gi + slot, ld }; }
+    __device__ __forceinline__ void adopt(int, int) const {}
+};
+struct RegLanes {                                    /* everything in this thread's registers */
+    ColdLaneFull *one;
+    __device__ __forceinline__ ColdLaneFull &rec(int) const { return *one; }
+    __device__ __forceinline__ ColdStruct cold(int) const { return ColdStruct(one->C); }
+    __device__ __forceinline__ void adopt(int, int) const {}
+};
+
 /* COLD: 0 everything in registers; 1 bookkeeping / sample constants / brackets in shared memory; 2 additionally the base
- *       state and the RK4 accumulator (SharedStore); 3 as 2 with the once-per-step half of the bookkeeping in global memory.
+ *       state and the RK4 accumulator (SharedStore) — the default; 4 as 2 with the lane records addressed through a slot
+ *       number and tail compaction (EMC_RUN_COMPACTION); 3 as 2 with the once-per-step half of the bookkeeping in global
+ *       memory (16 warps per SM; measured slower, kept selectable).
  * MK / WK: the motor kind and the presence of a wind table compiled in (-1: read from the model) */
 template <int BLOCK, int COLD, int MK, int WK>
 __device__ __forceinline__ void flight_body(const KernelArgs &a)
@@ -262,26 +388,31 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
         /* dynamic shared memory: [28][BLOCK] state store | BLOCK hot lane records | wind altitude grid (static shared
          * memory stops at 48 KB) */
         constexpr int HOT_WORDS = sizeof(Padded<ColdLaneHot>) / 8;
-        Padded<ColdLaneHot> *sh_hot = reinterpret_cast<Padded<ColdLaneHot> *>(emc_dyn + 28 * BLOCK);
         double *alt = emc_dyn + (28 + HOT_WORDS) * BLOCK;
         stage_tables(Tb, alt, a);
-        Padded<ColdLaneHot> &CL = sh_hot[threadIdx.x];
-        const int64_t gl = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-        const GlobalCold C = { a.gcold_d + gl, a.gcold_i + gl, a.gcold_ld };
-        flight_loop<BLOCK, SharedStore<BLOCK>, GlobalCold, MK, WK>(a, Tb, alt, CL.K, C, CL.S, CL.WB);
-    } else if constexpr (COLD >= 1) {
+        const int64_t g0 = (int64_t)blockIdx.x * BLOCK;
+        SmemLanesHot<Padded<ColdLaneHot>> lanes = { reinterpret_cast<Padded<ColdLaneHot> *>(emc_dyn + 28 * BLOCK),
+                                                    a.gcold_d + g0, a.gcold_i + g0, a.gcold_ld };
+        flight_loop<BLOCK, SharedStore<BLOCK>, false, MK, WK>(a, Tb, alt, lanes, (CompactBoard<BLOCK> *)nullptr);
+    } else if constexpr (COLD == 2 || COLD == 4) {
         __shared__ Padded<ColdLaneFull> sh_cold[BLOCK];
-        double *alt = (COLD == 2) ? emc_dyn + 28 * BLOCK : emc_dyn;
-        stage_tables(Tb, alt, a);
-        Padded<ColdLaneFull> &CL = sh_cold[threadIdx.x];
-        const ColdStruct C(CL.C);
-        if constexpr (COLD == 2) flight_loop<BLOCK, SharedStore<BLOCK>, ColdStruct, MK, WK>(a, Tb, alt, CL.K, C, CL.S, CL.WB);
-        else flight_loop<BLOCK, RegStore, ColdStruct, MK, WK>(a, Tb, alt, CL.K, C, CL.S, CL.WB);
+        __shared__ CompactBoard<BLOCK> board;
+        double *alt = emc_dyn + 28 * BLOCK;
+        if (threadIdx.x == 0) { board.reserved = 32; board.posted = 0; board.ready = 0; board.exited = 0; }
+        stage_tables(Tb, alt, a);                    /* ends with __syncthreads() */
+        SmemLanesFull<Padded<ColdLaneFull>> lanes = { sh_cold };
+        if constexpr (COLD == 4) flight_loop<BLOCK, SharedStore<BLOCK>, true, MK, WK>(a, Tb, alt, lanes, &board);
+        else flight_loop<BLOCK, SharedStore<BLOCK>, false, MK, WK>(a, Tb, alt, lanes, &board);
+    } else if constexpr (COLD == 1) {
+        __shared__ Padded<ColdLaneFull> sh_cold[BLOCK];
+        stage_tables(Tb, emc_dyn, a);
+        SmemLanesFull<Padded<ColdLaneFull>> lanes = { sh_cold };
+        flight_loop<BLOCK, RegStoreLane, false, MK, WK>(a, Tb, emc_dyn, lanes, (CompactBoard<BLOCK> *)nullptr);
     } else {
         stage_tables(Tb, emc_dyn, a);
         ColdLaneFull CL;
-        const ColdStruct C(CL.C);
-        flight_loop<BLOCK, RegStore, ColdStruct, MK, WK>(a, Tb, emc_dyn, CL.K, C, CL.S, CL.WB);
+        RegLanes lanes = { &CL };
+        flight_loop<BLOCK, RegStoreLane, false, MK, WK>(a, Tb, emc_dyn, lanes, (CompactBoard<BLOCK> *)nullptr);
     }
 }
 
@@ -567,7 +698,7 @@ static int check_run_args(emc_ctx *ctx, const emc_inputs *in, int64_t n, const e
 {
     if (!ctx || !in || !out) return fail(ctx, EMC_ERR_INVALID, "NULL argument");
     if (!ctx->has_model) return fail(ctx, EMC_ERR_NO_MODEL, "emc_set_model has not been called");
-    if (n < 0) return fail(ctx, EMC_ERR_INVALID, "n < 0");
+    if (n < 0 || n > 0x7fffffffLL) return fail(ctx, EMC_ERR_INVALID, "n must be in [0, 2^31)");
     if (n > 0 && (!in->scalars || !out->out || !out->iout)) return fail(ctx, EMC_ERR_INVALID, "NULL buffer");
     if (in->ld < n || out->ld < n) return fail(ctx, EMC_ERR_INVALID, "leading dimension smaller than n");
     if (ctx->dmodel.has_wind && n > 0 && !in->wind) return fail(ctx, EMC_ERR_INVALID, "model has a wind grid but inputs.wind is NULL");
@@ -613,10 +744,12 @@ static cudaError_t launch_flight_cfg(emc_ctx *ctx, const KernelArgs &a, size_t s
 /* all pointers in `a` are device pointers */
 static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
 {
-    emc_run_opts o = { 0, 0, 0, 1, 0 };
+    emc_run_opts o = { 0, 0, 0, 1, 0, 0 };
     if (opts) o = *opts;
     a.refill_threshold = o.refill_threshold > 0 ? o.refill_threshold : 1;
     a.nan_ff = o.nan_fast_forward;
+    a.sm_count = ctx->sm_count > 0 ? ctx->sm_count : 1;
+    a.compact = (o.flags & EMC_RUN_COMPACTION) ? 1 : 0;
     a.wind_alt = ctx->d_wind_alt;
     a.queue = ctx->d_ctrl; a.counters = ctx->d_ctrl + 1;
     if (a.tape) a.tape_n = reinterpret_cast<int64_t *>(ctx->d_ctrl + 5);
@@ -663,6 +796,7 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
         a.gcold_ld = lanes;
         e = launch_flight_cfg<256, 2, 3>(ctx, a, smem + (28 * sizeof(double) + sizeof(Padded<ColdLaneHot>)) * 256, bps);
     }
+    else if (bt == 128 && bps == 3 && store && a.compact) e = launch_flight_cfg<128, 3, 4>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
     else if (bt == 128 && bps == 3 && store) e = launch_flight_cfg<128, 3, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
     else if (bt == 128 && bps == 4 && store) e = launch_flight_cfg<128, 4, 2>(ctx, a, smem + 28 * 128 * sizeof(double), bps);
     else if (bt == 128 && bps == 3) e = cold ? launch_flight<128, 3, 1>(ctx, a, smem, bps) : launch_flight<128, 3, 0>(ctx, a, smem, bps);
@@ -685,6 +819,7 @@ static int finish_counters(emc_ctx *ctx)
     ctx->counters.rail_steps = (int64_t)h[3];
     ctx->counters.refills = (int64_t)h[4];
     ctx->counters.tape_rows = (int64_t)h[8];
+    ctx->counters.handovers = (int64_t)h[9];
     float ms = 0.f;
     if (ctx->counters.kernel_launches) {
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->counters.rail_ms = ms;
@@ -794,7 +929,7 @@ EMC_EXPORT int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_output
     if (int rc = upload_inputs(ctx, in, 1, a, false)) return rc;
     CK(grow(&ctx->d_tape, &ctx->cap_tape, (size_t)cap * EMC_TAPE_WIDTH));
     a.tape = ctx->d_tape; a.tape_cap = cap;
-    emc_run_opts o = { 1, 64, 1, 0, 0 };    /* every state is integrated: no fast-forward on the tape path */
+    emc_run_opts o = { 1, 64, 1, 0, 0, 0 };    /* every state is integrated: no fast-forward on the tape path */
     if (int rc = run_device(ctx, a, &o)) return rc;
     if (int rc = download_outputs(ctx, out, 1, ctx->d_out1, ctx->d_iout1)) return rc;
     if (int rc = finish_counters(ctx)) return rc;

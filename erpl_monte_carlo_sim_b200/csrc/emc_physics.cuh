@@ -662,7 +662,7 @@ struct TrackHot {
 enum { TC_APOGEE_T = 0, TC_LATCH, TC_MAX_COAST,         /* :488-490, :247-257 */
        TC_BURNOUT_TIME, TC_CHUTE_TIME,
        TC_MAX_MACH2, TC_MAX_Q, TC_MAX_V2, TC_MAX_OM, TC_MIN_STAB, TC_MAX_STAB, TC_MAX_AOA, TC_DCOUNT };
-enum { TI_APOGEE_INDEX = 0, TI_BT_SLOT, TI_BT_NEXT, TI_ICOUNT };   /* BT_*: batch tape row block (-1: not recorded), next stored-state index to record */
+enum { TI_APOGEE_INDEX = 0, TI_BT_SLOT, TI_BT_NEXT, TI_SAMPLE, TI_ICOUNT };   /* BT_*: batch tape row block (-1: not recorded), next stored-state index to record; SAMPLE: index of the sample this record flies */
 struct TrackCold { double d[TC_DCOUNT]; int32_t i[TI_ICOUNT]; };
 struct ColdStruct {
     TrackCold &c;

@@ -100,6 +100,49 @@ class SampleDict(dict):
         return self[key] if key in self else default
 
 
+class LazyAnalysis(dict):
+    """The analysis dict of run_monte_carlo.  `parameter_ranges_observed` (monte_carlo.py:425-441) needs the parameter
+    dict of every valid sample; it is computed on first access (a 1e7-sample run does not fetch 1e7 x 17 draws unless
+    somebody asks).  In a multi-rank job it is computed eagerly, because it takes a collective."""
+
+    def __init__(self, data, lazy):
+        super().__init__(data)
+        self._lazy = dict(lazy)
+
+    def __missing__(self, key):
+        if key in self._lazy:
+            self[key] = v = self._lazy.pop(key)()
+            return v
+        raise KeyError(key)
+
+    def __contains__(self, key):
+        return dict.__contains__(self, key) or key in self._lazy
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def materialize(self):
+        for key in list(self._lazy):
+            self[key]
+        return self
+
+    # anything that enumerates the dict sees every key of the reference's analysis
+    def __iter__(self):
+        return dict.__iter__(self.materialize())
+
+    def __len__(self):
+        return dict.__len__(self.materialize())
+
+    def keys(self):
+        return dict.keys(self.materialize())
+
+    def items(self):
+        return dict.items(self.materialize())
+
+    def values(self):
+        return dict.values(self.materialize())
+
+
 class SampleResults(Sequence):
     """`analysis['results']` / `analysis['outliers']`: one dict per sample, built on access from the
     engine's SoA summary (the reference materialises every time series of every sample in a list)."""
@@ -430,10 +473,11 @@ class MonteCarloAnalyzer:
         return d, (shear, base, rho, innov)
 
     def philox_parameters(self, n, first_index=0) -> DispersionSet:
-        """The parameter samples the device generator draws for indices first_index.. (from the same Philox bits)."""
-        from . import philox
+        """The parameter samples the device generator draws for indices first_index.. — the draws themselves are fetched
+        from the GPU (emc_philox_draws); philox.py holds the host mirror of the same bits (tests/test_philox.py)."""
         idx = np.arange(first_index, first_index + n, dtype=np.uint64)
-        return self._parameters_from_draws(philox.normals(self.philox_seed, idx, 15), philox.uniforms(self.philox_seed, idx), idx)
+        g, u = get_engine(self._dev()).philox_draws(self.philox_seed, first_index, n, 15)
+        return self._parameters_from_draws(g, u, idx)
 
     def numpy_device_parameters(self, n, first_seed=0) -> DispersionSet:
         """draw_parameters() from the MT19937 streams the device regenerates (no per-sample host loop)."""
@@ -772,35 +816,40 @@ class MonteCarloAnalyzer:
         ap, rg, ft = run.out[O["apogee_altitude"]], run.out[O["range"]], run.out[O["flight_time"]]
         bad = self.outlier_mask(ap, rg, ft)                       # per-sample membership for the lazy result lists
         valid_ids, out_ids = np.flatnonzero(~bad), np.flatnonzero(bad)
-        d = run.disp
-        keys, lo, hi = [], [], []
-        for key, arr in (("initial_position_offset", d.pos), ("initial_velocity_offset", d.vel),
-                         ("initial_attitude_offset", d.att), ("initial_angular_velocity_offset", d.omega),
-                         ("mass_multiplier", d.mass_multiplier), ("thrust_multiplier", d.thrust_multiplier),
-                         ("wind_speed", d.wind_speed), ("wind_direction", d.wind_direction),
-                         ("density_multiplier", d.density_multiplier), ("random_seed", d.seed.astype(float))):
-            sel = arr[valid_ids].reshape(valid_ids.size, -1)
-            keys.append((key, arr.ndim > 1, sel.shape[1]))
-            lo.append(sel.min(axis=0) if valid_ids.size else np.full(sel.shape[1], np.inf))
-            hi.append(sel.max(axis=0) if valid_ids.size else np.full(sel.shape[1], -np.inf))
-        lo, hi = np.concatenate(lo), np.concatenate(hi)
-        if world > 1:
-            lo, hi = stats.allreduce_minmax(eng, lo, hi)
-        ranges, k = {}, 0
-        for key, is_vec, width in keys:
-            a, b = lo[k:k + width], hi[k:k + width]
-            ranges[key] = {"min": a.tolist(), "max": b.tolist()} if is_vec else {"min": float(a[0]), "max": float(b[0])}
-            k += width
+        def observed_ranges():
+            d = run.disp
+            keys, lo, hi = [], [], []
+            for key, arr in (("initial_position_offset", d.pos), ("initial_velocity_offset", d.vel),
+                             ("initial_attitude_offset", d.att), ("initial_angular_velocity_offset", d.omega),
+                             ("mass_multiplier", d.mass_multiplier), ("thrust_multiplier", d.thrust_multiplier),
+                             ("wind_speed", d.wind_speed), ("wind_direction", d.wind_direction),
+                             ("density_multiplier", d.density_multiplier), ("random_seed", d.seed.astype(float))):
+                sel = arr[valid_ids].reshape(valid_ids.size, -1)
+                keys.append((key, arr.ndim > 1, sel.shape[1]))
+                lo.append(sel.min(axis=0) if valid_ids.size else np.full(sel.shape[1], np.inf))
+                hi.append(sel.max(axis=0) if valid_ids.size else np.full(sel.shape[1], -np.inf))
+            lo, hi = np.concatenate(lo), np.concatenate(hi)
+            if world > 1:
+                lo, hi = stats.allreduce_minmax(eng, lo, hi)
+            ranges, k = {}, 0
+            for key, is_vec, width in keys:
+                a, b = lo[k:k + width], hi[k:k + width]
+                ranges[key] = {"min": a.tolist(), "max": b.tolist()} if is_vec else {"min": float(a[0]), "max": float(b[0])}
+                k += width
+            return ranges
+
         analysis = {"n_samples": st["n_samples"], "n_failed": 0, "n_outliers": st["n_outliers"],
                     "apogee_altitude": st["apogee_altitude"], "range": st["range"], "flight_time": st["flight_time"],
                     "results": SampleResults(run, valid_ids), "outliers": SampleResults(run, out_ids, with_reasons=True),
-                    "parameter_ranges_observed": ranges,
                     # engine extras (not in the reference's dict): device-reduced landing ellipse, reasons, histograms
                     "landing_ellipse": st["landing_ellipse"], "outlier_reason_counts": st["outlier_reasons"]}
         if world > 1:
             analysis["shard"] = {"rank": rank, "world_size": world, "first_sample": run.first_id, "n_local": run.n}
         if "histograms" in st:
             analysis["histograms"] = st["histograms"]
+        analysis = LazyAnalysis(analysis, {"parameter_ranges_observed": observed_ranges})
+        if world > 1:
+            analysis.materialize()                  # the min/max reduction is a collective: every rank takes part now
         return analysis
 
     # ------------------------------------------------------------------------------------------

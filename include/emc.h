@@ -166,7 +166,12 @@ typedef struct emc_run_opts {
     int32_t blocks_per_sm;    /* 0 = default (3 when block_threads is 0, else the occupancy limit) */
     int32_t nan_fast_forward; /* 1 (default when opts==NULL): replay t += dt only once the altitude is NaN for good */
     int32_t cold_state_in_smem; /* 0 (default) or 2: per-lane bookkeeping, base state and RK4 accumulator live in shared memory; 1: bookkeeping only; -1: registers */
+    int32_t flags;            /* ABI 2: EMC_RUN_* bits */
 } emc_run_opts;
+#define EMC_RUN_COMPACTION 1      /* tail compaction: once the work queue is empty, sparse warps hand their trajectories (lane records in
+                                     shared memory, addressed by slot) to one collector warp per block and exit.  Bit-identical outputs.
+                                     Off by default: measured on the B200 the slot indirection costs more than the compacted tail
+                                     returns. */
 
 typedef struct emc_ctx emc_ctx;
 
@@ -179,6 +184,7 @@ typedef struct emc_counters {
     int64_t kernel_launches;  /* kernels launched by the call */
     double rail_ms, flight_ms;/* device time of the two kernels (CUDA events on the context stream) */
     int64_t tape_rows;        /* ABI 2: rows stored by an armed batch tape (emc_tape_request) */
+    int64_t handovers;        /* ABI 2: trajectories handed to a collector warp by the tail compaction (EMC_RUN_COMPACTION) */
 } emc_counters;
 
 int emc_abi_version(void);

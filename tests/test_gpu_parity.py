@@ -100,6 +100,34 @@ def test_gpu_scheduling_invariance(engine):
     assert engine.counters()["replay_steps"] == 0
 
 
+def test_gpu_tail_compaction_is_invisible(engine):
+    """Once the work queue is empty, sparse warps hand their trajectories (lane records in shared memory) to one collector
+    warp per block.  A batch of a few thousand flights of very different lengths (some NaN runs, some one-step flights):
+    outputs with and without compaction are bit-identical, and the tape of a handed-over trajectory is complete."""
+    z = util.golden("mc_liquid_default")
+    engine.set_model(_abi.model_from_npz(z))
+    rep = 40
+    sc = np.ascontiguousarray(np.tile(z["scalars"], (1, rep))); wind = np.ascontiguousarray(np.tile(z["wind"], (rep, 1, 1)))
+    sc[_abi.IN["q2"], ::7] = 0.0; sc[_abi.IN["q0"], ::7] = 1.0                 # horizontal launches: one-step flights in between
+    on = engine.run_batch(sc, wind, opts=_lib.run_opts(compaction=True))
+    assert engine.counters()["handovers"] > 50                                   # the tail really was compacted
+    off = engine.run_batch(sc, wind)
+    assert engine.counters()["handovers"] == 0
+    np.testing.assert_array_equal(on[1], off[1]); np.testing.assert_array_equal(on[0], off[0])
+    n = z["scalars"].shape[1]
+    keep = np.arange(n) % 7 != 0
+    np.testing.assert_array_equal(on[1][:, :n][:, keep], z["iout"][:, keep])
+    longest = np.argsort(on[1][_abi.IOUT["n_steps"]] - np.maximum(on[1][_abi.IOUT["first_nan_step"]], 0))[-6:]
+    engine.tape_request(longest, 50, 1300)
+    engine.run_batch(sc, wind, opts=_lib.run_opts(compaction=True))
+    rows, cnt = engine.tape_fetch()
+    for k, i in enumerate(longest):
+        if on[1][_abi.IOUT["first_nan_step"], i] < 0:
+            ns = int(on[1][_abi.IOUT["n_steps"], i])
+            assert cnt[k] == ns // 50 + 1 + (1 if ns % 50 else 0)
+            assert rows[k, cnt[k] - 1, 0] == on[0][_abi.OUT["flight_time"], i] and rows[k, cnt[k] - 1, 3] == on[0][_abi.OUT["final_z"], i]
+
+
 _synth = util.synth
 
 

@@ -77,3 +77,13 @@ def test_parameter_ranges_reduce_over_two_ranks_gloo():
     assert all(p.exitcode == 0 for p in ps)
     for r in range(2):
         assert ret[r] == ([0.5, -3.0, 4.0], [1.0, 2.0, 4.0])      # an empty shard (+inf / -inf) does not disturb the result
+
+
+def test_lazy_analysis_keys_behave_like_the_reference_dict():
+    from erpl_monte_carlo_sim_b200.monte_carlo import LazyAnalysis
+    calls = []
+    a = LazyAnalysis({"n_samples": 3}, {"parameter_ranges_observed": lambda: (calls.append(1), {"mass_multiplier": {"min": 0.9, "max": 1.1}})[1]})
+    assert "parameter_ranges_observed" in a and calls == []                    # promised, not computed
+    assert a.get("nope", 7) == 7 and calls == []
+    assert set(a) == {"n_samples", "parameter_ranges_observed"} and calls == [1]   # enumeration materialises it, once
+    assert a["parameter_ranges_observed"]["mass_multiplier"]["max"] == 1.1 and len(a) == 2 and calls == [1]
