@@ -378,10 +378,11 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     barrier()
     t0 = time.perf_counter()
-    flight_ms = rail_ms = 0.0; rk4 = replay = 0
+    flight_ms = rail_ms = strict_ms = 0.0; rk4 = replay = strict_steps = parked = 0
     for _ in range(a.steps):
         c = step_resident()
         flight_ms += c["flight_ms"]; rail_ms += c["rail_ms"]; rk4 += c["rk4_steps"]; replay += c["replay_steps"]
+        strict_ms += c["strict_ms"]; strict_steps += c["strict_steps"]; parked += c["parked"]
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)
@@ -411,12 +412,12 @@ def main():
         json.dumps(e2e_stats[0], sort_keys=True, default=float) == json.dumps(last_stats[0], sort_keys=True, default=float)
 
     per_rank = gather_ranks([flight_ms / a.steps, rail_ms / a.steps], world, dev)
-    tmax = torch.tensor([wall, wall_e2e, flight_ms, rail_ms], dtype=torch.float64, device=dev)
-    tsum = torch.tensor([float(rk4), float(replay)], dtype=torch.float64, device=dev)
+    tmax = torch.tensor([wall, wall_e2e, flight_ms, rail_ms, strict_ms], dtype=torch.float64, device=dev)
+    tsum = torch.tensor([float(rk4), float(replay), float(strict_steps), float(parked)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tsum)
-    wall, wall_e2e, flight_ms, rail_ms = tmax.tolist()
-    rk4_all, replay_all = tsum.tolist()
+    wall, wall_e2e, flight_ms, rail_ms, strict_ms = tmax.tolist()
+    rk4_all, replay_all, strict_all, parked_all = tsum.tolist()
 
     extras = api = None
     if not a.no_extras and a.workload == "c3":
@@ -440,8 +441,11 @@ def main():
                        "launch": {"block_threads": a.block_threads, "blocks_per_sm": a.blocks_per_sm, "refill_threshold": a.refill_threshold, "cold_smem": a.cold_smem}},
             "rk4_steps_per_s": steps_per_s, "mean_rk4_steps_per_trajectory": rk4_all / a.steps / n_total,
             "replayed_steps_per_trajectory": replay_all / a.steps / n_total,
-            "kernel_ms_per_step": {"flight": flight_ms / a.steps, "rail": rail_ms / a.steps,
+            "kernel_ms_per_step": {"flight": flight_ms / a.steps, "rail": rail_ms / a.steps, "strict_continuation": strict_ms / a.steps,
                                    "flight_per_rank": [round(r[0], 3) for r in per_rank]},
+            "strict_continuation": {"parked_trajectories_per_step": parked_all / a.steps, "rk4_steps_per_step": strict_all / a.steps,
+                                    "what": "blown-up flights (|v| > 1e7 m/s or |omega| > 1000 rad/s) are finished by emc_strict_kernel in the "
+                                            "reference's operation order so that step counts / terminations / first-NaN indices are the reference's"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf * world, "unit": "TFLOP/s",
                          "frac": achieved_tf / (peak_tf * world),
                          "traffic": FLIGHT_KERNEL_DRAM_BYTES_100K if (a.workload == "c3" and n == 100_000) else None, "traffic_unit": "bytes/launch (ncu)",
@@ -451,7 +455,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "trajectories/s",
                     "h2d_bytes_per_step": int(blk.nbytes + wind.nbytes), "d2h_bytes_per_step": int(h_out.nbytes + h_iout.nbytes),
                     "what": "emc_run_batch on pinned host buffers (H2D, rail + flight kernels, D2H of every summary) + the device statistics chain"},
-            "gpu_launches": (2 + STATS_LAUNCHES_FUSED) * a.steps * world,
+            "gpu_launches": (3 + STATS_LAUNCHES_FUSED) * a.steps * world,     # rail + flight + strict continuation + the statistics chain
             "clocks": sampler.summary(),
             "statistics": {k: last_stats[0][k] for k in ("n_total", "n_samples", "n_outliers", "apogee_altitude", "range", "flight_time", "landing_ellipse")},
             "e2e_equals_resident": parity_hint,

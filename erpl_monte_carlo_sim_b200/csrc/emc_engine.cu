@@ -28,6 +28,7 @@
 #include <string>
 
 #include "emc_model_build.h"
+#include "emc_strict.cuh"
 #include "emc_stats.cuh"
 #include "emc_philox.cuh"
 
@@ -54,7 +55,12 @@ struct KernelArgs {
     /* once-per-step bookkeeping of the 16-warp variant: [TC_DCOUNT][gcold_ld] doubles, [TI_ICOUNT][gcold_ld] ints */
     double *gcold_d; int32_t *gcold_i; int64_t gcold_ld;
     int32_t sm_count, compact;         /* tail compaction (shared-memory variant): collector choice, on/off */
+    /* strict continuation: trajectories parked by the flight kernel (emc_strict.cuh) */
+    struct ParkRec *park; unsigned long long *park_count; int32_t park_on;
 };
+
+/* everything the strict kernel needs to finish a parked trajectory (its sample index is C.i[TI_SAMPLE]) */
+struct ParkRec { State s; TrackHot K; TrackCold C; };
 
 /* Stage the run-constant tables into shared memory.  The tables are a STATIC __shared__ object and the wind
  * altitude grid the only dynamic part: objects addressed as shared arrays are read with plain LDS offsets, whereas
@@ -211,7 +217,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                             load_flight_state(S, a.scalars + idx, a.ld, a.out + idx, a.old, s, t_rail);
                             store_put(st, s);
                             track_init(K, C, s, t_rail);
-                            if (COMPACT) C.seti(TI_SAMPLE, (int32_t)idx);
+                            C.seti(TI_SAMPLE, (int32_t)idx);
                             wind_bracket_reset(WB);
                             if (!(K.t < c_model.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
                             if (a.tape && a.tape_cap > 0) {
@@ -299,7 +305,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
             TrackHot &K = R.K; Sample &S = R.S; WindBracket &WB = R.WB;
             const auto C = lanes.cold(threadIdx.x);
             bool stepped; int64_t rep = 0;
-            const bool retired = lane_advance<Store, decltype(C), MK, WK>(c_model, Tb, alt, S, WB, K, C, st, a.nan_ff != 0, stepped, rep);
+            const bool retired = lane_advance<Store, decltype(C), MK, WK>(c_model, Tb, alt, S, WB, K, C, st, a.nan_ff != 0, stepped, rep, a.park_on != 0);
             if (stepped) {
                 ++n_steps;
                 if (a.tape && (int64_t)K.n_steps < a.tape_cap) {
@@ -315,7 +321,17 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                     }
                 }
             }
-            if (retired) {
+            if (retired && K.replay == EMC_REPLAY_PARK) {
+                /* blow-up under way: hand the trajectory to the strict continuation (emc_strict_kernel) */
+                ParkRec &P = a.park[atomicAdd(a.park_count, 1ull)];
+                store_get(st, P.s);
+                K.replay = 0;
+                P.K = K;
+                for (int f = 0; f < TC_DCOUNT; ++f) P.C.d[f] = C.getd(f);
+                for (int f = 0; f < TI_ICOUNT; ++f) P.C.i[f] = C.geti(f);
+                P.C.i[TI_SAMPLE] = (int32_t)idx;
+                active = false;
+            } else if (retired) {
                 n_replay += (unsigned long long)rep;
                 State s; store_get(st, s);
                 write_flight_outputs(K, C, s, a.out + idx, a.iout + idx, a.old);
@@ -418,6 +434,74 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
 
 template <int BLOCK, int MINB, int COLD, int MK = -1, int WK = -1>
 __global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a) { flight_body<BLOCK, COLD, MK, WK>(a); }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* One thread per parked trajectory: the strict continuation (emc_strict.cuh) to the end of the flight, then the
+ * summary.  Convergent in code (every lane is strict), ragged in length (a handful of steps each; NaN tails are
+ * replayed in closed form). */
+struct StrictTape {
+    const KernelArgs *a; ColdStruct C;
+    __device__ __forceinline__ void operator()(const TrackHot &K, const double *st) const
+    {
+        if (a->tape && (int64_t)K.n_steps < a->tape_cap) {
+            double *row = a->tape + (int64_t)K.n_steps * EMC_TAPE_WIDTH;
+            row[0] = K.t;
+            for (int c = 0; c < 14; ++c) row[1 + c] = st[c];
+        }
+        if (a->bt_slot) {
+            const int32_t slot = C.geti(TI_BT_SLOT);
+            if (slot >= 0 && K.n_steps == C.geti(TI_BT_NEXT)) {
+                bt_write(*a, slot, K.n_steps / a->bt_stride, K.t - K.t_rail, st[0], st[1], st[2]);
+                C.seti(TI_BT_NEXT, K.n_steps + a->bt_stride);
+            }
+        }
+    }
+};
+
+__global__ void __launch_bounds__(128) emc_strict_kernel(KernelArgs a)
+{
+    extern __shared__ double alt[];
+    __shared__ DevTables Tb;
+    stage_tables(Tb, alt, a);
+    const unsigned long long n_parked = *a.park_count;
+    unsigned long long steps = 0, replays = 0;
+    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_parked; p += (unsigned long long)gridDim.x * blockDim.x) {
+        ParkRec &P = a.park[p];
+        const int64_t idx = P.C.i[TI_SAMPLE];
+        Sample S;
+        load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
+        TrackHot K = P.K;
+        const ColdStruct C(P.C);
+        double st[14];
+        memcpy(st, &P.s, sizeof st);
+        int64_t ns = 0;
+        const StrictTape tape = { &a, C };
+        const int64_t rep = strict_fly(c_model, Tb, alt, S, K, C, st, a.nan_ff != 0, &ns, tape);
+        State s;
+        memcpy(&s, st, sizeof s);
+        write_flight_outputs(K, C, s, a.out + idx, a.iout + idx, a.old);
+        if (a.tape_n) *a.tape_n = (int64_t)K.n_steps + 1 - rep;
+        if (a.bt_slot) {
+            const int32_t slot = C.geti(TI_BT_SLOT);
+            if (slot >= 0) {
+                const int32_t last = K.n_steps - (int32_t)rep;
+                int32_t rows = last / a.bt_stride + 1;
+                if (rep == 0 && last % a.bt_stride != 0) { bt_write(a, slot, rows, K.t - K.t_rail, s.x, s.y, s.z); ++rows; }
+                a.bt_count[slot] = rows;
+                atomicAdd(a.counters + 7, (unsigned long long)(rows < a.bt_max ? rows : a.bt_max));
+            }
+        }
+        steps += (unsigned long long)ns; replays += (unsigned long long)rep;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        steps += __shfl_down_sync(0xffffffffu, steps, o);
+        replays += __shfl_down_sync(0xffffffffu, replays, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (steps) atomicAdd(a.counters + 9, steps);
+        if (replays) atomicAdd(a.counters + 1, replays);
+    }
+}
 
 /* ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) emc_derivative_kernel(KernelArgs a, const double *t, const double *state,
@@ -530,7 +614,7 @@ struct emc_ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool has_model = false;
     emc_model model;              /* raw copy (wind_altitudes pointer is NOT valid after set_model) */
     DevModel dmodel;              /* host copies of what c_model / c_tables must hold while this context launches */
@@ -559,6 +643,7 @@ struct emc_ctx {
     int32_t *d_bt_count = nullptr; size_t cap_bt_count = 0;
     int64_t *d_bt_list = nullptr; size_t cap_bt_list = 0;
     unsigned char *d_gcold = nullptr; size_t cap_gcold = 0;     /* GlobalCold arrays of the 16-warp kernel */
+    ParkRec *d_park = nullptr; size_t cap_park = 0;             /* trajectories parked for the strict continuation */
     int64_t bt_n_sel = 0; int32_t bt_stride = 0, bt_max = 0;
     bool bt_armed = false;                    /* a request waits for the next run */
     int64_t bt_have = 0;                      /* n_sel of the tape the last armed run left in d_bt_rows */
@@ -615,7 +700,7 @@ EMC_EXPORT int emc_create(emc_ctx **out, int device)
     memset(&ctx->counters, 0, sizeof ctx->counters);
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctrl, 16 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         std::string m = std::string("emc_create: ") + cudaGetErrorString(e);
@@ -635,10 +720,10 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
         std::lock_guard<std::mutex> lk(g_owner_mu);
         if (ctx->device >= 0 && ctx->device < 64 && g_owner[ctx->device] == ctx) g_owner[ctx->device] = nullptr;
     }
-    cudaFree(ctx->d_out1); cudaFree(ctx->d_iout1); cudaFree(ctx->d_bt_slot); cudaFree(ctx->d_bt_rows); cudaFree(ctx->d_bt_count); cudaFree(ctx->d_bt_list); cudaFree(ctx->d_gcold);
+    cudaFree(ctx->d_out1); cudaFree(ctx->d_iout1); cudaFree(ctx->d_bt_slot); cudaFree(ctx->d_bt_rows); cudaFree(ctx->d_bt_count); cudaFree(ctx->d_bt_list); cudaFree(ctx->d_gcold); cudaFree(ctx->d_park);
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
     cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_summary); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
-    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return EMC_OK;
@@ -750,6 +835,11 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     a.nan_ff = o.nan_fast_forward;
     a.sm_count = ctx->sm_count > 0 ? ctx->sm_count : 1;
     a.compact = (o.flags & EMC_RUN_COMPACTION) ? 1 : 0;
+    a.park_on = (o.flags & EMC_RUN_NO_STRICT_TAIL) ? 0 : 1;
+    if (a.park_on && a.n > 0) {
+        CK(grow(&ctx->d_park, &ctx->cap_park, (size_t)a.n));
+        a.park = ctx->d_park; a.park_count = ctx->d_ctrl + 11;
+    }
     a.wind_alt = ctx->d_wind_alt;
     a.queue = ctx->d_ctrl; a.counters = ctx->d_ctrl + 1;
     if (a.tape) a.tape_n = reinterpret_cast<int64_t *>(ctx->d_ctrl + 5);
@@ -806,6 +896,16 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("flight kernel launch: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->counters.kernel_launches = 2;
+    if (a.park_on) {
+        /* the parked trajectories (their number is only known on the device: a grid that covers the SMs, grid-stride) */
+        int64_t grid = (a.n + 127) / 128;
+        const int64_t cap = (int64_t)ctx->sm_count * 4;
+        if (grid > cap) grid = cap;
+        emc_strict_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        ctx->counters.kernel_launches = 3;
+    }
+    CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     return EMC_OK;
 }
 
@@ -820,10 +920,13 @@ static int finish_counters(emc_ctx *ctx)
     ctx->counters.refills = (int64_t)h[4];
     ctx->counters.tape_rows = (int64_t)h[8];
     ctx->counters.handovers = (int64_t)h[9];
+    ctx->counters.strict_steps = (int64_t)h[10];
+    ctx->counters.parked = (int64_t)h[11];
     float ms = 0.f;
     if (ctx->counters.kernel_launches) {
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->counters.rail_ms = ms;
         CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); ctx->counters.flight_ms = ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[4])); ctx->counters.strict_ms = ms;
     }
     return EMC_OK;
 }

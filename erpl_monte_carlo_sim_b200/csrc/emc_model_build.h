@@ -190,6 +190,8 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
     const double aoc = AR / ((1e-6 > cs) ? 1e-6 : cs);                                /* rocket.py:179 */
     D.AR_over_cos2 = aoc * aoc;
     D.two_pi_AR_cos = (2 * M_PI * AR) * cs;                                           /* rocket.py:180 */
+    D.fin_AR = AR; D.fin_cos = cs; D.fin_cos_floor = (1e-6 > cs) ? 1e-6 : cs; D.two_pi_AR = 2 * M_PI * AR;
+    D.stall_span = 45.0 * (M_PI / 180.0) - 15.0 * (M_PI / 180.0);                     /* rocket.py:168,185 */
     D.power_off_factor = m.power_off_drag_factor;
     D.stall_angle = 15.0 * (M_PI / 180.0);                                            /* rocket.py:167 */
     D.inv_stall_span = 1.0 / (45.0 * (M_PI / 180.0) - 15.0 * (M_PI / 180.0));         /* rocket.py:168,185 */

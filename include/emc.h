@@ -168,6 +168,11 @@ typedef struct emc_run_opts {
     int32_t cold_state_in_smem; /* 0 (default) or 2: per-lane bookkeeping, base state and RK4 accumulator live in shared memory; 1: bookkeeping only; -1: registers */
     int32_t flags;            /* ABI 2: EMC_RUN_* bits */
 } emc_run_opts;
+#define EMC_RUN_NO_STRICT_TAIL 2   /* finish every trajectory on the fast path.  Default: a trajectory whose stored state shows the reference's
+                                     blow-up in its last steps (|v| > 1e7 m/s or |omega| > 1000 rad/s) is finished by a second kernel that follows the
+                                     reference's arithmetic operation by operation (no FMA contraction, IEEE division / square root, libm), so
+                                     that the inf / NaN pattern of the overflowing steps — step count, termination, first-NaN index — is the
+                                     reference's. */
 #define EMC_RUN_COMPACTION 1      /* tail compaction: once the work queue is empty, sparse warps hand their trajectories (lane records in
                                      shared memory, addressed by slot) to one collector warp per block and exit.  Bit-identical outputs.
                                      Off by default: measured on the B200 the slot indirection costs more than the compacted tail
@@ -185,6 +190,9 @@ typedef struct emc_counters {
     double rail_ms, flight_ms;/* device time of the two kernels (CUDA events on the context stream) */
     int64_t tape_rows;        /* ABI 2: rows stored by an armed batch tape (emc_tape_request) */
     int64_t handovers;        /* ABI 2: trajectories handed to a collector warp by the tail compaction (EMC_RUN_COMPACTION) */
+    int64_t parked;           /* ABI 2: trajectories finished by the strict continuation (blow-up under way; csrc/emc_strict.cuh) */
+    int64_t strict_steps;     /* ABI 2: RK4 steps taken there (not included in rk4_steps) */
+    double strict_ms;         /* ABI 2: device time of emc_strict_kernel */
 } emc_counters;
 
 int emc_abi_version(void);

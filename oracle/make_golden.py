@@ -16,6 +16,7 @@ Files written
   mc_solid_csv.npz       C3: Solid + sample_wind.csv + perturbations, seeds 0..63
   mc_planar_liquid.npz / mc_planar_solid.npz   W-B launch->landing set (beta == 0), seeds 0..7
   mc_readme_literal.npz  C2 literal (pitch 0.02): one-step flights, seeds 0..15
+  mc_solid_csv_blowup.npz  C3 seeds from 300000 on whose blow-up reaches z = -inf inside an RK4 stage (round-2 regression set)
   analysis.npz           MonteCarloAnalyzer._analyze_results on a mixed valid/outlier result list
 """
 from __future__ import annotations
@@ -330,6 +331,10 @@ def gen_analysis(valid_slim, outlier_slim):
     print(f"[analysis] n_samples={an['n_samples']} n_outliers={an['n_outliers']} n_failed={an['n_failed']}", flush=True)
 
 
+# seeds of the round-2 blow-up regression set (see main)
+BLOWUP_SEEDS = [300565, 302472, 305702, 305805, 307702, 309836, 310157, 310290, 310955, 312340, 313147, 314634, 314852, 315939, 316406, 317392, 317574, 317885, 318351, 318468, 319094, 320154, 320637, 320954, 320985, 321037, 321503, 321505, 324352, 326049, 326298, 328898, 329273, 330702, 333907, 334880, 335859, 336121, 336832, 338056, 338878, 339516, 340040, 340186, 342310, 342370, 344207, 346030, 346672, 346675]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--jobs", type=int, default=os.cpu_count())
@@ -359,6 +364,11 @@ def main():
             wa, _ = run_mc("mc_liquid_default", dict(motor="liquid", csv=False, ic=ic_vert, planar=False), range(64), pool)
         if want("mc_solid_csv"):
             run_mc("mc_solid_csv", dict(motor="solid", csv=True, ic=ic_vert10, planar=False), range(64), pool)
+        if want("mc_blowup"):
+            # round 2: the 50 samples of a 50 000-sample C3 sweep (seeds 300000..) on which the first strict continuation still
+            # differed from the C oracle — all of them blow-ups that reach z = -inf in an RK4 stage (np.interp returns the end
+            # value of the wind table there, not NaN) and then grind to max_time as NaN runs
+            run_mc("mc_solid_csv_blowup", dict(motor="solid", csv=True, ic=ic_vert10, planar=False), BLOWUP_SEEDS, pool)
         if want("mc_readme"):
             run_mc("mc_readme_literal", dict(motor="liquid", csv=False, ic=ic_readme, planar=False), range(16), pool)
         if want("analysis") and planar is not None and wa is not None:

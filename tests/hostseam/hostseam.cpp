@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include "../../erpl_monte_carlo_sim_b200/csrc/emc_model_build.h"
+#include "../../erpl_monte_carlo_sim_b200/csrc/emc_strict.cuh"
 
 using namespace emc;
 
@@ -70,6 +71,81 @@ int hs_batch(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outp
         }
         write_flight_outputs(K, C, s, out, iout, o->ld);
         if (n_states) *n_states = ns;
+    }
+    return 0;
+}
+
+
+/* strict_derivative on arrays (same layout as hs_derivative) */
+__attribute__((visibility("default")))
+int hs_strict_derivative(const emc_model *m, const emc_inputs *in, int64_t n, const double *t, const double *state,
+                         int32_t *chute, double *state_dot)
+{
+    if (validate_model(*m)) return -1;
+    DevModel D; DevTables T;
+    build_dev_model(*m, D, T);
+    for (int64_t i = 0; i < n; ++i) {
+        Sample S;
+        load_sample(D, in->scalars + i, in->ld, in->wind ? in->wind + i * in->wind_sample_stride : nullptr, S);
+        WindBracket WB; wind_bracket_reset(WB);
+        bool ch = chute[i] != 0; double ct = NAN;
+        strict_derivative(D, T, m->wind_altitudes, S, WB, t[i], state + 14 * i, ch, ct, state_dot + 14 * i);
+        chute[i] = ch ? 1 : 0;
+    }
+    return 0;
+}
+
+
+/* n flights continued by the STRICT code (emc_strict.cuh).  from_step < 0: strict from the rail-exit state found in o->out
+ * (the rail_* fields must be filled, e.g. by the oracle).  from_step >= 0: the fast path flies until its trigger fires
+ * (strict_trigger) or the flight ends, exactly as the flight kernel + emc_strict_kernel pair does. */
+struct HostTape {
+    double *rows; int64_t cap;
+    void operator()(const TrackHot &K, const double *st) const
+    {
+        if (rows && K.n_steps < cap) { rows[(int64_t)K.n_steps * EMC_TAPE_WIDTH] = K.t; memcpy(rows + (int64_t)K.n_steps * EMC_TAPE_WIDTH + 1, st, 14 * sizeof(double)); }
+    }
+};
+
+__attribute__((visibility("default")))
+int hs_batch_strict(const emc_model *m, const emc_inputs *in, int64_t n, const emc_outputs *o, int nan_fast_forward, int from_step,
+                    int64_t *strict_steps, double *tape, int64_t tape_cap)
+{
+    if (validate_model(*m)) return -1;
+    DevModel D; DevTables T;
+    build_dev_model(*m, D, T);
+    for (int64_t i = 0; i < n; ++i) {
+        const double *col = in->scalars + i;
+        double *out = o->out + i; int32_t *iout = o->iout + i;
+        Sample S;
+        load_sample(D, col, in->ld, in->wind ? in->wind + i * in->wind_sample_stride : nullptr, S);
+        if (from_step >= 0) iout[EMC_IOUT_RAIL_STEPS * o->ld] = rail_phase(D, T, m->wind_altitudes, S, col, in->ld, out, o->ld);
+        State s; double t_rail;
+        load_flight_state(S, col, in->ld, out, o->ld, s, t_rail);
+        Track TK; TrackHot &K = TK.h; const ColdStruct C(TK.c);
+        track_init(K, C, s, t_rail);
+        if (!(K.t < D.max_time)) { K.term = EMC_TERM_MAX_TIME; K.finishing = true; }
+        int64_t replayed = 0;
+        bool finished = false;
+        if (from_step >= 0) {
+            RegStore st; store_put(st, s);
+            WindBracket WB; wind_bracket_reset(WB);
+            for (;;) {
+                bool stepped;
+                if (lane_advance(D, T, m->wind_altitudes, S, WB, K, C, st, nan_fast_forward != 0, stepped, replayed, true)) { finished = (K.replay != EMC_REPLAY_PARK); break; }
+            }
+            store_get(st, s);
+        }
+        if (!finished) {
+            K.replay = 0;
+            double st14[14]; memcpy(st14, &s, sizeof st14);
+            int64_t steps = 0;
+            const HostTape ht = { tape, tape_cap };
+            replayed += strict_fly(D, T, m->wind_altitudes, S, K, C, st14, nan_fast_forward != 0, &steps, ht);
+            memcpy(&s, st14, sizeof st14);
+            if (strict_steps) strict_steps[i] = steps;
+        } else if (strict_steps) strict_steps[i] = 0;
+        write_flight_outputs(K, C, s, out, iout, o->ld);
     }
     return 0;
 }

@@ -45,9 +45,9 @@ def test_gpu_mc_sets(engine, name):
     np.testing.assert_array_equal(iout, z["iout"])
     util.assert_summary_close(out, z["out"], what=name)
     c = engine.counters()
-    assert c["kernel_launches"] == 2 and c["refills"] == z["scalars"].shape[1]
+    assert c["kernel_launches"] == 3 and c["refills"] == z["scalars"].shape[1]      # rail, flight, strict continuation
     nan_ff = z["iout"][_abi.IOUT["first_nan_step"]] >= 0
-    assert c["rk4_steps"] + c["replay_steps"] == int(z["iout"][0].sum())
+    assert c["rk4_steps"] + c["strict_steps"] + c["replay_steps"] == int(z["iout"][0].sum())
     assert (c["replay_steps"] > 0) == bool(nan_ff.any())
 
 
@@ -160,7 +160,8 @@ def test_gpu_full_size_properties(engine):
     out, iout = engine.run_batch(sc, wind)
     c = engine.counters()
     steps = iout[_abi.IOUT["n_steps"]].astype(np.int64)
-    assert c["rk4_steps"] + c["replay_steps"] == int(steps.sum())
+    assert c["rk4_steps"] + c["strict_steps"] + c["replay_steps"] == int(steps.sum())
+    assert 0 < c["parked"] <= n and c["strict_steps"] >= c["parked"]          # blown-up flights finished by the strict continuation
     assert c["refills"] == n
     term = iout[_abi.IOUT["termination"]]
     assert np.all((term >= 1) & (term <= 4))

@@ -188,3 +188,42 @@ def test_mach_union_grid_reproduces_both_tables():
             ref[:, i] = list(c)
         np.testing.assert_allclose(got[:6], ref, rtol=2e-14, atol=1e-16, err_msg=f"trial {trial}")
         np.testing.assert_allclose(got[5], ref[5], rtol=4e-16)            # CP: table value + cp_location, one FMA rounding apart
+
+
+@pytest.mark.parametrize("name", ["mc_solid_csv", "mc_liquid_default", "mc_planar_solid", "mc_planar_liquid", "mc_readme_literal"])
+def test_strict_continuation_reproduces_the_oracle_bit_for_bit(name):
+    """csrc/emc_strict.cuh (the code emc_strict_kernel runs for trajectories whose blow-up is under way) compiled by g++:
+    flown from the oracle's rail-exit state it must give the oracle's flight outputs BIT FOR BIT — integers, summaries and
+    the running maxima/minima, NaN patterns included.  This pins its operation order to the reference's."""
+    z = util.golden(name)
+    md = _abi.model_from_npz(z)
+    n = min(z["scalars"].shape[1], 4 if "planar" in name else 64)
+    sc, wind = z["scalars"][:, :n], z["wind"][:n]
+    ref, iref = O.batch(md, sc, wind)
+    out, iout, steps = util.hostseam_batch_strict(md, sc, wind, out_with_rail=ref)
+    np.testing.assert_array_equal(iout[:4], iref[:4])
+    flight = [i for i, k in enumerate(_abi.OUT_FIELDS) if not k.startswith("rail_") and not k.startswith("wind_at")]
+    np.testing.assert_array_equal(out[flight], ref[flight])                    # NaN == NaN positionally
+    np.testing.assert_array_equal(iout[:4], z["iout"][:4, :n])                 # ... and the reference's own integers
+    assert steps.sum() > 0
+
+
+def test_fast_path_hands_blown_up_flights_to_the_strict_continuation():
+    """The pair the GPU runs (fast kernel until |v| > 1e7 m/s or |omega| > 1000 rad/s, then the strict code), on 3 000 seeded
+    C3 samples the goldens do not contain: every integer output equals the oracle's (the fast path alone leaves ~0.6 %
+    of them different, all blown-up flights whose overflow pattern depends on the operation order); flights that land
+    are never parked."""
+    z = util.golden("mc_solid_csv")
+    md = _abi.model_from_npz(z)
+    sc, wind = util.synth(z, 3000, 11)
+    ref, iref = O.batch(md, sc, wind)
+    fast, ifast = util.hostseam_batch(md, sc, wind)
+    both, iboth, steps = util.hostseam_batch_strict(md, sc, wind)
+    assert int((ifast[:4] != iref[:4]).any(axis=0).sum()) >= 5               # the defect this exists for
+    np.testing.assert_array_equal(iboth[:4], iref[:4])
+    assert 0.4 < (steps > 0).mean() <= 1.0 and steps.max() <= 6                 # only the last steps of a blow-up are strict
+    zp = util.golden("mc_planar_solid")
+    out, iout, steps_p = util.hostseam_batch_strict(_abi.model_from_npz(zp), zp["scalars"][:, :4], zp["wind"][:4])
+    landed = zp["iout"][_abi.IOUT["termination"], :4] == 1
+    assert np.all(steps_p[landed & (zp["iout"][_abi.IOUT["first_nan_step"], :4] < 0) & (np.abs(zp["out"][_abi.OUT["max_speed"], :4]) < 1e4)] == 0)
+    np.testing.assert_array_equal(iout, zp["iout"][:, :4])

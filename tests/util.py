@@ -100,10 +100,11 @@ def hostseam_lib():
     srcs = [os.path.join(d, "hostseam.cpp"),
             os.path.join(os.path.dirname(HERE), "erpl_monte_carlo_sim_b200", "csrc", "emc_physics.cuh"),
             os.path.join(os.path.dirname(HERE), "erpl_monte_carlo_sim_b200", "csrc", "emc_model_build.h"),
+            os.path.join(os.path.dirname(HERE), "erpl_monte_carlo_sim_b200", "csrc", "emc_strict.cuh"),
             os.path.join(os.path.dirname(HERE), "include", "emc.h")]
     if not os.path.isfile(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-std=c++17",
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-fvisibility=hidden", "-std=c++17", "-ffp-contract=off",
                                "-o", so, srcs[0], "-lm"])
     return C.CDLL(so)
 
@@ -141,13 +142,35 @@ def hostseam_batch(md, scalars, wind, nan_ff=True):
     return out, iout
 
 
+def hostseam_batch_strict(md, scalars, wind, out_with_rail=None, nan_ff=True, tape=None):
+    """Flights finished by the strict continuation (csrc/emc_strict.cuh) compiled by g++.  out_with_rail: an output block
+    whose rail_* fields are filled (strict from the rail exit); None: fast path until the blow-up trigger, then strict.
+    Returns (out, iout, strict_steps)."""
+    HS = hostseam_lib()
+    m, keep = _abi.pack_model(md)
+    scalars = np.ascontiguousarray(scalars, np.float64)
+    n = scalars.shape[1]
+    wind = np.ascontiguousarray(wind, np.float64) if wind is not None and np.size(wind) else None
+    ins = _abi.inputs_struct(scalars, wind, wind_shared=(wind is not None and wind.ndim == 2))
+    outs, out, iout = _abi.outputs_alloc(n)
+    if out_with_rail is not None:
+        out[:] = out_with_rail
+        iout[:] = 0
+    steps = np.zeros(n, np.int64)
+    rc = HS.hs_batch_strict(C.byref(m), C.byref(ins), C.c_int64(n), C.byref(outs), C.c_int(1 if nan_ff else 0),
+                            C.c_int(-1 if out_with_rail is not None else 0), steps.ctypes.data_as(C.POINTER(C.c_int64)),
+                            tape.ctypes.data_as(_dp) if tape is not None else None, C.c_int64(tape.shape[0] if tape is not None else 0))
+    assert rc == 0
+    return out, iout, steps
+
+
 def single_case(z, name):
     md = _abi.model_from_npz(z, name + "__")
     wind = z[name + "__wind"][0] if (name + "__wind") in z.files else None
     return md, z[name + "__scalars"], wind, z[name + "__out"], z[name + "__iout"]
 
 
-MC_SETS = ["mc_planar_liquid", "mc_planar_solid", "mc_liquid_default", "mc_solid_csv", "mc_readme_literal"]
+MC_SETS = ["mc_planar_liquid", "mc_planar_solid", "mc_liquid_default", "mc_solid_csv", "mc_readme_literal", "mc_solid_csv_blowup"]
 DERIV_SETS = ["derivative_liquid_wind100", "derivative_solid_csv", "derivative_liquid_nowind"]
 
 

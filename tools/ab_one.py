@@ -38,7 +38,7 @@ def best_of(blk, wind, reps=3):
 
 
 c = best_of(z["blk"], z["wind"], 4)
-res["handovers"] = c.get("handovers"); res["c3_100k_ms"] = round(c["flight_ms"], 3); res["c3_100k_gsteps"] = round(c["rk4_steps"] / c["flight_ms"] / 1e6, 3)
+res["handovers"] = c.get("handovers"); res["parked"] = c.get("parked"); res["strict_ms"] = round(c.get("strict_ms", 0.0), 3); res["strict_steps"] = c.get("strict_steps"); res["c3_100k_ms"] = round(c["flight_ms"], 3); res["c3_100k_gsteps"] = round(c["rk4_steps"] / c["flight_ms"] / 1e6, 3)
 big_b = np.ascontiguousarray(np.tile(z["blk"], (1, 8))); big_w = np.ascontiguousarray(np.tile(z["wind"], (8, 1, 1)))
 c = best_of(big_b, big_w, 2)
 res["c3_800k_ms"] = round(c["flight_ms"], 3); res["c3_800k_gsteps"] = round(c["rk4_steps"] / c["flight_ms"] / 1e6, 3)

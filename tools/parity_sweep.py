@@ -16,6 +16,8 @@ from erpl_monte_carlo_sim_b200 import _abi, _lib  # noqa: E402
 
 eng = _lib.Engine(0)
 for workload, n, seed0 in (("c3", int(os.environ.get("N_C3", "20000")), 300000), ("planar", int(os.environ.get("N_PLANAR", "1500")), 700000)):
+    if n <= 0:
+        continue
     md, blk, wind, _ = bench.make_workload(workload, n, seed0)
     eng.set_model(md)
     out, iout = eng.run_batch(blk, wind)
@@ -34,6 +36,10 @@ for workload, n, seed0 in (("c3", int(os.environ.get("N_C3", "20000")), 300000),
     mask = lambda o: MonteCarloAnalyzer.outlier_mask(o[OUT["apogee_altitude"]], o[OUT["range"]], o[OUT["flight_time"]])
     mg, mr = mask(out), mask(ref)
     differ = ~same
+    if os.environ.get("DUMP_DIFFER"):
+        idx = np.flatnonzero(differ)
+        np.savez(os.environ["DUMP_DIFFER"] + "_" + workload + ".npz", idx=idx, scalars=blk[:, idx], wind=wind[idx], out=out[:, idx], iout=iout[:, idx],
+                 ref=ref[:, idx], iref=iref[:, idx])
     if os.environ.get("VERBOSE"):
         names = list(OUT)
         for f, i in list(zip(*np.nonzero(bad)))[:40]:
