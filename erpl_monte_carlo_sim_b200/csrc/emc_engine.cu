@@ -122,9 +122,10 @@ struct GlobalCold {
     __device__ __forceinline__ void seti(int f, int32_t v) const { i[f * ld] = v; }
 };
 
-/* Dynamic shared memory of the flight kernel: [28][BLOCK] state store (COLD >= 2) followed by the wind altitude grid.
- * It is indexed directly (never through a pointer carved out of it), so the accesses are plain LDS/STS. */
-extern __shared__ double emc_dyn[];
+/* Dynamic shared memory of the flight kernel: [14][BLOCK] PAIRS of state words (7 pairs of the base state, 7 of the RK4
+ * accumulator; COLD >= 2) followed by the wind altitude grid.  It is indexed directly (never through a pointer carved out
+ * of it), so the accesses are plain LDS/STS — 128-bit ones for the pairs: a warp reads 32 consecutive 16-byte words. */
+extern __shared__ __align__(16) double emc_dyn[];
 
 /* one row {t - t_rail, x, y, z} of the downsampled batch tape: a 32-byte store per lane (one sector) */
 __device__ __forceinline__ void bt_write(const KernelArgs &a, int32_t slot, int32_t row, double t, double x, double y, double z)
@@ -135,16 +136,36 @@ __device__ __forceinline__ void bt_write(const KernelArgs &a, int32_t slot, int3
     }
 }
 
-/* base state + RK4 accumulator of this thread's lane record (a column of the [28][BLOCK] block at the start of emc_dyn) */
+/* A shared-memory address the compiler cannot rebuild: ptxas otherwise REMATERIALISES the address of a lane record
+ * (S2R CgaCtaId, S2R tid, shift, add: six instructions and two long-latency special-register reads) twice per
+ * derivative instead of holding it in one register (profiles/, round 2).  The round trip through the 32-bit shared
+ * window address keeps the address space known, so the accesses stay LDS/STS. */
+template <class T>
+__device__ __forceinline__ T *opaque_shared(T *p)
+{
+#ifndef EMC_NO_OPAQUE
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("" : "+r"(a));
+    return reinterpret_cast<T *>(__cvta_shared_to_generic((size_t)a));
+#else
+    return p;
+#endif
+}
+
+/* base state + RK4 accumulator of this thread's lane record (a column of the [14][BLOCK] pair block at the start of emc_dyn) */
 template <int BLOCK>
 struct SharedStore {
-    __device__ __forceinline__ double s(int i) const { return emc_dyn[i * BLOCK + threadIdx.x]; }
-    __device__ __forceinline__ void set_s(int i, double v) { emc_dyn[i * BLOCK + threadIdx.x] = v; }
-    __device__ __forceinline__ double acc(int i) const { return emc_dyn[(14 + i) * BLOCK + threadIdx.x]; }
-    __device__ __forceinline__ void set_acc(int i, double v) { emc_dyn[(14 + i) * BLOCK + threadIdx.x] = v; }
+    Pair *col;
+    __device__ __forceinline__ SharedStore() : col(opaque_shared(reinterpret_cast<Pair *>(emc_dyn) + threadIdx.x)) {}
+    __device__ __forceinline__ Pair s2(int p) const { return col[p * BLOCK]; }
+    __device__ __forceinline__ void set_s2(int p, Pair v) { col[p * BLOCK] = v; }
+    __device__ __forceinline__ Pair acc2(int p) const { return col[(7 + p) * BLOCK]; }
+    __device__ __forceinline__ void set_acc2(int p, Pair v) { col[(7 + p) * BLOCK] = v; }
+    __device__ __forceinline__ double s(int i) const { return reinterpret_cast<const double *>(col + (i >> 1) * BLOCK)[i & 1]; }
+    __device__ __forceinline__ void set_s(int i, double v) { reinterpret_cast<double *>(col + (i >> 1) * BLOCK)[i & 1] = v; }
     __device__ __forceinline__ void adopt(int src) {                      /* take over another record's column */
 #pragma unroll
-        for (int i = 0; i < 28; ++i) emc_dyn[i * BLOCK + threadIdx.x] = emc_dyn[i * BLOCK + src];
+        for (int p = 0; p < 14; ++p) col[p * BLOCK] = reinterpret_cast<const Pair *>(emc_dyn)[p * BLOCK + src];
     }
 };
 struct RegStoreLane : RegStore { __device__ __forceinline__ void adopt(int) {} };
@@ -368,9 +389,9 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
 
 /* where the lane records live */
 template <class REC> struct SmemLanesFull {          /* hot + cold halves side by side in shared memory */
-    REC *recs;
-    __device__ __forceinline__ REC &rec(int slot) const { return recs[slot]; }
-    __device__ __forceinline__ ColdStruct cold(int slot) const { return ColdStruct(recs[slot].C); }
+    REC *recs, *me;                                  /* me: this thread's own record (opaque_shared) */
+    __device__ __forceinline__ REC &rec(int) const { return *me; }
+    __device__ __forceinline__ ColdStruct cold(int) const { return ColdStruct(me->C); }
     __device__ __forceinline__ void adopt(int dst, int src) const {
         const double *s = reinterpret_cast<const double *>(&recs[src]);
         double *d = reinterpret_cast<double *>(&recs[dst]);
@@ -411,18 +432,23 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
                                                     a.gcold_d + g0, a.gcold_i + g0, a.gcold_ld };
         flight_loop<BLOCK, SharedStore<BLOCK>, false, MK, WK>(a, Tb, alt, lanes, (CompactBoard<BLOCK> *)nullptr);
     } else if constexpr (COLD == 2 || COLD == 4) {
-        __shared__ Padded<ColdLaneFull> sh_cold[BLOCK];
+        /* lane records: static shared memory while they fit under its 48 KB limit, else behind the state store in the
+         * dynamic block (one large block per SM) */
+        constexpr bool REC_STATIC = sizeof(Padded<ColdLaneFull>) * BLOCK <= 40960;
+        __shared__ Padded<ColdLaneFull> sh_cold[REC_STATIC ? BLOCK : 1];
         __shared__ CompactBoard<BLOCK> board;
-        double *alt = emc_dyn + 28 * BLOCK;
+        constexpr int REC_WORDS = REC_STATIC ? 0 : (int)(sizeof(Padded<ColdLaneFull>) / 8) * BLOCK;
+        Padded<ColdLaneFull> *recs = REC_STATIC ? sh_cold : reinterpret_cast<Padded<ColdLaneFull> *>(emc_dyn + 28 * BLOCK);
+        double *alt = emc_dyn + 28 * BLOCK + REC_WORDS;
         if (threadIdx.x == 0) { board.reserved = 32; board.posted = 0; board.ready = 0; board.exited = 0; }
         stage_tables(Tb, alt, a);                    /* ends with __syncthreads() */
-        SmemLanesFull<Padded<ColdLaneFull>> lanes = { sh_cold };
+        SmemLanesFull<Padded<ColdLaneFull>> lanes = { recs, opaque_shared(recs + threadIdx.x) };
         if constexpr (COLD == 4) flight_loop<BLOCK, SharedStore<BLOCK>, true, MK, WK>(a, Tb, alt, lanes, &board);
         else flight_loop<BLOCK, SharedStore<BLOCK>, false, MK, WK>(a, Tb, alt, lanes, &board);
     } else if constexpr (COLD == 1) {
         __shared__ Padded<ColdLaneFull> sh_cold[BLOCK];
         stage_tables(Tb, emc_dyn, a);
-        SmemLanesFull<Padded<ColdLaneFull>> lanes = { sh_cold };
+        SmemLanesFull<Padded<ColdLaneFull>> lanes = { sh_cold, opaque_shared(sh_cold + threadIdx.x) };
         flight_loop<BLOCK, RegStoreLane, false, MK, WK>(a, Tb, emc_dyn, lanes, (CompactBoard<BLOCK> *)nullptr);
     } else {
         stage_tables(Tb, emc_dyn, a);
@@ -432,8 +458,13 @@ __device__ __forceinline__ void flight_body(const KernelArgs &a)
     }
 }
 
+#ifdef EMC_SLIM_MAXNREG      /* developer builds: a register cap that launch bounds cannot express (odd warp counts) */
+#define EMC_FLIGHT_BOUNDS __maxnreg__(EMC_SLIM_MAXNREG)
+#else
+#define EMC_FLIGHT_BOUNDS __launch_bounds__(BLOCK, MINB)
+#endif
 template <int BLOCK, int MINB, int COLD, int MK = -1, int WK = -1>
-__global__ void __launch_bounds__(BLOCK, MINB) emc_flight_kernel(KernelArgs a) { flight_body<BLOCK, COLD, MK, WK>(a); }
+__global__ void EMC_FLIGHT_BOUNDS emc_flight_kernel(KernelArgs a) { flight_body<BLOCK, COLD, MK, WK>(a); }
 
 /* ------------------------------------------------------------------------------------------------ */
 /* One thread per parked trajectory: the strict continuation (emc_strict.cuh) to the end of the flight, then the
@@ -877,6 +908,14 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     cudaError_t e;
     const bool cold = o.cold_state_in_smem >= 0;
     const bool store = o.cold_state_in_smem == 0 || o.cold_state_in_smem >= 2;   /* default: base state + RK4 accumulator in shared memory as well */
+#ifdef EMC_SLIM     /* developer builds (tools/build_variant.sh): only the default instances, seconds instead of a minute */
+    (void)bt; (void)bps; (void)cold; (void)store;
+#ifndef EMC_SLIM_BLOCK
+#define EMC_SLIM_BLOCK 128
+#define EMC_SLIM_MINB 3
+#endif
+    e = launch_flight_cfg<EMC_SLIM_BLOCK, EMC_SLIM_MINB, 2>(ctx, a, smem + (28 * sizeof(double) + (sizeof(Padded<ColdLaneFull>) * EMC_SLIM_BLOCK <= 40960 ? 0 : sizeof(Padded<ColdLaneFull>))) * EMC_SLIM_BLOCK, EMC_SLIM_MINB);
+#else
     if (bt == 256 && bps == 2) {
         /* 16 warps per SM: 2 blocks x 256 lanes at 128 registers; the once-per-step bookkeeping lives in global memory */
         const int64_t lanes = (int64_t)ctx->sm_count * 2048;
@@ -893,6 +932,7 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     else if (bt == 128) e = launch_flight<128, 1, 0>(ctx, a, smem, bps);
     else if (bt == 64) e = launch_flight<64, 1, 0>(ctx, a, smem, bps);
     else return fail(ctx, EMC_ERR_INVALID, "block_threads must be 64, 128 or 256 (with 2 blocks per SM)");
+#endif
     if (e != cudaSuccess) return fail(ctx, EMC_ERR_CUDA, std::string("flight kernel launch: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->counters.kernel_launches = 2;

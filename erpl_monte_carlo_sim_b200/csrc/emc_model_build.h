@@ -147,6 +147,8 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
     D.R_gas = R; D.g0 = g;
     D.mach_k = (R == 287.053) ? 1.0 / 1.4 : R / (1.4 * 287.053);                      /* utils.py:152-157 */
     D.gamma = (m.gamma > 0.0) ? m.gamma : 1.4;                                        /* environment.py:19,96 */
+    D.a2_k = 1.4 * 287.053;                                                           /* a^2 = 1.4*287.053*T, utils.py:152-157 */
+    D.rho_k = (1.4 * 287.053) / R;                                                    /* 1/(R T) = rho_k / a^2 */
     {
         /* p0*(1 - a z)^e, a = L/T0, about zc: p0*(1 - a zc)^e * (1 - ap zeta)^e with ap = a zh/(1 - a zc); binomial series
          * c_k = c_{k-1} * (e - k + 1)/k * (-ap).  Used on [-2 km, troposphere_height] when the series has converged to
@@ -200,6 +202,8 @@ inline void build_dev_model(const emc_model &m, DevModel &D, DevTables &T)
     D.max_time = m.max_time; D.dt_rail = m.dt_initial;
     D.dt = (0.005 < m.dt_initial) ? 0.005 : m.dt_initial;                             /* simulator.py:209 */
     D.half_dt = 0.5 * D.dt; D.dt_over_6 = D.dt / 6.0;
+    D.stage_t[0] = 0.0; D.stage_t[1] = D.half_dt; D.stage_t[2] = D.half_dt; D.stage_t[3] = D.dt;      /* simulator.py:218-222 */
+    D.stage_c[0] = D.half_dt; D.stage_c[1] = D.half_dt; D.stage_c[2] = D.dt; D.stage_c[3] = 0.0;
     D.pitch_damping = m.pitch_damping; D.yaw_damping = m.yaw_damping; D.rail_length = m.rail_length;
 
     D.motor_kind = m.motor_kind; D.n_cd = m.n_cd; D.n_cp = m.n_cp;

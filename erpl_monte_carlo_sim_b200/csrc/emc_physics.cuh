@@ -78,6 +78,7 @@ struct DevModel {
     double R_gas, g0;
     double mach_k;       /* R_gas/(1.4*287.053): utils.mach_number hardcodes gamma and R (utils.py:152-157) whatever the atmosphere holds */
     double gamma;        /* atmosphere.gamma: speed_of_sound of get_properties only (environment.py:96) */
+    double a2_k, rho_k;  /* 1.4*287.053 (a^2 = a2_k*T, utils.py:152-157) and a2_k/R_gas (1/(R T) = rho_k/a^2) */
     /* troposphere pressure as ONE polynomial: p0*(1 - L z/T0)^(g/(R L)) expanded about the middle of [tp_lo, tp_hi]
      * (binomial series in zeta = (z - tp_zc)*tp_inv_zh, |zeta| <= 1, truncation < 1e-18 relative; built in long double
      * by build_dev_model).  Replaces exp(e*log(T/T0)) where nearly every sounding-rocket step is flown; an atmosphere
@@ -101,6 +102,7 @@ struct DevModel {
     double chute_cd, chute_area, chute_alt;
     /* simulator knobs, simulator.py:19-37,42,209 */
     double max_time, dt_rail, dt, half_dt, dt_over_6, pitch_damping, yaw_damping, rail_length;
+    double stage_t[4], stage_c[4];   /* RK4 stage time offsets {0, dt/2, dt/2, dt} and next-state coefficients {dt/2, dt/2, dt, -} (simulator.py:218-222) */
     /* wind grid */
     double wind_alt0, wind_inv_dz;
     int32_t motor_kind, n_cd, n_cp, n_thrust, has_wind, n_wind, wind_uniform, n_mb;   /* n_mb: brackets of the Mach union grid */
@@ -286,13 +288,39 @@ EMC_HD double fast_log(double x)
 
 /* atan2 with one division and a degree-18 minimax polynomial in t^2 (tools/fit_atan.py, relative error
  * 2.8e-17 before rounding): atan(t) = t + t*u*Q(u), u = t^2, t = min(|x|,|y|)/max(|x|,|y|) in [0,1]. */
+/* |x| off the FP64 pipe (where the value feeds a select, fabs() would be materialised by a DADD) */
+EMC_HD double fabs_bits(double x)
+{
+#if defined(__CUDA_ARCH__)
+    return __hiloint2double(__double2hiint(x) & 0x7fffffff, __double2loint(x));
+#else
+    return fabs(x);
+#endif
+}
+
+/* x > 0 ? x : 0.0 (NaN -> 0.0): one compare and one select (the ternary is pattern-matched into a seven-instruction
+ * fmax emulation with NaN quieting, and rematerialised wherever the value is needed again) */
+EMC_HD double pos_part(double x)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("{\n\t.reg .pred p;\n\tsetp.gt.f64 p, %1, 0d0000000000000000;\n\tselp.f64 %0, %1, 0d0000000000000000, p;\n\t}" : "=d"(r) : "d"(x));
+    return r;
+#else
+    return (x > 0.0) ? x : 0.0;
+#endif
+}
+
+/* XPOS: x >= 0 is known (sideslip: x = |v_xz|), the half-plane fix-up is dropped.
+ * NONZERO: max(|x|, |y|) > 0 is known (the caller has excluded the dead zone), the atan2(0, 0) guard is dropped. */
+template <bool XPOS = false, bool NONZERO = false>
 EMC_HD double fast_atan2(double y, double x)
 {
-    const double ax = fabs(x), ay = fabs(y);
+    const double ax = fabs_bits(x), ay = fabs_bits(y);
     const bool swap = ay > ax;
     const double num = swap ? ax : ay, den = swap ? ay : ax;
     double t = num * fast_rcp(den);
-    t = (den == 0.0) ? 0.0 : t;                          /* atan2(0, 0) = 0 (0 * rcp(0) is NaN); NaN stays NaN */
+    if (!NONZERO) t = (den == 0.0) ? 0.0 : t;            /* atan2(0, 0) = 0 (0 * rcp(0) is NaN); NaN stays NaN */
     const double u = t * t, u2 = u * u;
     /* two interleaved Horner chains (even / odd coefficients).  A shorter polynomial for |t| <= 1/4 behind a per-lane
      * branch was measured slower (round 2): the branch diverges inside warps that hold a tumbling flight. */
@@ -311,9 +339,52 @@ EMC_HD double fast_atan2(double y, double x)
     /* octant fix-ups as straight-line selects: r <- c_hi - r + c_lo */
     const double r1 = (K_MISC[0] - r) + K_MISC[1];
     r = swap ? r1 : r;
-    const double r2 = (K_MISC[2] - r) + K_MISC[3];
-    r = (x < 0.0) ? r2 : r;
+    if (!XPOS) {
+        const double r2 = (K_MISC[2] - r) + K_MISC[3];
+        r = (x < 0.0) ? r2 : r;
+    }
     return copysign(r, y);
+}
+
+/* The angle of attack atan2(y1, x1) and the sideslip atan2(y2, x2), x2 >= 0, of one derivative evaluation, computed
+ * TOGETHER: the two evaluations are independent, and written side by side their four Horner chains interleave, so the
+ * ~8-cycle latency of a dependent DFMA is covered by the other chains instead of being waited out twice (the flight
+ * kernel holds three warps per scheduler; fixed-latency dependency waits are its largest stall, profiles/).  Same
+ * arithmetic per value as fast_atan2<., true>: both dead zones have been excluded by the caller. */
+EMC_HD void fast_atan2_pair(double y1, double x1, double y2, double x2, double &r1, double &r2)
+{
+    const double ax1 = fabs_bits(x1), ay1 = fabs_bits(y1), ay2 = fabs_bits(y2);
+    const bool sw1 = ay1 > ax1, sw2 = ay2 > x2;
+    const double n1 = sw1 ? ax1 : ay1, d1 = sw1 ? ay1 : ax1;
+    const double n2 = sw2 ? x2 : ay2, d2 = sw2 ? ay2 : x2;
+    const double t1 = n1 * fast_rcp(d1), t2 = n2 * fast_rcp(d2);
+    const double u1 = t1 * t1, u2 = t2 * t2, v1 = u1 * u1, v2 = u2 * u2;
+    double pe1 = K_ATAN[18], po1 = K_ATAN[17], pe2 = K_ATAN[18], po2 = K_ATAN[17];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 16; i >= 2; i -= 2) {
+        pe1 = fma(pe1, v1, K_ATAN[i]); pe2 = fma(pe2, v2, K_ATAN[i]);
+        po1 = fma(po1, v1, K_ATAN[i - 1]); po2 = fma(po2, v2, K_ATAN[i - 1]);
+    }
+    pe1 = fma(pe1, v1, K_ATAN[0]); pe2 = fma(pe2, v2, K_ATAN[0]);
+    const double q1 = fma(po1, u1, pe1), q2 = fma(po2, u2, pe2);
+    double a = fma(t1 * u1, q1, t1), b = fma(t2 * u2, q2, t2);
+    const double a1 = (K_MISC[0] - a) + K_MISC[1], b1 = (K_MISC[0] - b) + K_MISC[1];
+    a = sw1 ? a1 : a; b = sw2 ? b1 : b;
+    const double a2 = (K_MISC[2] - a) + K_MISC[3];
+    a = (x1 < 0.0) ? a2 : a;
+    r1 = copysign(a, y1); r2 = copysign(b, y2);
+}
+
+/* true if the predicate holds for any lane of the warp that is executing this code */
+EMC_HD bool any_lane(bool p)
+{
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), p) != 0;
+#else
+    return p;
+#endif
 }
 
 /* remembered-bracket lookup: j stays valid while lo[j] <= x < hi[j]; NaN leaves j alone (the FMA that
@@ -328,14 +399,37 @@ EMC_HD int brk_find(const double *lo, const double *hi, int nb, int j, double x)
 }
 
 /* ---------------- atmosphere: T and 1/(R*T), p  (environment.py:26-103) ---------------- */
-EMC_HD void atmosphere(const DevModel &M, double z, int &j_atm, double &T, double &inv_RT, double &p)
+/* T and p; 1/(R T) is left to the caller (the flight derivative takes 1/a = rsqrt(1.4*287.053*T) instead and derives
+ * 1/(R T) from it, the other users take fast_rcp(R T), see the wrapper below) */
+EMC_HD void atmosphere_upper(const DevModel &M, double z, int &j_atm, double &T, double &p);
+
+/* SPEC: the troposphere value is computed before the range test, in the caller's straight-line code (where its
+ * eleven-deep dependent chain overlaps the quaternion and mass-property work), and the other layers overwrite it
+ * behind one rarely taken branch. */
+template <bool SPEC = false>
+EMC_HD void atmosphere_Tp(const DevModel &M, double z, int &j_atm, double &T, double &p)
 {
+    if (SPEC) {
+        T = M.T0 - M.lapse * z;
+        p = poly16(M.tp_c, (z - M.tp_zc) * M.tp_inv_zh);
+        if (!EMC_LIKELY(z >= M.tp_lo && z <= M.tp_hi)) {
+            double T2, p2;
+            atmosphere_upper(M, z, j_atm, T2, p2);
+            T = T2; p = p2;
+        }
+        return;
+    }
     if (EMC_LIKELY(z >= M.tp_lo && z <= M.tp_hi)) {          /* troposphere (environment.py:28-33): T linear, p by the series above */
         T = M.T0 - M.lapse * z;
-        inv_RT = fast_rcp(M.R_gas * T);
         p = poly16(M.tp_c, (z - M.tp_zc) * M.tp_inv_zh);
         return;
     }
+    atmosphere_upper(M, z, j_atm, T, p);
+}
+
+/* everything outside the troposphere polynomial's range */
+EMC_HD void atmosphere_upper(const DevModel &M, double z, int &j_atm, double &T, double &p)
+{
     if (M.n_atm > 0) {                          /* upper layers (environment.py:35-103) by segment polynomial */
         int j = j_atm;
         bool ok = (z > M.at_lo[j]) && (z <= M.at_hi[j]);
@@ -348,7 +442,6 @@ EMC_HD void atmosphere(const DevModel &M, double z, int &j_atm, double &T, doubl
             T = M.at_tb[j] + M.at_ts[j] * (z - M.at_tz0[j]);
             T = py_min(T, M.at_tmax[j]);
             T = py_max(T, M.at_tmin[j]);
-            inv_RT = fast_rcp(M.R_gas * T);
             p = poly16(M.at_c[j], (z - M.at_zc[j]) * M.at_izh[j]);
             return;
         }
@@ -372,10 +465,15 @@ EMC_HD void atmosphere(const DevModel &M, double z, int &j_atm, double &T, doubl
         T = py_max(T, 180.0);
         base = 868.02; arg = 0.0;     /* filled below once 1/(R*T) is known */
     }
-    inv_RT = fast_rcp(M.R_gas * T);
     if (use_log) arg = le * fast_log(lx);
-    if (z > 32000.0 || z != z) arg = -(z - 32000.0) * (M.g0 * inv_RT);   /* -(z-32000)/(R*T/g) */
+    if (z > 32000.0 || z != z) arg = -(z - 32000.0) * (M.g0 * fast_rcp(M.R_gas * T));   /* -(z-32000)/(R*T/g) */
     p = base * fast_exp(arg);
+}
+
+EMC_HD void atmosphere(const DevModel &M, double z, int &j_atm, double &T, double &inv_RT, double &p)
+{
+    atmosphere_Tp<false>(M, z, j_atm, T, p);
+    inv_RT = fast_rcp(M.R_gas * T);
 }
 
 EMC_HD void atmosphere(const DevModel &M, double z, double &T, double &inv_RT, double &p)
@@ -443,12 +541,13 @@ EMC_HD void wind_at(const DevModel &M, const double *alt, const Sample &S, doubl
 
 /* ---------------- thrust (motor.py:54-76, 152-156), caller has checked pf>0 && t<=burn ---------- */
 /* thrust inside the burn window (the caller has established 0 <= t <= burn_time) */
+/* th_safe: the caller has established th_lo[j_th] <= t < th_hi[j_th] (rk4_step tests [t, t + dt] once per step) */
 template <int MK = -1>
-EMC_HD double thrust_core(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, double p)
+EMC_HD double thrust_core(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, double p, bool th_safe = false)
 {
     if (cfg_solid<MK>(M)) {
-        const int j = brk_find(Tb.th_lo, Tb.th_hi, M.n_thrust + 1, C.j_th, t);
-        C.j_th = j;
+        int j = C.j_th;
+        if (!th_safe) { j = brk_find(Tb.th_lo, Tb.th_hi, M.n_thrust + 1, j, t); C.j_th = j; }
         const double f = fma(Tb.th_s[j], t - Tb.th_x0[j], Tb.th_f[j]) * S.thrust_a;
         return f + S.nozzle_area * (101325.0 - p);
     }
@@ -480,18 +579,22 @@ EMC_HD bool time_negative(double t)
 template <int MK = -1, int WK = -1>
 EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
                        WindBracket &WB, double t, const State &s, bool &chute, double &chute_time,
-                       State &k, bool want_diag, Diag &dg)
+                       State &k, bool want_diag, Diag &dg, bool th_safe = false)
 {
     /* :305  pf = max(0.0, pf)  (NaN -> 0.0) */
-    const double pf = (s.pf > 0.0) ? s.pf : 0.0;
+    const double pf = pos_part(s.pf);
     const bool burning = (pf > 0.0) && (t <= S.burn_time);
 
-    /* :308  normalise the quaternion (identity if |q| <= 1e-12 or NaN), utils.py:76-82 */
-    const double n2 = s.q0 * s.q0 + s.q1 * s.q1 + s.q2 * s.q2 + s.q3 * s.q3;
-    const bool q_ok = n2 > 1e-24;
-    const double rn = fast_rsqrt(q_ok ? n2 : 1.0);
-    const double qw = q_ok ? s.q0 * rn : 1.0, qx = q_ok ? s.q1 * rn : 0.0;
-    const double qy = q_ok ? s.q2 * rn : 0.0, qz = q_ok ? s.q3 * rn : 0.0;
+    /* :308  the quaternion is normalised by the reference (identity if |q| <= 1e-12 or NaN, utils.py:76-82).  Here the
+     * components stay as they are and the norm goes into two scalars: a = 2 v / |q|^2 for the rotations and
+     * hq = 1 / (2 |q|) for q_dot. */
+    double qw = s.q0, qx = s.q1, qy = s.q2, qz = s.q3;
+    double n2 = qw * qw + qx * qx + qy * qy + qz * qz;
+    if (!(n2 > 1e-24)) { qw = 1.0; qx = 0.0; qy = 0.0; qz = 0.0; n2 = 1.0; }
+    const double rn = fast_rsqrt(n2);
+    const double hq = 0.5 * rn;
+    const double s2 = (rn + rn) * rn;
+    const double ax = s2 * qx, ay = s2 * qy, az = s2 * qz;
 
     /* :311-321  mass properties, rocket.py:110-136 */
     double mp = S.prop_mass * pf;
@@ -503,60 +606,83 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double Ixx = M.Ixx_dry + mp * M.d4sq;
     const double Iyy = M.Iyy_dry + mp * (M.len2_12 + dcg * dcg);
 
-    /* :324  rotation matrix body->inertial, utils.py:100-111 (q already unit) */
-    /* the factors of two are folded into one operand (exact), so 2*(a*b - c*d) costs one product and one FMA */
-    const double x2 = qx + qx, y2 = qy + qy, z2 = qz + qz;
-    const double r00 = 1.0 - (qy * y2 + qz * z2), r01 = qx * y2 - qw * z2, r02 = qx * z2 + qw * y2;
-    const double r10 = qx * y2 + qw * z2, r11 = 1.0 - (qx * x2 + qz * z2), r12 = qy * z2 - qw * x2;
-    const double r20 = qx * z2 - qw * y2, r21 = qy * z2 + qw * x2, r22 = 1.0 - (qx * x2 + qy * y2);
-
-    /* :328-338  atmosphere + wind */
-    double T, inv_RT, p;
-    atmosphere(M, s.z, WB.j_atm, T, inv_RT, p);
-    const double rho = p * inv_RT;
+    /* :328-338  atmosphere + wind.  ya = 1/a with a^2 = 1.4*287.053*T (utils.py:152-157): Mach = |v| ya, and
+     * 1/(R T) = ya^2 * (1.4*287.053/R) gives the density, so one reciprocal square root serves both. */
+    double T, p;
+#ifndef EMC_NO_SPEC_ATM
+    atmosphere_Tp<true>(M, s.z, WB.j_atm, T, p);
+#else
+    atmosphere_Tp<false>(M, s.z, WB.j_atm, T, p);
+#endif
+    const double ya = fast_rsqrt(M.a2_k * T);
+    const double ya2 = ya * ya;
+    const double rho = p * (ya2 * M.rho_k);
     double w[3];
     wind_at<WK>(M, wind_alt, S, s.z, WB, w);
 
-    /* :341-352 */
+    /* :341-352  v_body = R(q)^T u as a quaternion rotation: u - w tb + v x tb, tb = a x u (utils.py:100-111,129-136) */
     const double ux = s.vx - w[0], uy = s.vy - w[1], uz = s.vz - w[2];
-    const double vbx = r00 * ux + r10 * uy + r20 * uz;
-    const double vby = r01 * ux + r11 * uy + r21 * uz;
-    const double vbz = r02 * ux + r12 * uy + r22 * uz;
-    const double v2 = ux * ux + uy * uy + uz * uz;
-    const double mach2 = v2 * (inv_RT * M.mach_k);           /* (|v|/sqrt(1.4*287.053*T))^2, utils.py:152-157 */
-    const double qdyn = 0.5 * rho * v2;
+    const double tbx = ay * uz - az * uy, tby = az * ux - ax * uz, tbz = ax * uy - ay * ux;
+    const double vbx = fma(-qz, tby, fma(qy, tbz, fma(-qw, tbx, ux)));
+    const double vby = fma(-qx, tbz, fma(qz, tbx, fma(-qw, tby, uy)));
+    const double vbz = fma(-qy, tbx, fma(qx, tby, fma(-qw, tbz, uz)));
+    /* |u| = |v_body| (a rotation): the squared speed is taken from the body components, whose partial sum the
+     * aerodynamic angles need anyway */
+    const double vxz2 = vbx * vbx + vbz * vbz;
+    const double vb2 = vxz2 + vby * vby;
+    const double rvb = fast_rsqrt(vb2);                      /* 1/|v|: Mach, sideslip ratios, parachute drag direction */
+    const double mach2 = vb2 * ya2;                          /* (|v|/sqrt(1.4*287.053*T))^2 */
+    const double qdyn = 0.5 * rho * vb2;
 
     /* :359-363 thrust along body x */
-    double fbx = (burning && !time_negative(t)) ? thrust_core<MK>(M, Tb, S, WB, t, p) : 0.0;   /* motor.py:55,153: 0 outside [0, burn_time] */
+#ifndef EMC_NO_SPEC_THRUST
+    /* evaluated in the straight-line code and selected afterwards (np.interp clamps outside the curve, so any time is
+     * a valid argument): no branch region around the table reads */
+    const double thrust = thrust_core<MK>(M, Tb, S, WB, t, p, th_safe);
+    double fbx = (burning && !time_negative(t)) ? thrust : 0.0;                                          /* motor.py:55,153: 0 outside [0, burn_time] */
+#else
+    double fbx = (burning && !time_negative(t)) ? thrust_core<MK>(M, Tb, S, WB, t, p, th_safe) : 0.0;   /* motor.py:55,153: 0 outside [0, burn_time] */
+#endif
     double fby = 0.0, fbz = 0.0;
     double mx = 0.0, my = 0.0, mz = 0.0;
 
     /* :366-369 sticky parachute latch */
-    if (!chute && s.z <= M.chute_alt && s.vz < 0.0) { chute = true; chute_time = t; }
+    {
+        const bool latch = (!chute) & (s.z <= M.chute_alt) & (s.vz < 0.0);
+        chute_time = latch ? t : chute_time;
+        chute = chute | latch;
+    }
 
     const bool aero = (!chute) && (qdyn > 0.0);
-    const double vxz2 = vbx * vbx + vbz * vbz;
-    const double vb2 = vxz2 + vby * vby;
     if (aero || want_diag) {
         /* Mach-table brackets (rocket.py:105-108,156-157): shared by Cd0/Cda, separate knots for CP */
-        double mach = fast_sqrt(mach2);
+        double speed = vb2 * rvb;
+        speed = (vb2 == 0.0 || vb2 > 1.7976931348623157e308) ? vb2 : speed;        /* sqrt(0) = 0, sqrt(inf) = inf */
+        double mach = speed * ya;
         mach = (mach > 1e300) ? 1e300 : mach;     /* +inf clamps like np.interp (right value), NaN stays NaN */
         const int jm = brk_find(Tb.m_lo, Tb.m_hi, M.n_mb, WB.j_m, mach);
         WB.j_m = jm;
         const double cp = M.cp_location + fma(Tb.cp_s[jm], mach - Tb.cp_x0[jm], Tb.cp_f[jm]);
         const double sm = cp - cg;
-        /* utils.py:160-164 */
+        /* utils.py:160-164,167-172: angle of attack and sideslip; their sin/cos (utils.py:194-197) come from the
+         * velocity ratios.  Where any lane of the warp needs the sideslip polynomial (3-D flights: always; planar
+         * flights: never, atan2(+-0, vxz) = +-0) the two angles are evaluated together. */
         const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
-        const double alpha = a_dead ? 0.0 : fast_atan2(vbz, vbx);
+        const double rvxz = fast_rsqrt(vxz2);
+        const double vxz = (vxz2 > 0.0) ? vxz2 * rvxz : vxz2;
+        const bool b_dead = vxz < 1e-6;
+        const bool need_beta = aero && !b_dead && vby != 0.0;
+        double alpha, beta;
+        if (any_lane(need_beta)) {
+            fast_atan2_pair(vbz, vbx, vby, vxz, alpha, beta);
+            alpha = a_dead ? 0.0 : alpha;
+            beta = need_beta ? beta : (b_dead ? 0.0 : vby);
+        } else {
+            alpha = a_dead ? 0.0 : fast_atan2<false, true>(vbz, vbx);      /* not dead: max(|vbx|, |vbz|) >= 1e-6 */
+            beta = b_dead ? 0.0 : vby;
+        }
         if (want_diag) { dg.mach2 = mach2; dg.qdyn = qdyn; dg.abs_aoa = fabs(alpha); dg.stab = sm * M.inv_ref_diam; }
         if (aero) {
-            /* utils.py:167-172 and the sin/cos of utils.py:194-197 from the velocity ratios */
-            const double rvxz = fast_rsqrt(vxz2);
-            const double vxz = (vxz2 > 0.0) ? vxz2 * rvxz : vxz2;
-            const bool b_dead = vxz < 1e-6;
-            double beta = b_dead ? 0.0 : vby;               /* planar flights: atan2(+-0, vxz) = +-0, no polynomial */
-            if (!b_dead && vby != 0.0) beta = fast_atan2(vby, vxz);
-            const double rvb = fast_rsqrt(vb2);
             const double ca = a_dead ? 1.0 : vbx * rvxz, sa = a_dead ? 0.0 : vbz * rvxz;
             const double cb = b_dead ? 1.0 : vxz * rvb, sb = b_dead ? 0.0 : vby * rvb;
 
@@ -599,10 +725,9 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     }
     if (chute) {
         /* :372-377 */
-        const double rrel = fast_rsqrt(vb2);
         if (vb2 > 0.0) {                                   /* rel_speed > 0 (False for NaN) */
             const double drag = (0.5 * rho * vb2 * M.chute_cd) * M.chute_area;
-            const double f = -drag * rrel;
+            const double f = -drag * rvb;
             fbx += f * vbx; fby += f * vby; fbz += f * vbz;
         }
     }
@@ -611,11 +736,12 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     my += -M.pitch_damping * s.wy;
     mz += -M.yaw_damping * s.wz;
 
-    /* :418-425 */
+    /* :418-425  F_inertial = R(q) F_body = F + w tf + v x tf, tf = a x F */
     const double g = gravity(M, s.z);
-    const double fix = r00 * fbx + r01 * fby + r02 * fbz;
-    const double fiy = r10 * fbx + r11 * fby + r12 * fbz;
-    const double fiz = r20 * fbx + r21 * fby + r22 * fbz;
+    const double tfx = ay * fbz - az * fby, tfy = az * fbx - ax * fbz, tfz = ax * fby - ay * fbx;
+    const double fix = fma(-qz, tfy, fma(qy, tfz, fma(qw, tfx, fbx)));
+    const double fiy = fma(-qx, tfz, fma(qz, tfx, fma(qw, tfy, fby)));
+    const double fiz = fma(-qy, tfx, fma(qx, tfy, fma(qw, tfz, fbz)));
     k.x = s.vx; k.y = s.vy; k.z = s.vz;
     k.vx = fix * inv_m; k.vy = fiy * inv_m; k.vz = fma(fiz, inv_m, -g);      /* (F_z - m g)/m */
 
@@ -626,20 +752,20 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     k.wy = (Iyy > 0.0) ? (my - (Ixx - Iyy) * s.wz * s.wx) * inv_Iyy : 0.0;
     k.wz = (Iyy > 0.0) ? (mz - (Iyy - Ixx) * s.wx * s.wy) * inv_Iyy : 0.0;
 
-    /* :439  q_dot = 0.5 * q (x) (0,w) - 0.5*(q.q - 1)*q, utils.py:114-121.  q was normalised above, so q.q - 1 is a
+    /* :439  q_dot = 0.5 * qn (x) (0,w) - 0.5*(qn.qn - 1)*qn with qn = q/|q|, utils.py:114-121.  qn.qn - 1 is a
      * rounding residue (<= 3e-16): its term is 1e-16 of q_dot and, times dt, 1e-3 ulp of q — dropped (a non-finite q
      * makes every product below non-finite as well, so the NaN behaviour is the same). */
-    k.q0 = 0.5 * (-qx * s.wx - qy * s.wy - qz * s.wz);
-    k.q1 = 0.5 * (qw * s.wx + qy * s.wz - qz * s.wy);
-    k.q2 = 0.5 * (qw * s.wy - qx * s.wz + qz * s.wx);
-    k.q3 = 0.5 * (qw * s.wz + qx * s.wy - qy * s.wx);
+    k.q0 = hq * (-qx * s.wx - qy * s.wy - qz * s.wz);
+    k.q1 = hq * (qw * s.wx + qy * s.wz - qz * s.wy);
+    k.q2 = hq * (qw * s.wy - qx * s.wz + qz * s.wx);
+    k.q3 = hq * (qw * s.wz + qx * s.wy - qy * s.wx);
 
-    /* :442-450 propellant; the 10 ms taper test pf/|rate| < 0.01 is written as pf < 0.01*|rate|
-     * (the two branches are continuous at the boundary) */
+    /* :442-450 propellant; the 10 ms taper test pf/|rate| < 0.01 is written as pf < 0.01*|rate| (the two branches are
+     * continuous at the boundary; a zero rate gives 0 and the test fails like the reference's `rate != 0`) */
     double pfr = 0.0;
     if (burning) {
         pfr = S.pf_rate;
-        if (pfr != 0.0 && pf < 0.01 * fabs(pfr)) pfr = -pf * 100.0;
+        if (pf < 0.01 * fabs(pfr)) pfr = -pf * 100.0;
     }
     k.pf = pfr;
 }
@@ -740,13 +866,17 @@ EMC_HD bool track_post_step(const DevModel &M, const Sample &S, TrackHot &K, con
 /* Where a lane keeps its base state s and the RK4 accumulator between stages.  RegStore: registers
  * (host seam, and the register-resident kernel variants).  The flight kernel can instead keep them in
  * shared memory (SharedStore in emc_engine.cu): they are touched only at stage boundaries, and the ~56
- * registers they would pin for the whole derivative are better spent on instruction-level parallelism. */
+ * registers they would pin for the whole derivative are better spent on instruction-level parallelism.
+ * The 14 state words are moved as 7 PAIRS (Pair = 16 bytes: one LDS.128 / STS.128 per pair on the device). */
+struct alignas(16) Pair { double a, b; };
 struct RegStore {
     State s_, a_;
     EMC_HD double s(int i) const { return reinterpret_cast<const double *>(&s_)[i]; }
     EMC_HD void set_s(int i, double v) { reinterpret_cast<double *>(&s_)[i] = v; }
-    EMC_HD double acc(int i) const { return reinterpret_cast<const double *>(&a_)[i]; }
-    EMC_HD void set_acc(int i, double v) { reinterpret_cast<double *>(&a_)[i] = v; }
+    EMC_HD Pair s2(int p) const { Pair r; r.a = s(2 * p); r.b = s(2 * p + 1); return r; }
+    EMC_HD void set_s2(int p, Pair v) { set_s(2 * p, v.a); set_s(2 * p + 1, v.b); }
+    EMC_HD Pair acc2(int p) const { const double *q = reinterpret_cast<const double *>(&a_); Pair r; r.a = q[2 * p]; r.b = q[2 * p + 1]; return r; }
+    EMC_HD void set_acc2(int p, Pair v) { double *q = reinterpret_cast<double *>(&a_); q[2 * p] = v.a; q[2 * p + 1] = v.b; }
 };
 
 template <class Store>
@@ -756,7 +886,7 @@ EMC_HD void store_put(Store &st, const State &s)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 14; ++i) st.set_s(i, p[i]);
+    for (int i = 0; i < 7; ++i) { Pair v; v.a = p[2 * i]; v.b = p[2 * i + 1]; st.set_s2(i, v); }
 }
 template <class Store>
 EMC_HD void store_get(const Store &st, State &s)
@@ -765,7 +895,7 @@ EMC_HD void store_get(const Store &st, State &s)
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 14; ++i) p[i] = st.s(i);
+    for (int i = 0; i < 7; ++i) { const Pair v = st.s2(i); p[2 * i] = v.a; p[2 * i + 1] = v.b; }
 }
 
 /* One classical RK4 step (simulator.py:217-229): the four stages share ONE copy of the derivative.
@@ -788,12 +918,16 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
     const bool chute_keep = K.chute;
     bool chute = chute_keep;
     double chute_time = 0.0;                        /* only read back when a stage of THIS step latches the flag */
+    /* the stage times of this step lie in [t, t + dt]: if the remembered thrust-curve bracket holds both ends, the
+     * four stages skip the bracket test (the time axis is the one table argument that is known in advance) */
+    bool th_safe = false;
+    if (cfg_solid<MK>(M)) { const int j = WB.j_th; th_safe = (K.t >= Tb.th_lo[j]) && (K.t + M.dt < Tb.th_hi[j]); }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int stage = 0; stage < 4; ++stage) {
-        const double ts = K.t + ((stage == 0) ? 0.0 : ((stage == 3) ? M.dt : M.half_dt));   /* warp-uniform offset */
-        derivative<MK, WK>(M, Tb, wind_alt, S, WB, ts, ys, chute, chute_time, k, stage == 0, dg);
+        const double ts = K.t + M.stage_t[stage];      /* warp-uniform offset */
+        derivative<MK, WK>(M, Tb, wind_alt, S, WB, ts, ys, chute, chute_time, k, stage == 0, dg, th_safe);
         if (stage == 0) {
             track_diag(C, ys, dg);                      /* ys == s at stage 0 */
             if (fin) return false;                      /* diagnostic pass only: a latch by this evaluation is dropped */
@@ -801,34 +935,51 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
         if (stage < 3) {
             /* acc = k1 + 2 k2 + 2 k3 (+ k4 below), in the reference's order ((k1 + 2k2) + 2k3) + k4 (:224);
              * next stage state = s + c k  (:218-222) */
-            const double c = (stage == 2) ? M.dt : M.half_dt;
+            const double c = M.stage_c[stage];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int i = 0; i < 14; ++i) y[i] = fma(c, kk[i], st.s(i));
+            for (int i = 0; i < 7; ++i) {
+                const Pair sv = st.s2(i);
+                y[2 * i] = fma(c, kk[2 * i], sv.a); y[2 * i + 1] = fma(c, kk[2 * i + 1], sv.b);
+            }
             if (stage == 0) {                         /* warp-uniform: stage 0 only stores, stages 1-2 accumulate */
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-                for (int i = 0; i < 14; ++i) st.set_acc(i, kk[i]);
+                for (int i = 0; i < 7; ++i) { Pair v; v.a = kk[2 * i]; v.b = kk[2 * i + 1]; st.set_acc2(i, v); }
             } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-                for (int i = 0; i < 14; ++i) st.set_acc(i, fma(2.0, kk[i], st.acc(i)));
+                for (int i = 0; i < 7; ++i) {
+                    Pair v = st.acc2(i);
+                    v.a = fma(2.0, kk[2 * i], v.a); v.b = fma(2.0, kk[2 * i + 1], v.b);
+                    st.set_acc2(i, v);
+                }
             }
         } else {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int i = 0; i < 14; ++i) st.set_s(i, fma(M.dt_over_6, st.acc(i) + kk[i], st.s(i)));
+            for (int i = 0; i < 7; ++i) {
+                const Pair av = st.acc2(i);
+                Pair sv = st.s2(i);
+                sv.a = fma(M.dt_over_6, av.a + kk[2 * i], sv.a); sv.b = fma(M.dt_over_6, av.b + kk[2 * i + 1], sv.b);
+                if (i == 3 || i == 4) { y[2 * i] = sv.a; y[2 * i + 1] = sv.b; }      /* q0..q3: renormalised below */
+                else st.set_s2(i, sv);
+            }
         }
     }
-    /* :227 renormalise */
-    const double q0 = st.s(6), q1 = st.s(7), q2 = st.s(8), q3 = st.s(9);
-    const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
-    if (n2 > 1e-24) { const double rn = fast_rsqrt(n2); st.set_s(6, q0 * rn); st.set_s(7, q1 * rn); st.set_s(8, q2 * rn); st.set_s(9, q3 * rn); }
-    else { st.set_s(6, 1.0); st.set_s(7, 0.0); st.set_s(8, 0.0); st.set_s(9, 0.0); }
+    /* :227 renormalise (q0..q3 = words 6..9 = pairs 3 and 4, still in registers) */
+    {
+        const double q0 = y[6], q1 = y[7], q2 = y[8], q3 = y[9];
+        const double n2 = q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3;
+        Pair u, v;
+        if (n2 > 1e-24) { const double rn = fast_rsqrt(n2); u.a = q0 * rn; u.b = q1 * rn; v.a = q2 * rn; v.b = q3 * rn; }
+        else { u.a = 1.0; u.b = 0.0; v.a = 0.0; v.b = 0.0; }
+        st.set_s2(3, u); st.set_s2(4, v);
+    }
     if (chute != chute_keep) { K.chute = true; C.setd(TC_CHUTE_TIME, chute_time); }
     K.t += M.dt;
     return true;
