@@ -489,7 +489,11 @@ struct StrictTape {
     }
 };
 
-__global__ void __launch_bounds__(128) emc_strict_kernel(KernelArgs a)
+#ifndef EMC_STRICT_BLOCK
+#define EMC_STRICT_BLOCK 128
+#define EMC_STRICT_MINB 1
+#endif
+__global__ void __launch_bounds__(EMC_STRICT_BLOCK, EMC_STRICT_MINB) emc_strict_kernel(KernelArgs a)
 {
     extern __shared__ double alt[];
     __shared__ DevTables Tb;
@@ -938,10 +942,10 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     ctx->counters.kernel_launches = 2;
     if (a.park_on) {
         /* the parked trajectories (their number is only known on the device: a grid that covers the SMs, grid-stride) */
-        int64_t grid = (a.n + 127) / 128;
-        const int64_t cap = (int64_t)ctx->sm_count * 4;
+        int64_t grid = (a.n + EMC_STRICT_BLOCK - 1) / EMC_STRICT_BLOCK;
+        const int64_t cap = (int64_t)ctx->sm_count * (512 / EMC_STRICT_BLOCK);
         if (grid > cap) grid = cap;
-        emc_strict_kernel<<<(unsigned)grid, 128, smem, ctx->stream>>>(a);
+        emc_strict_kernel<<<(unsigned)grid, EMC_STRICT_BLOCK, smem, ctx->stream>>>(a);
         CK(cudaGetLastError());
         ctx->counters.kernel_launches = 3;
     }
