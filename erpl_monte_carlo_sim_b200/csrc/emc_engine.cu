@@ -57,10 +57,16 @@ struct KernelArgs {
     int32_t sm_count, compact;         /* tail compaction (shared-memory variant): collector choice, on/off */
     /* strict continuation: trajectories parked by the flight kernel (emc_strict.cuh) */
     struct ParkRec *park; unsigned long long *park_count; int32_t park_on;
+    /* streaming hand-over to emc_strict_kernel, which runs CONCURRENTLY on a second stream: a record is published by
+     * writing the run's epoch into it after its contents; consumers draw tickets from park_next and wait for their record
+     * or for the flight kernel's last warp (flight_done == flight_warps) */
+    int32_t epoch, flight_warps;
+    unsigned long long *park_next, *flight_done, *strict_err;
 };
 
-/* everything the strict kernel needs to finish a parked trajectory (its sample index is C.i[TI_SAMPLE]) */
-struct ParkRec { State s; TrackHot K; TrackCold C; };
+/* everything the strict kernel needs to finish a parked trajectory (its sample index is C.i[TI_SAMPLE]); `epoch` is
+ * written last (after a fence) and marks the record as belonging to this run */
+struct ParkRec { State s; TrackHot K; TrackCold C; int32_t epoch, pad_; };
 
 /* Stage the run-constant tables into shared memory.  The tables are a STATIC __shared__ object and the wind
  * altitude grid the only dynamic part: objects addressed as shared arrays are read with plain LDS offsets, whereas
@@ -351,6 +357,8 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                 for (int f = 0; f < TC_DCOUNT; ++f) P.C.d[f] = C.getd(f);
                 for (int f = 0; f < TI_ICOUNT; ++f) P.C.i[f] = C.geti(f);
                 P.C.i[TI_SAMPLE] = (int32_t)idx;
+                __threadfence();
+                *reinterpret_cast<volatile int32_t *>(&P.epoch) = a.epoch;       /* publish */
                 active = false;
             } else if (retired) {
                 n_replay += (unsigned long long)rep;
@@ -384,6 +392,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
         if (n_replay) atomicAdd(a.counters + 1, n_replay);
         if (n_refill) atomicAdd(a.counters + 3, n_refill);
         if (n_tape) atomicAdd(a.counters + 7, n_tape);
+        if (a.flight_done) { __threadfence(); atomicAdd(a.flight_done, 1ull); }   /* after every park of this warp */
     }
 }
 
@@ -489,19 +498,43 @@ struct StrictTape {
     }
 };
 
+/* The consumer runs on the context's second stream WHILE the flight kernel flies (64-lane blocks of <= 200 registers fit
+ * next to the three resident flight blocks of an SM): every thread draws a ticket, waits until the record of that number
+ * has been published (or until the last flight warp has left and no such record exists), finishes the flight, draws again.
+ * No flight block ever waits for a consumer, and any flight block can fly any sample (work queue), so the pair cannot
+ * deadlock whatever the order in which the two grids become resident. */
 #ifndef EMC_STRICT_BLOCK
-#define EMC_STRICT_BLOCK 128
-#define EMC_STRICT_MINB 1
+#define EMC_STRICT_BLOCK 64
+#define EMC_STRICT_MINB 5
 #endif
 __global__ void __launch_bounds__(EMC_STRICT_BLOCK, EMC_STRICT_MINB) emc_strict_kernel(KernelArgs a)
 {
     extern __shared__ double alt[];
     __shared__ DevTables Tb;
     stage_tables(Tb, alt, a);
-    const unsigned long long n_parked = *a.park_count;
     unsigned long long steps = 0, replays = 0;
-    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_parked; p += (unsigned long long)gridDim.x * blockDim.x) {
+    const long long t_start = clock64();
+    for (;;) {
+        const unsigned long long p = atomicAdd(a.park_next, 1ull);
+        if (p >= (unsigned long long)a.n) break;                       /* more tickets than samples: nothing can follow */
         ParkRec &P = a.park[p];
+        bool have = false;
+        for (unsigned spin = 0;; ++spin) {
+            if (*reinterpret_cast<volatile int32_t *>(&P.epoch) == a.epoch) { have = true; break; }
+            /* the shared counter is read on every eighth poll only: thousands of waiting threads, one cache line */
+            if ((spin & 7u) == 7u && *reinterpret_cast<volatile unsigned long long *>(a.flight_done) >= (unsigned long long)a.flight_warps) {
+                __threadfence();                                       /* every park precedes its warp's count */
+                have = *reinterpret_cast<volatile int32_t *>(&P.epoch) == a.epoch;
+                break;
+            }
+            __nanosleep(spin < 16 ? 1000 : 8000);
+            if ((spin & 1023u) == 1023u && clock64() - t_start > 40000000000ll) {      /* ~20 s: never on a healthy run */
+                atomicAdd(a.strict_err, 1ull);
+                break;
+            }
+        }
+        if (!have) break;
+        __threadfence();
         const int64_t idx = P.C.i[TI_SAMPLE];
         Sample S;
         load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
@@ -528,6 +561,7 @@ __global__ void __launch_bounds__(EMC_STRICT_BLOCK, EMC_STRICT_MINB) emc_strict_
         }
         steps += (unsigned long long)ns; replays += (unsigned long long)rep;
     }
+    __syncwarp();
     for (int o = 16; o > 0; o >>= 1) {
         steps += __shfl_down_sync(0xffffffffu, steps, o);
         replays += __shfl_down_sync(0xffffffffu, replays, o);
@@ -648,7 +682,8 @@ __global__ void emc_dfma_latency_kernel(double *sink, long long *cycles, int ite
 struct emc_ctx {
     int device = -1;
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, stream2 = nullptr;      /* stream2: the strict consumer, concurrent with the flight kernel */
+    int32_t epoch = 0;                                     /* run counter: publication mark of the park records */
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool has_model = false;
     emc_model model;              /* raw copy (wind_altitudes pointer is NOT valid after set_model) */
@@ -735,6 +770,7 @@ EMC_EXPORT int emc_create(emc_ctx **out, int device)
     memset(&ctx->counters, 0, sizeof ctx->counters);
     e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctrl, 16 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
@@ -759,6 +795,7 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
     cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_summary); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
     for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return EMC_OK;
@@ -827,7 +864,7 @@ static int check_run_args(emc_ctx *ctx, const emc_inputs *in, int64_t n, const e
     return EMC_OK;
 }
 
-static cudaError_t launch_kernel(emc_ctx *ctx, void (*kern)(KernelArgs), int block, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
+static cudaError_t launch_kernel(emc_ctx *ctx, void (*kern)(KernelArgs), int block, KernelArgs &a, size_t smem, int blocks_per_sm_req)
 {
     int occ = 0;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -840,19 +877,20 @@ static cudaError_t launch_kernel(emc_ctx *ctx, void (*kern)(KernelArgs), int blo
     const int64_t need = (a.n + block - 1) / block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
+    a.flight_warps = (int32_t)(grid * (block / 32));      /* what the strict consumer waits for (flight_done) */
     kern<<<(unsigned)grid, block, smem, ctx->stream>>>(a);
     return cudaGetLastError();
 }
 
 template <int BLOCK, int MINB, int COLD>
-static cudaError_t launch_flight(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
+static cudaError_t launch_flight(emc_ctx *ctx, KernelArgs &a, size_t smem, int blocks_per_sm_req)
 {
     return launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD>, BLOCK, a, smem, blocks_per_sm_req);
 }
 
 /* the production instances: motor kind and wind-table presence compiled in */
 template <int BLOCK, int MINB, int COLD>
-static cudaError_t launch_flight_cfg(emc_ctx *ctx, const KernelArgs &a, size_t smem, int blocks_per_sm_req)
+static cudaError_t launch_flight_cfg(emc_ctx *ctx, KernelArgs &a, size_t smem, int blocks_per_sm_req)
 {
     const bool solid = ctx->dmodel.motor_kind == EMC_MOTOR_SOLID, wind = ctx->dmodel.has_wind != 0;
     if (solid) return wind ? launch_kernel(ctx, emc_flight_kernel<BLOCK, MINB, COLD, 1, 1>, BLOCK, a, smem, blocks_per_sm_req)
@@ -905,6 +943,12 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
         CK(cudaGetLastError());
     }
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (a.park_on) {
+        /* the strict consumer starts on the second stream as soon as the inputs and the rail outputs are in place */
+        a.epoch = ++ctx->epoch;
+        a.park_next = ctx->d_ctrl + 12; a.flight_done = ctx->d_ctrl + 13; a.strict_err = ctx->d_ctrl + 14;
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev[1], 0));
+    }
     /* default launch: 128 threads, 3 blocks/SM (159 registers, 12 warps/SM), cold lane state, base state and RK4
      * accumulator in shared memory */
     const int bt = o.block_threads > 0 ? o.block_threads : 128;
@@ -941,12 +985,14 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->counters.kernel_launches = 2;
     if (a.park_on) {
-        /* the parked trajectories (their number is only known on the device: a grid that covers the SMs, grid-stride) */
+        /* one 64-lane consumer block per SM (two where a batch is large), grid-independent: tickets, not indices */
         int64_t grid = (a.n + EMC_STRICT_BLOCK - 1) / EMC_STRICT_BLOCK;
-        const int64_t cap = (int64_t)ctx->sm_count * (512 / EMC_STRICT_BLOCK);
+        const int64_t cap = (int64_t)ctx->sm_count * (a.n > 400000 ? 2 : 1);
         if (grid > cap) grid = cap;
-        emc_strict_kernel<<<(unsigned)grid, EMC_STRICT_BLOCK, smem, ctx->stream>>>(a);
+        emc_strict_kernel<<<(unsigned)grid, EMC_STRICT_BLOCK, smem, ctx->stream2>>>(a);
         CK(cudaGetLastError());
+        CK(cudaEventRecord(ctx->ev[3], ctx->stream2));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
         ctx->counters.kernel_launches = 3;
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
@@ -966,6 +1012,7 @@ static int finish_counters(emc_ctx *ctx)
     ctx->counters.handovers = (int64_t)h[9];
     ctx->counters.strict_steps = (int64_t)h[10];
     ctx->counters.parked = (int64_t)h[11];
+    if (h[14]) return fail(ctx, EMC_ERR_CUDA, "strict continuation: a consumer gave up waiting for the flight kernel");
     float ms = 0.f;
     if (ctx->counters.kernel_launches) {
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->counters.rail_ms = ms;
