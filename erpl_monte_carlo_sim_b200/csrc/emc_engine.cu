@@ -27,6 +27,9 @@
 #include <new>
 #include <string>
 
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include "emc_model_build.h"
 #include "emc_strict.cuh"
 #include "emc_stats.cuh"
@@ -59,9 +62,10 @@ struct KernelArgs {
     struct ParkRec *park; unsigned long long *park_count; int32_t park_on;
     /* streaming hand-over to emc_strict_kernel, which runs CONCURRENTLY on a second stream: a record is published by
      * writing the run's epoch into it after its contents; consumers draw tickets from park_next and wait for their record
-     * or for the flight kernel's last warp (flight_done == flight_warps) */
+     * or until no flight warp can publish any more: the sample queue is exhausted and every warp that has
+     * started has finished (flight_started == flight_done; blocks that become resident later find the queue empty) */
     int32_t epoch, flight_warps;
-    unsigned long long *park_next, *flight_done, *strict_err;
+    unsigned long long *park_next, *flight_started, *flight_done, *strict_err;
 };
 
 /* everything the strict kernel needs to finish a parked trajectory (its sample index is C.i[TI_SAMPLE]); `epoch` is
@@ -214,6 +218,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
     const int warp = threadIdx.x >> 5;
     const bool compact = COMPACT;
     const bool collector = compact && (warp == (int)((blockIdx.x / (unsigned)a.sm_count) % NW));
+    if (a.flight_started && lane == 0) atomicAdd(a.flight_started, 1ull);        /* before this warp's first claim on the queue */
     bool opened = false;          /* collector: `reserved` switched from "closed" to its own lane count */
     int taken = 0, last_cnt = 33; /* collector: board entries adopted; donor: active count at the last donation attempt */
 
@@ -498,69 +503,79 @@ struct StrictTape {
     }
 };
 
-/* The consumer runs on the context's second stream WHILE the flight kernel flies (64-lane blocks of <= 200 registers fit
- * next to the three resident flight blocks of an SM): every thread draws a ticket, waits until the record of that number
- * has been published (or until the last flight warp has left and no such record exists), finishes the flight, draws again.
- * No flight block ever waits for a consumer, and any flight block can fly any sample (work queue), so the pair cannot
- * deadlock whatever the order in which the two grids become resident. */
+/* The strict continuation runs on the context's second stream WHILE the flight kernel flies (one 64-lane block of <= 168
+ * registers and no shared memory per SM fits next to the three resident flight blocks): every thread draws a ticket,
+ * waits until the record of that number has been published — or until none can be published any more —, claims it
+ * (epoch -> -epoch), finishes the flight, draws again.
+ *   - Termination does not depend on flight blocks that are not resident yet (they would wait for the consumers'
+ *     resources in turn): once the sample queue is exhausted, parks can only come from warps that have already started.
+ *   - A consumer never has to succeed: a thread that has waited too long (no flight warp running anywhere after 20 ms —
+ *     the two grids did not become co-resident —, or 2 s in any case) simply leaves.  Whatever is still unclaimed when
+ *     the flight kernel has finished is swept by a second, ordinary launch of the same code on the main stream
+ *     (emc_strict_tail_kernel: usually nothing).  So the pair cannot deadlock and cannot lose a record. */
 #ifndef EMC_STRICT_BLOCK
 #define EMC_STRICT_BLOCK 64
 #define EMC_STRICT_MINB 5
 #endif
-__global__ void __launch_bounds__(EMC_STRICT_BLOCK, EMC_STRICT_MINB) emc_strict_kernel(KernelArgs a)
+__device__ __forceinline__ bool no_more_parks(const KernelArgs &a)
 {
-    extern __shared__ double alt[];
-    __shared__ DevTables Tb;
-    stage_tables(Tb, alt, a);
-    unsigned long long steps = 0, replays = 0;
-    const long long t_start = clock64();
-    for (;;) {
-        const unsigned long long p = atomicAdd(a.park_next, 1ull);
-        if (p >= (unsigned long long)a.n) break;                       /* more tickets than samples: nothing can follow */
-        ParkRec &P = a.park[p];
-        bool have = false;
-        for (unsigned spin = 0;; ++spin) {
-            if (*reinterpret_cast<volatile int32_t *>(&P.epoch) == a.epoch) { have = true; break; }
-            /* the shared counter is read on every eighth poll only: thousands of waiting threads, one cache line */
-            if ((spin & 7u) == 7u && *reinterpret_cast<volatile unsigned long long *>(a.flight_done) >= (unsigned long long)a.flight_warps) {
-                __threadfence();                                       /* every park precedes its warp's count */
-                have = *reinterpret_cast<volatile int32_t *>(&P.epoch) == a.epoch;
-                break;
-            }
-            __nanosleep(spin < 16 ? 1000 : 8000);
-            if ((spin & 1023u) == 1023u && clock64() - t_start > 40000000000ll) {      /* ~20 s: never on a healthy run */
-                atomicAdd(a.strict_err, 1ull);
-                break;
-            }
-        }
-        if (!have) break;
-        __threadfence();
-        const int64_t idx = P.C.i[TI_SAMPLE];
-        Sample S;
-        load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
-        TrackHot K = P.K;
-        const ColdStruct C(P.C);
-        double st[14];
-        memcpy(st, &P.s, sizeof st);
-        int64_t ns = 0;
-        const StrictTape tape = { &a, C };
-        const int64_t rep = strict_fly(c_model, Tb, alt, S, K, C, st, a.nan_ff != 0, &ns, tape);
-        State s;
-        memcpy(&s, st, sizeof s);
-        write_flight_outputs(K, C, s, a.out + idx, a.iout + idx, a.old);
-        if (a.tape_n) *a.tape_n = (int64_t)K.n_steps + 1 - rep;
-        if (a.bt_slot) {
-            const int32_t slot = C.geti(TI_BT_SLOT);
-            if (slot >= 0) {
-                const int32_t last = K.n_steps - (int32_t)rep;
-                int32_t rows = last / a.bt_stride + 1;
-                if (rep == 0 && last % a.bt_stride != 0) { bt_write(a, slot, rows, K.t - K.t_rail, s.x, s.y, s.z); ++rows; }
-                a.bt_count[slot] = rows;
-                atomicAdd(a.counters + 7, (unsigned long long)(rows < a.bt_max ? rows : a.bt_max));
-            }
-        }
-        steps += (unsigned long long)ns; replays += (unsigned long long)rep;
+    /* order matters: queue, then finished, then started (equality then proves that every warp started by the last read
+     * had finished by the second, and a warp that starts later finds no sample) */
+    if (*reinterpret_cast<volatile unsigned long long *>(a.queue) < (unsigned long long)a.n) return false;
+    __threadfence();
+    const unsigned long long fin = *reinterpret_cast<volatile unsigned long long *>(a.flight_done);
+    __threadfence();
+    const unsigned long long sta = *reinterpret_cast<volatile unsigned long long *>(a.flight_started);
+    return sta == fin;
+}
+
+/* finish the parked flight of record P (already claimed by the caller) */
+__device__ __noinline__ void finish_parked(const KernelArgs &a, ParkRec &P, unsigned long long &steps, unsigned long long &replays)
+{
+    /* tables and altitude grid are read where they are (constant bank, global memory): a consumer block must not take
+     * shared memory from the flight blocks it runs beside */
+    const DevTables &Tb = c_tables;
+    const double *alt = a.wind_alt;
+    /* The record is read with L2 loads into a private copy.  Records are not cache-line aligned: a neighbour on this SM
+     * that read record p - 1 may have pulled the line holding the head of record p into L1 BEFORE that record was
+     * written, and L1 is not coherent. */
+    ParkRec R;
+    {
+        static_assert(sizeof(ParkRec) % 8 == 0, "ParkRec is copied word by word");
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&P);
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(&R);
+        for (int w = 0; w < (int)(sizeof(ParkRec) / 8); ++w) dst[w] = __ldcg(src + w);
     }
+    const int64_t idx = R.C.i[TI_SAMPLE];
+    if (idx < 0 || idx >= a.n) { atomicAdd(a.strict_err, 1ull); return; }      /* not a record of this run: refuse */
+    Sample S;
+    load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, S);
+    TrackHot K = R.K;
+    const ColdStruct C(R.C);
+    double st[14];
+    memcpy(st, &R.s, sizeof st);
+    int64_t ns = 0;
+    const StrictTape tape = { &a, C };
+    const int64_t rep = strict_fly(c_model, Tb, alt, S, K, C, st, a.nan_ff != 0, &ns, tape);
+    State s;
+    memcpy(&s, st, sizeof s);
+    write_flight_outputs(K, C, s, a.out + idx, a.iout + idx, a.old);
+    if (a.tape_n) *a.tape_n = (int64_t)K.n_steps + 1 - rep;
+    if (a.bt_slot) {
+        const int32_t slot = C.geti(TI_BT_SLOT);
+        if (slot >= 0) {
+            const int32_t last = K.n_steps - (int32_t)rep;
+            int32_t rows = last / a.bt_stride + 1;
+            if (rep == 0 && last % a.bt_stride != 0) { bt_write(a, slot, rows, K.t - K.t_rail, s.x, s.y, s.z); ++rows; }
+            a.bt_count[slot] = rows;
+            atomicAdd(a.counters + 7, (unsigned long long)(rows < a.bt_max ? rows : a.bt_max));
+        }
+    }
+    steps += (unsigned long long)ns; replays += (unsigned long long)rep;
+}
+
+__device__ __forceinline__ void strict_counts(const KernelArgs &a, unsigned long long steps, unsigned long long replays)
+{
     __syncwarp();
     for (int o = 16; o > 0; o >>= 1) {
         steps += __shfl_down_sync(0xffffffffu, steps, o);
@@ -570,6 +585,54 @@ __global__ void __launch_bounds__(EMC_STRICT_BLOCK, EMC_STRICT_MINB) emc_strict_
         if (steps) atomicAdd(a.counters + 9, steps);
         if (replays) atomicAdd(a.counters + 1, replays);
     }
+}
+
+__global__ void __launch_bounds__(EMC_STRICT_BLOCK, EMC_STRICT_MINB) emc_strict_kernel(KernelArgs a)
+{
+    unsigned long long steps = 0, replays = 0;
+    const long long t_start = clock64();
+    for (;;) {
+        const unsigned long long p = atomicAdd(a.park_next, 1ull);
+        if (p >= (unsigned long long)a.n) break;                       /* more tickets than samples: nothing can follow */
+        ParkRec &P = a.park[p];
+        bool have = false;
+        for (unsigned spin = 0;; ++spin) {
+            if (*reinterpret_cast<volatile int32_t *>(&P.epoch) == a.epoch) { have = true; break; }
+            /* the shared counters are read on every eighth poll only: thousands of waiting threads, three cache lines */
+            if ((spin & 7u) == 7u) {
+                if (no_more_parks(a)) {
+                    __threadfence();                                   /* every park precedes its warp's count */
+                    have = *reinterpret_cast<volatile int32_t *>(&P.epoch) == a.epoch;
+                    break;
+                }
+                const long long waited = clock64() - t_start;
+                const bool nobody = *reinterpret_cast<volatile unsigned long long *>(a.flight_started) == 0ull;
+                if ((nobody && waited > 40000000ll) || waited > 4000000000ll) {       /* ~20 ms / ~2 s: leave it to the sweep */
+                    atomicAdd(a.strict_err + 1, 1ull);                 /* counted (d_ctrl[15 + ...]), not an error */
+                    break;
+                }
+            }
+            __nanosleep(spin < 16 ? 1000 : 8000);
+        }
+        if (!have) break;
+        __threadfence();
+        *reinterpret_cast<volatile int32_t *>(&P.epoch) = -a.epoch;    /* claimed */
+        finish_parked(a, P, steps, replays);
+    }
+    strict_counts(a, steps, replays);
+}
+
+/* the sweep after the flight kernel: every record that is published and not claimed */
+__global__ void __launch_bounds__(EMC_STRICT_BLOCK, EMC_STRICT_MINB) emc_strict_tail_kernel(KernelArgs a)
+{
+    unsigned long long steps = 0, replays = 0;
+    const unsigned long long n_parked = *a.park_count;
+    for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_parked; p += (unsigned long long)gridDim.x * blockDim.x) {
+        ParkRec &P = a.park[p];
+        if (__ldcg(&P.epoch) != a.epoch) continue;
+        finish_parked(a, P, steps, replays);
+    }
+    strict_counts(a, steps, replays);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -684,6 +747,7 @@ struct emc_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;      /* stream2: the strict consumer, concurrent with the flight kernel */
     int32_t epoch = 0;                                     /* run counter: publication mark of the park records */
+    int64_t strict_left_early = 0;                         /* concurrent consumers that gave up waiting in the last run (their records went to the sweep) */
     cudaEvent_t ev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
     bool has_model = false;
     emc_model model;              /* raw copy (wind_altitudes pointer is NOT valid after set_model) */
@@ -725,6 +789,7 @@ static thread_local std::string g_create_err;
 
 /* c_model / c_tables are per-device globals shared by every context on that device: remember which context uploaded
  * last and re-upload (after draining the device) when another one is about to launch. */
+static std::atomic<int32_t> g_epoch{0};      /* run counter of the process: publication mark of the park records (never 0) */
 static std::mutex g_owner_mu;
 static emc_ctx *g_owner[64] = { nullptr };
 
@@ -772,7 +837,7 @@ EMC_EXPORT int emc_create(emc_ctx **out, int device)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
-    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctrl, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&ctx->d_ctrl, 32 * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         std::string m = std::string("emc_create: ") + cudaGetErrorString(e);
         delete ctx;
@@ -877,7 +942,7 @@ static cudaError_t launch_kernel(emc_ctx *ctx, void (*kern)(KernelArgs), int blo
     const int64_t need = (a.n + block - 1) / block;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    a.flight_warps = (int32_t)(grid * (block / 32));      /* what the strict consumer waits for (flight_done) */
+    a.flight_warps = (int32_t)(grid * (block / 32));      /* diagnostic only: the consumer compares flight_started with flight_done */
     kern<<<(unsigned)grid, block, smem, ctx->stream>>>(a);
     return cudaGetLastError();
 }
@@ -910,7 +975,11 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     a.compact = (o.flags & EMC_RUN_COMPACTION) ? 1 : 0;
     a.park_on = (o.flags & EMC_RUN_NO_STRICT_TAIL) ? 0 : 1;
     if (a.park_on && a.n > 0) {
+        const size_t cap_before = ctx->cap_park;
         CK(grow(&ctx->d_park, &ctx->cap_park, (size_t)a.n));
+        /* fresh device memory may be a recycled park buffer of ANOTHER context of this process: clear the publication marks
+         * (the epochs themselves come from one process-wide counter, so a stale mark can never equal a later run's) */
+        if (ctx->cap_park != cap_before) CK(cudaMemsetAsync(ctx->d_park, 0, sizeof(ParkRec) * ctx->cap_park, ctx->stream));
         a.park = ctx->d_park; a.park_count = ctx->d_ctrl + 11;
     }
     a.wind_alt = ctx->d_wind_alt;
@@ -919,7 +988,7 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     if (!ctx->dmodel.has_wind) { a.wind = nullptr; a.wind_stride = 0; }
     const size_t smem = smem_bytes(ctx->dmodel.n_wind);
     if (int rc = make_resident(ctx)) return rc;
-    CK(cudaMemsetAsync(ctx->d_ctrl, 0, 16 * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_ctrl, 0, 32 * sizeof(unsigned long long), ctx->stream));
     memset(&ctx->counters, 0, sizeof ctx->counters);
     if (a.n == 0) return EMC_OK;
     if (ctx->bt_armed && !a.tape) {
@@ -945,8 +1014,8 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     CK(cudaEventRecord(ctx->ev[1], ctx->stream));
     if (a.park_on) {
         /* the strict consumer starts on the second stream as soon as the inputs and the rail outputs are in place */
-        a.epoch = ++ctx->epoch;
-        a.park_next = ctx->d_ctrl + 12; a.flight_done = ctx->d_ctrl + 13; a.strict_err = ctx->d_ctrl + 14;
+        a.epoch = ctx->epoch = ++g_epoch;
+        a.park_next = ctx->d_ctrl + 12; a.flight_done = ctx->d_ctrl + 13; a.strict_err = ctx->d_ctrl + 14; a.flight_started = ctx->d_ctrl + 18;      /* d_ctrl[15]: consumers that left early */
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev[1], 0));
     }
     /* default launch: 128 threads, 3 blocks/SM (159 registers, 12 warps/SM), cold lane state, base state and RK4
@@ -985,15 +1054,26 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     CK(cudaEventRecord(ctx->ev[2], ctx->stream));
     ctx->counters.kernel_launches = 2;
     if (a.park_on) {
-        /* one 64-lane consumer block per SM (two where a batch is large), grid-independent: tickets, not indices */
+        /* one 64-lane consumer block per SM (registers: 3 x 128 x 136 + 64 x 168 <= 65 536; no shared memory): tickets,
+         * not indices, so the grid is independent of the batch */
         int64_t grid = (a.n + EMC_STRICT_BLOCK - 1) / EMC_STRICT_BLOCK;
-        const int64_t cap = (int64_t)ctx->sm_count * (a.n > 400000 ? 2 : 1);
-        if (grid > cap) grid = cap;
-        emc_strict_kernel<<<(unsigned)grid, EMC_STRICT_BLOCK, smem, ctx->stream2>>>(a);
+        if (grid > ctx->sm_count) grid = ctx->sm_count;
+        /* same shared-memory carve-out as the flight kernel: an SM cannot change its carve-out while blocks are resident, so
+         * a consumer block that arrived first with a small one would keep the flight blocks of that SM out until it leaves */
+        static bool carve_set = false;
+        if (!carve_set) {
+            CK(cudaFuncSetAttribute(emc_strict_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            CK(cudaFuncSetAttribute(emc_strict_tail_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            carve_set = true;
+        }
+        emc_strict_kernel<<<(unsigned)grid, EMC_STRICT_BLOCK, 0, ctx->stream2>>>(a);
         CK(cudaGetLastError());
         CK(cudaEventRecord(ctx->ev[3], ctx->stream2));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev[3], 0));
-        ctx->counters.kernel_launches = 3;
+        /* the sweep: what the concurrent consumers left behind (normally nothing: one look at each record's mark) */
+        emc_strict_tail_kernel<<<(unsigned)(2 * ctx->sm_count), EMC_STRICT_BLOCK, 0, ctx->stream>>>(a);
+        CK(cudaGetLastError());
+        ctx->counters.kernel_launches = 4;
     }
     CK(cudaEventRecord(ctx->ev[4], ctx->stream));
     return EMC_OK;
@@ -1001,7 +1081,7 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
 
 static int finish_counters(emc_ctx *ctx)
 {
-    unsigned long long h[16];
+    unsigned long long h[32];
     CK(cudaMemcpyAsync(h, ctx->d_ctrl, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->counters.rk4_steps = (int64_t)h[1];
@@ -1012,7 +1092,10 @@ static int finish_counters(emc_ctx *ctx)
     ctx->counters.handovers = (int64_t)h[9];
     ctx->counters.strict_steps = (int64_t)h[10];
     ctx->counters.parked = (int64_t)h[11];
-    if (h[14]) return fail(ctx, EMC_ERR_CUDA, "strict continuation: a consumer gave up waiting for the flight kernel");
+    if (h[14]) return fail(ctx, EMC_ERR_CUDA, "strict continuation: " + std::to_string(h[14]) + " park records do not belong to this run (epoch " +
+                           std::to_string(ctx->epoch) + ", parked " + std::to_string(h[11]) + ", tickets " + std::to_string(h[12]) + ")");
+    ctx->strict_left_early = (int64_t)h[15];
+    if (h[15] && getenv("EMC_DEBUG")) fprintf(stderr, "[emc] %llu strict consumers left early (their records were swept after the flight kernel)\n", h[15]);
     float ms = 0.f;
     if (ctx->counters.kernel_launches) {
         CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); ctx->counters.rail_ms = ms;

@@ -192,7 +192,8 @@ typedef struct emc_counters {
     int64_t handovers;        /* ABI 2: trajectories handed to a collector warp by the tail compaction (EMC_RUN_COMPACTION) */
     int64_t parked;           /* ABI 2: trajectories finished by the strict continuation (blow-up under way; csrc/emc_strict.cuh) */
     int64_t strict_steps;     /* ABI 2: RK4 steps taken there (not included in rk4_steps) */
-    double strict_ms;         /* ABI 2: device time of emc_strict_kernel */
+    double strict_ms;         /* ABI 2: device time between the end of the flight kernel and the end of the strict continuation (it runs
+                               * concurrently on a second stream: normally the cost of the final sweep only) */
 } emc_counters;
 
 int emc_abi_version(void);
