@@ -105,6 +105,7 @@ def load():
     L.emc_extract_series.argtypes = [vp, C.POINTER(_abi.EmcInputs), _dp, i64, _dp]
     L.emc_extract_series.restype = C.c_int
     L.emc_resident_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
+    L.emc_fetch_outputs.argtypes = [vp, i64, C.POINTER(_abi.EmcOutputs)]
     L.emc_resident_outputs.restype = C.c_int
     L.emc_upload_outputs.argtypes = [vp, vp, i64, i64]
     L.emc_upload_outputs.restype = C.c_int
@@ -187,6 +188,7 @@ class Engine:
     def run_batch(self, scalars, wind=None, opts=None, wind_shared=False, outputs=None):
         """scalars [IN_COUNT][n] float64, wind [n][N][3] (or [N][3] with wind_shared) -> (out, iout).
         `outputs=(out, iout)` lets the caller supply (e.g. pinned) result arrays."""
+        self._spill_pending()
         scalars = np.ascontiguousarray(scalars, np.float64)
         n = scalars.shape[1]
         w = None
@@ -266,9 +268,28 @@ class Engine:
                                               d.ctypes.data_as(_dp)), "emc_numpy_draws")
         return g, u, d
 
+    def fetch_outputs(self, n):
+        """(out, iout) of the last batch run of n samples, downloaded from the context's resident blocks."""
+        outs, out, iout = _abi.outputs_alloc(n)
+        self._check(self._lib.emc_fetch_outputs(self._ctx, n, C.byref(outs)), "emc_fetch_outputs")
+        return out, iout
+
+    def _spill_pending(self):
+        """A batch whose outputs exist only in HBM (BatchRun with lazy outputs) is about to lose them: download first."""
+        ref = getattr(self, "_pending", None)
+        self._pending = None
+        run = ref() if ref is not None else None
+        if run is not None:
+            run.materialize_outputs()
+
+    def hold_outputs_for(self, run):
+        import weakref
+        self._pending = weakref.ref(run)
+
     def run_batch_staged(self, n, opts=None, download=True):
         """Fly the staged samples.  download=False leaves the outputs in HBM only (statistics run there; fetch them later
         with fetch_outputs)."""
+        self._spill_pending()
         if download:
             outs, out, iout = _abi.outputs_alloc(n)
         else:
@@ -363,6 +384,7 @@ class Engine:
         return ptr.value, ld.value
 
     def upload_outputs(self, out):
+        self._spill_pending()
         out = np.ascontiguousarray(out, np.float64)
         assert out.shape[0] == _abi.OUT_COUNT
         self._check(self._lib.emc_upload_outputs(self._ctx, out.ctypes.data, out.shape[1], out.shape[1]), "emc_upload_outputs")

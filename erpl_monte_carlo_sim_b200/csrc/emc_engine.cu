@@ -1475,6 +1475,16 @@ EMC_EXPORT int emc_resident_outputs(emc_ctx *ctx, double **out_dev, int64_t *ld)
 /* ---------------------------------------------------------------------------------------------------
  *  downsampled batch tape (reference monte_carlo.py:296-302 'trajectory')
  * ------------------------------------------------------------------------------------------------- */
+EMC_EXPORT int emc_fetch_outputs(emc_ctx *ctx, int64_t n, const emc_outputs *out)
+{
+    if (!ctx || !out || !out->out || !out->iout || out->ld < n) return fail(ctx, EMC_ERR_INVALID, "emc_fetch_outputs: bad argument");
+    if (!ctx->d_out || !ctx->d_iout || n <= 0 || n != ctx->last_n) return fail(ctx, EMC_ERR_INVALID, "emc_fetch_outputs: the context holds no resident outputs of that size");
+    CK(cudaSetDevice(ctx->device));
+    if (int rc = download_outputs(ctx, out, n, ctx->d_out, ctx->d_iout)) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return EMC_OK;
+}
+
 EMC_EXPORT int emc_tape_request(emc_ctx *ctx, const int64_t *samples, int64_t n_sel, int32_t stride, int32_t max_rows)
 {
     if (!ctx) return EMC_ERR_INVALID;

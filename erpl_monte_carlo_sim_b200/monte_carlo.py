@@ -147,11 +147,21 @@ class SampleResults(Sequence):
     """`analysis['results']` / `analysis['outliers']`: one dict per sample, built on access from the
     engine's SoA summary (the reference materialises every time series of every sample in a list)."""
 
-    def __init__(self, owner, ids, with_reasons=False):
-        self._owner, self._ids, self._with_reasons = owner, np.asarray(ids, np.int64), with_reasons
+    def __init__(self, owner, ids, with_reasons=False, length=None):
+        """ids: index array, or a zero-argument callable that produces it on first use (it needs the outputs on the host);
+        length: the list's length when it is known without them (the device statistics count the valid samples)."""
+        self._owner, self._ids_src, self._with_reasons, self._length = owner, ids, with_reasons, length
+
+    @property
+    def _ids(self):
+        if callable(self._ids_src):
+            self._ids_src = self._ids_src()
+        if not isinstance(self._ids_src, np.ndarray) or self._ids_src.dtype != np.int64:
+            self._ids_src = np.asarray(self._ids_src, np.int64)
+        return self._ids_src
 
     def __len__(self):
-        return len(self._ids)
+        return int(self._length) if self._length is not None else len(self._ids)
 
     @property
     def sample_indices(self):
@@ -172,15 +182,33 @@ class BatchRun:
     """Everything one Monte Carlo batch produced on this rank: dispersions, inputs and the SoA outputs.  `disp` and
     `scalars` may be given as zero-argument callables: the device-generated modes fetch them only when somebody looks."""
 
-    def __init__(self, analyzer, base_ic, disp, out, iout, altitude_profile, scalars, outputs_resident=False, first_id=0):
+    def __init__(self, analyzer, base_ic, disp, out, iout, altitude_profile, scalars, outputs_resident=False, first_id=0,
+                 n=None, engine=None):
         self.analyzer, self.base_ic, self._disp = analyzer, base_ic, disp
-        self.out, self.iout, self.altitude_profile, self._scalars = out, iout, altitude_profile, scalars
+        self._out, self._iout, self.altitude_profile, self._scalars = out, iout, altitude_profile, scalars
         self.outputs_resident = outputs_resident      # the engine still holds these outputs in HBM (single chunk)
         self.first_id = int(first_id)                 # global index (= seed) of local sample 0: rank r of a sharded run
-        self.n = out.shape[1]
+        self.n = int(n) if out is None else out.shape[1]
+        self._engine = engine                         # out is None: the outputs live in this engine's HBM until somebody looks
+        if out is None:
+            engine.hold_outputs_for(self)             # ... or until the engine's next batch would overwrite them
         self.tape_ids = np.zeros(0, np.int64)         # local samples whose downsampled trajectory was recorded
         self.tape_rows = np.zeros((0, 2, _abi.BTAPE_WIDTH)); self.tape_count = np.zeros(0, np.int32); self.tape_stride = 0
         self._tape_pos = {}
+
+    def materialize_outputs(self):
+        if self._out is None:
+            self._out, self._iout = self._engine.fetch_outputs(self.n)
+
+    @property
+    def out(self):
+        self.materialize_outputs()
+        return self._out
+
+    @property
+    def iout(self):
+        self.materialize_outputs()
+        return self._iout
 
     @property
     def disp(self):
@@ -287,6 +315,9 @@ class MonteCarloAnalyzer:
         # the reference stores the whole trajectory of every sample (monte_carlo.py:296-302); the engine records a
         # downsampled tape {t, x, y, z} of the first `trajectory_samples` samples of a run while they fly (every
         # `trajectory_stride`-th stored state = 0.1 s, plus the last one); any other sample is taped on demand
+        self.eager_collectives = True     # torch.distributed jobs: reduce `parameter_ranges_observed` over the ranks inside run_monte_carlo
+                                          # (False: on first access, which then has to happen on every rank; it costs a download of the
+                                          # shard's outputs and parameters, which a statistics-only campaign does not need)
         self.trajectory_samples = 64
         self.trajectory_stride = 20
         # inside an initialised torch.distributed job the samples are sharded over the ranks (rank r flies the seeds
@@ -536,9 +567,9 @@ class MonteCarloAnalyzer:
             ids = self._chunk_tape_ids(lo, hi, tape_ids)
             if ids.size:
                 eng.tape_request(ids, stride, rows_cap)
-            o, io = eng.run_batch_staged(hi - lo, opts=self.run_opts)
+            o, io = eng.run_batch_staged(hi - lo, opts=self.run_opts, download=not single)
             if single:
-                out, iout = o, io
+                out, iout = o, io                    # None: the outputs stay in HBM until somebody looks (BatchRun.out)
             else:
                 out[:, lo:hi] = o; iout[:, lo:hi] = io
             if ids.size:
@@ -558,7 +589,8 @@ class MonteCarloAnalyzer:
                 sc[:, lo:hi] = eng.staged_inputs(hi - lo, want_wind=False)[0]
             return sc
 
-        run = BatchRun(self, dict(initial_conditions), params, out, iout, alts, scalars, outputs_resident=single, first_id=first_index)
+        run = BatchRun(self, dict(initial_conditions), params, out, iout, alts, scalars, outputs_resident=single, first_id=first_index,
+                       n=n, engine=eng)
         run.mode = "numpy-device" if numpy_streams else "philox"
         for ids, rows, cnt in taped:
             run.add_tape(ids, rows, cnt, stride)
@@ -813,10 +845,17 @@ class MonteCarloAnalyzer:
             raise ValueError("No valid simulation results")
         if st["n_samples"] == 0:
             raise ValueError("No physically reasonable simulation results after outlier filtering")
-        ap, rg, ft = run.out[O["apogee_altitude"]], run.out[O["range"]], run.out[O["flight_time"]]
-        bad = self.outlier_mask(ap, rg, ft)                       # per-sample membership for the lazy result lists
-        valid_ids, out_ids = np.flatnonzero(~bad), np.flatnonzero(bad)
+        split_cache = []
+
+        def split():                                             # per-sample membership for the lazy result lists: needs the
+            if not split_cache:                                  # outputs on the host, so it waits until somebody looks
+                ap, rg, ft = run.out[O["apogee_altitude"]], run.out[O["range"]], run.out[O["flight_time"]]
+                bad = self.outlier_mask(ap, rg, ft)
+                split_cache.append((np.flatnonzero(~bad), np.flatnonzero(bad)))
+            return split_cache[0]
+
         def observed_ranges():
+            valid_ids = split()[0]
             d = run.disp
             keys, lo, hi = [], [], []
             for key, arr in (("initial_position_offset", d.pos), ("initial_velocity_offset", d.vel),
@@ -840,7 +879,8 @@ class MonteCarloAnalyzer:
 
         analysis = {"n_samples": st["n_samples"], "n_failed": 0, "n_outliers": st["n_outliers"],
                     "apogee_altitude": st["apogee_altitude"], "range": st["range"], "flight_time": st["flight_time"],
-                    "results": SampleResults(run, valid_ids), "outliers": SampleResults(run, out_ids, with_reasons=True),
+                    "results": SampleResults(run, lambda: split()[0], length=st["n_samples"] if world == 1 else None),
+                    "outliers": SampleResults(run, lambda: split()[1], with_reasons=True, length=st["n_outliers"] if world == 1 else None),
                     # engine extras (not in the reference's dict): device-reduced landing ellipse, reasons, histograms
                     "landing_ellipse": st["landing_ellipse"], "outlier_reason_counts": st["outlier_reasons"]}
         if world > 1:
@@ -848,7 +888,7 @@ class MonteCarloAnalyzer:
         if "histograms" in st:
             analysis["histograms"] = st["histograms"]
         analysis = LazyAnalysis(analysis, {"parameter_ranges_observed": observed_ranges})
-        if world > 1:
+        if world > 1 and self.eager_collectives:
             analysis.materialize()                  # the min/max reduction is a collective: every rank takes part now
         return analysis
 

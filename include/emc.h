@@ -323,6 +323,11 @@ int emc_copy_to_device(emc_ctx *ctx, void *dev, const void *host, int64_t bytes)
  * sub-ranges: pass out_dev + first_sample with the same ld) */
 int emc_resident_outputs(emc_ctx *ctx, double **out_dev, int64_t *ld);
 
+/* download the resident outputs (both blocks) of the last batch run of n samples: what emc_run_batch_staged with NULL
+ * output pointers left in HBM.  The reference returns every sample's result dict (monte_carlo.py:296-302); the package
+ * builds them on access, so a statistics-only campaign never moves the 300 bytes per sample. */
+int emc_fetch_outputs(emc_ctx *ctx, int64_t n, const emc_outputs *out);
+
 /* make a host [EMC_OUT_COUNT][ld] block the context's resident outputs (for statistics over a run that was
  * executed in several chunks) */
 int emc_upload_outputs(emc_ctx *ctx, const double *out_host, int64_t ld, int64_t n);

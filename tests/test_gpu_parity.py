@@ -45,7 +45,7 @@ def test_gpu_mc_sets(engine, name):
     np.testing.assert_array_equal(iout, z["iout"])
     util.assert_summary_close(out, z["out"], what=name)
     c = engine.counters()
-    assert c["kernel_launches"] == 3 and c["refills"] == z["scalars"].shape[1]      # rail, flight, strict continuation
+    assert c["kernel_launches"] == 4 and c["refills"] == z["scalars"].shape[1]      # rail, flight, strict continuation (concurrent consumer + sweep)
     nan_ff = z["iout"][_abi.IOUT["first_nan_step"]] >= 0
     assert c["rk4_steps"] + c["strict_steps"] + c["replay_steps"] == int(z["iout"][0].sum())
     assert (c["replay_steps"] > 0) == bool(nan_ff.any())
