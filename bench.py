@@ -227,8 +227,10 @@ def secondary_measurements(eng, opts, peak_tf, rank, world, dev, barrier, n_plan
             an = mc.run_monte_carlo(IC_C4, n_samples=n_c4 * world)
             barrier(); wall = time.perf_counter() - t0
             c = eng_counters_of(mc)
+            keep = {k: an[k] for k in ("n_samples", "n_outliers", "apogee_altitude", "landing_ellipse")}
+            an = None; mc.last_run = None         # drop the batch: its outputs were never asked for, nothing is downloaded
             if best is None or wall < best[1]:
-                best = (c, wall, an)
+                best = (c, wall, keep)
         an = best[2]
         out["c4"] = kernel_line("C4: LiquidMotor, default dispersions, 100-knot stochastic wind per sample, Philox draws on the device, "
                                 "MonteCarloAnalyzer.run_monte_carlo sharded over the ranks, NCCL-reduced statistics", n_c4, best[0], best[1], {
@@ -258,7 +260,9 @@ def api_end_to_end(n_total, rank, world, barrier, opts):
         mc = c3_analyzer()
         mc.rng = mode; mc.host_rng_max = 1 << 40; mc.run_opts = opts
         best = None
+        an = None
         for rep in range(3 if mode != "numpy" else 1):
+            an = None; mc.last_run = None         # a campaign whose per-sample results were not read leaves nothing to download
             barrier(); t0 = time.perf_counter()
             an = mc.run_monte_carlo(IC_C3, n_samples=n)
             barrier(); dt = time.perf_counter() - t0
