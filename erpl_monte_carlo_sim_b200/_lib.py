@@ -106,6 +106,16 @@ def load():
     L.emc_extract_series.restype = C.c_int
     L.emc_resident_outputs.argtypes = [vp, C.POINTER(vp), C.POINTER(i64)]
     L.emc_fetch_outputs.argtypes = [vp, i64, C.POINTER(_abi.EmcOutputs)]
+    L.emc_group_create.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.emc_group_destroy.argtypes = [vp]
+    L.emc_group_last_error.restype = C.c_char_p
+    L.emc_group_last_error.argtypes = [vp]
+    L.emc_group_size.argtypes = [vp]
+    L.emc_group_set_model.argtypes = [vp, C.POINTER(_abi.EmcModel)]
+    L.emc_group_run_batch.argtypes = [vp, C.POINTER(_abi.EmcInputs), i64, C.POINTER(_abi.EmcOutputs), C.POINTER(_abi.EmcRunOpts)]
+    L.emc_group_shard.argtypes = [vp, C.c_int, C.POINTER(i64), C.POINTER(i64)]
+    L.emc_group_stats_summary.argtypes = [vp, _dp, C.c_int, _dp]
+    L.emc_group_get_counters.argtypes = [vp, C.POINTER(_abi.EmcCounters)]
     L.emc_resident_outputs.restype = C.c_int
     L.emc_upload_outputs.argtypes = [vp, vp, i64, i64]
     L.emc_upload_outputs.restype = C.c_int
@@ -403,3 +413,74 @@ class Engine:
         tf, ms = C.c_double(), C.c_double()
         self._check(self._lib.emc_fp64_peak(self._ctx, C.byref(tf), C.byref(ms)), "emc_fp64_peak")
         return tf.value, ms.value
+
+
+class EngineGroup:
+    """emc_group: several GPUs of one box driven from this ONE process through the C ABI alone (no torch): contiguous sample
+    shards flown concurrently, statistics of the whole job reduced with NCCL all-reduces inside libemc.so.  (Jobs launched
+    with torchrun use one Engine per rank and torch.distributed instead; see stats.py.)"""
+
+    def __init__(self, devices):
+        self._lib = load()
+        self._g = C.c_void_p()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        rc = self._lib.emc_group_create(C.byref(self._g), devs, len(devices))
+        if rc != 0:
+            msg = self._lib.emc_group_last_error(None).decode()
+            self._g = C.c_void_p()
+            raise EmcError(f"emc_group_create failed ({_abi.STATUS.get(rc, rc)}): {msg}")
+        self.devices = [int(d) for d in devices]
+        self._model_keep = None
+
+    def close(self):
+        if getattr(self, "_g", None) and self._g.value:
+            self._lib.emc_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EmcError(f"{what} failed ({_abi.STATUS.get(rc, rc)}): {self._lib.emc_group_last_error(self._g).decode()}")
+
+    def set_model(self, md: dict):
+        m, keep = _abi.pack_model(md)
+        self._check(self._lib.emc_group_set_model(self._g, C.byref(m)), "emc_group_set_model")
+        self._model_keep = (m, keep)
+        self.has_wind = bool(m.has_wind)
+
+    def run_batch(self, scalars, wind=None, opts=None):
+        """scalars [IN_COUNT][n], wind [n][N][3] -> (out, iout) of all n samples; the shards stay resident per device."""
+        scalars = np.ascontiguousarray(scalars, np.float64)
+        n = scalars.shape[1]
+        w = np.ascontiguousarray(wind, np.float64) if (self.has_wind and wind is not None) else None
+        ins = _abi.inputs_struct(scalars, w, wind_shared=(w is not None and w.ndim == 2))
+        outs, out, iout = _abi.outputs_alloc(n)
+        self._check(self._lib.emc_group_run_batch(self._g, C.byref(ins), n, C.byref(outs), C.byref(opts) if opts is not None else None),
+                    "emc_group_run_batch")
+        return out, iout
+
+    def shards(self):
+        res = []
+        for i in range(len(self.devices)):
+            a, b = C.c_int64(), C.c_int64()
+            self._lib.emc_group_shard(self._g, i, C.byref(a), C.byref(b))
+            res.append((a.value, b.value))
+        return res
+
+    def stats_summary(self, percentiles=(5, 25, 50, 75, 95)):
+        """Raw result block of emc_stats_summary over the whole job: sum[14] | min[3] | max[3] | s2[6] | means[5] | 0 | val[3][2 n_pct]."""
+        npct = len(percentiles)
+        pct = (C.c_double * npct)(*[float(p) for p in percentiles])
+        res = np.empty(32 + 3 * 2 * npct, np.float64)
+        self._check(self._lib.emc_group_stats_summary(self._g, pct, npct, res.ctypes.data_as(_dp)), "emc_group_stats_summary")
+        return res
+
+    def counters(self) -> dict:
+        c = _abi.EmcCounters()
+        self._lib.emc_group_get_counters(self._g, C.byref(c))
+        return {k: getattr(c, k) for k, _ in _abi.EmcCounters._fields_}

@@ -1823,3 +1823,6 @@ EMC_EXPORT int emc_fp64_peak(emc_ctx *ctx, double *tflops, double *ms_out)
     if (ms_out) *ms_out = best;
     return EMC_OK;
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+#include "emc_group.inl"

@@ -370,6 +370,29 @@ int emc_stream(emc_ctx *ctx, void **stream);
 int emc_stats_linear_hist(emc_ctx *ctx, const double *out_dev, int64_t ld, int64_t n, int field, double lo, double hi,
                           int nbins, uint64_t *hist_dev /*[nbins], zeroed by the call*/);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Several GPUs of one box from ONE host process, without torch (ABI 2).  The reference fans samples out over a process pool
+ * (rocket_simulation/monte_carlo.py:63-83) and analyses the gathered list in the parent (:337-473); a group owns one
+ * context per device, cuts [0, n) into contiguous shards (np.array_split's sizes), flies them concurrently (one host
+ * thread per device inside the call) and reduces the statistics with NCCL all-reduces of the small blocks between the
+ * stages of emc_stats_summary_stage, on the devices' streams.  NCCL (libnccl.so.2) is loaded with dlopen by the first
+ * group of more than one device.  Python jobs under torchrun use one context per rank and torch.distributed instead
+ * (erpl_monte_carlo_sim_b200/stats.py); both drive the same staged chain.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct emc_group emc_group;
+int emc_group_create(emc_group **out, const int *devices, int n_dev);
+int emc_group_destroy(emc_group *g);
+const char *emc_group_last_error(const emc_group *g);            /* g NULL: the last emc_group_create failure of this thread */
+int emc_group_size(const emc_group *g);
+emc_ctx *emc_group_context(emc_group *g, int i);                 /* the i-th device's context (owned by the group) */
+int emc_group_set_model(emc_group *g, const emc_model *model);
+/* host buffers as in emc_run_batch, covering all n samples; every device's shard stays resident in its HBM */
+int emc_group_run_batch(emc_group *g, const emc_inputs *in, int64_t n, const emc_outputs *out, const emc_run_opts *opts);
+int emc_group_shard(const emc_group *g, int i, int64_t *first, int64_t *count);       /* shard of device i in the last run */
+/* statistics of the WHOLE job over the resident shards; result laid out as in emc_stats_summary */
+int emc_group_stats_summary(emc_group *g, const double *percentiles, int n_pct, double *result);
+int emc_group_get_counters(const emc_group *g, emc_counters *c);  /* sums over the devices; the times are maxima */
+
 /* Component evaluation on arrays (the model-evaluation helpers of the reference's parameter classes, run on the device;
  * also the component known-answer test seam).  in[k][n] / out[k][n] are HOST, field-major.
  *   EMC_COMP_ATMOSPHERE  in: altitude                          out: temperature, pressure, density, speed_of_sound, gravity

@@ -192,6 +192,50 @@ def test_device_generated_batch_keeps_its_outputs_in_hbm_until_read():
     assert [len(a1["results"]), len(a1["outliers"])] == [a1["n_samples"], a1["n_outliers"]]
 
 
+def _raw_summary(engine, n, pcts):
+    import ctypes as C
+    pct = (C.c_double * len(pcts))(*[float(p) for p in pcts])
+    res = np.empty(32 + 6 * len(pcts))
+    engine._check(engine._lib.emc_stats_summary(engine._ctx, None, 0, n, pct, len(pcts), res.ctypes.data_as(C.POINTER(C.c_double))), "emc_stats_summary")
+    return res
+
+
+@pytest.mark.parametrize("n_dev", [1, 2])
+def test_device_group_through_the_c_abi(engine, n_dev):
+    """emc_group (torch-free multi-device path of the C ABI): the shards flown by the group are bit-identical to one
+    engine flying everything, and the NCCL-reduced statistics equal the one-device statistics of the whole batch."""
+    import torch
+    if torch.cuda.device_count() < n_dev:
+        pytest.skip(f"needs {n_dev} GPUs")
+    z = util.golden("mc_solid_csv")
+    md = _abi.model_from_npz(z)
+    sc, wind = util.synth(z, 3001, seed=5)                     # odd count: uneven shards
+    sc, wind = np.ascontiguousarray(sc), np.ascontiguousarray(wind)
+    engine.set_model(md)
+    ref_out, ref_iout = engine.run_batch(sc, wind)
+    pcts = (5, 25, 50, 75, 95)
+    ref_stats = _raw_summary(engine, sc.shape[1], pcts)
+    grp = _lib.EngineGroup(list(range(n_dev)))
+    try:
+        grp.set_model(md)
+        out, iout = grp.run_batch(sc, wind)
+        np.testing.assert_array_equal(iout, ref_iout)
+        np.testing.assert_array_equal(out, ref_out)            # same kernels, same samples: bit for bit (NaN == NaN by position)
+        sh = grp.shards()
+        assert sh[0][0] == 0 and sum(c for _, c in sh) == sc.shape[1] and all(sh[i][0] + sh[i][1] == sh[i + 1][0] for i in range(n_dev - 1))
+        st = grp.stats_summary(pcts)
+        # counts, min / max and the order statistics are exact; the sums differ by the order of summation
+        np.testing.assert_array_equal(st[:9], ref_stats[:9])
+        np.testing.assert_array_equal(st[14:20], ref_stats[14:20])
+        np.testing.assert_array_equal(st[32:], ref_stats[32:])
+        np.testing.assert_allclose(st[9:14], ref_stats[9:14], rtol=1e-12)
+        np.testing.assert_allclose(st[20:31], ref_stats[20:31], rtol=1e-9)
+        c = grp.counters()
+        assert c["refills"] == sc.shape[1] and c["kernel_launches"] == 4 * n_dev
+    finally:
+        grp.close()
+
+
 def test_sharded_run_monte_carlo_equals_single_rank(tmp_path):
     """torchrun x2: rank r flies seeds [r n/2, (r+1) n/2) and every rank reports the statistics of the whole job
     (NCCL all-reduce between the passes); equal to the one-process run on the same seeds, statistics included."""
