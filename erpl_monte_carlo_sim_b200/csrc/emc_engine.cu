@@ -200,6 +200,21 @@ struct CompactBoard {
     short slots[BLOCK];
 };
 
+/* hand a trajectory to the strict continuation: copy its state and bookkeeping into the next park record and publish it */
+template <class Store, class CA>
+__device__ __forceinline__ void park_lane(const KernelArgs &a, int64_t idx, const Store &st, TrackHot &K, const CA &C)
+{
+    ParkRec &P = a.park[atomicAdd(a.park_count, 1ull)];
+    store_get(st, P.s);
+    K.replay = 0;
+    P.K = K;
+    for (int f = 0; f < TC_DCOUNT; ++f) P.C.d[f] = C.getd(f);
+    for (int f = 0; f < TI_ICOUNT; ++f) P.C.i[f] = C.geti(f);
+    P.C.i[TI_SAMPLE] = (int32_t)idx;
+    __threadfence();
+    *reinterpret_cast<volatile int32_t *>(&P.epoch) = a.epoch;       /* publish */
+}
+
 /* the persistent loop, generic over where the lane records live (REC: registers or shared memory) and the cold accessor */
 template <int BLOCK, class Store, bool COMPACT, int MK, int WK, class LANES>
 __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables &Tb, const double *alt, LANES lanes,
@@ -264,6 +279,10 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                             }
                             active = true;
                             ++n_refill;
+                            /* the fast path assumes a regular sample (derivative<., ., REG>): anything else — a non-positive
+                             * or non-finite mass, degenerate inertia constants — is flown by the strict continuation
+                             * from its first state, with the reference's own guards */
+                            if (!sample_regular(c_model, S)) { park_lane(a, idx, st, K, C); active = false; }
                         }
                     }
                     act = __ballot_sync(FULL, active);
@@ -337,7 +356,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
             TrackHot &K = R.K; Sample &S = R.S; WindBracket &WB = R.WB;
             const auto C = lanes.cold(threadIdx.x);
             bool stepped; int64_t rep = 0;
-            const bool retired = lane_advance<Store, decltype(C), MK, WK>(c_model, Tb, alt, S, WB, K, C, st, a.nan_ff != 0, stepped, rep, a.park_on != 0);
+            const bool retired = lane_advance<Store, decltype(C), MK, WK, true>(c_model, Tb, alt, S, WB, K, C, st, a.nan_ff != 0, stepped, rep, true);
             if (stepped) {
                 ++n_steps;
                 if (a.tape && (int64_t)K.n_steps < a.tape_cap) {
@@ -355,15 +374,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
             }
             if (retired && K.replay == EMC_REPLAY_PARK) {
                 /* blow-up under way: hand the trajectory to the strict continuation (emc_strict_kernel) */
-                ParkRec &P = a.park[atomicAdd(a.park_count, 1ull)];
-                store_get(st, P.s);
-                K.replay = 0;
-                P.K = K;
-                for (int f = 0; f < TC_DCOUNT; ++f) P.C.d[f] = C.getd(f);
-                for (int f = 0; f < TI_ICOUNT; ++f) P.C.i[f] = C.geti(f);
-                P.C.i[TI_SAMPLE] = (int32_t)idx;
-                __threadfence();
-                *reinterpret_cast<volatile int32_t *>(&P.epoch) = a.epoch;       /* publish */
+                park_lane(a, idx, st, K, C);
                 active = false;
             } else if (retired) {
                 n_replay += (unsigned long long)rep;
@@ -973,7 +984,7 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     a.nan_ff = o.nan_fast_forward;
     a.sm_count = ctx->sm_count > 0 ? ctx->sm_count : 1;
     a.compact = (o.flags & EMC_RUN_COMPACTION) ? 1 : 0;
-    a.park_on = (o.flags & EMC_RUN_NO_STRICT_TAIL) ? 0 : 1;
+    a.park_on = 1;       /* EMC_RUN_NO_STRICT_TAIL is ignored since the fast path relies on the strict continuation for irregular samples */
     if (a.park_on && a.n > 0) {
         const size_t cap_before = ctx->cap_park;
         CK(grow(&ctx->d_park, &ctx->cap_park, (size_t)a.n));
@@ -1206,7 +1217,10 @@ EMC_EXPORT int emc_run_tape(emc_ctx *ctx, const emc_inputs *in, const emc_output
     if (int rc = upload_inputs(ctx, in, 1, a, false)) return rc;
     CK(grow(&ctx->d_tape, &ctx->cap_tape, (size_t)cap * EMC_TAPE_WIDTH));
     a.tape = ctx->d_tape; a.tape_cap = cap;
-    emc_run_opts o = { 1, 64, 1, 0, 0, 0 };    /* every state is integrated: no fast-forward on the tape path */
+    /* every state is integrated: no fast-forward on the tape path.  Default launch shape: the SAME kernel instance that
+     * flies the batches, so that a tape is bit for bit the flight the batch flew (two instances of the same source may
+     * differ in FMA contraction) */
+    emc_run_opts o = { 1, 0, 0, 0, 0, 0 };
     if (int rc = run_device(ctx, a, &o)) return rc;
     if (int rc = download_outputs(ctx, out, 1, ctx->d_out1, ctx->d_iout1)) return rc;
     if (int rc = finish_counters(ctx)) return rc;

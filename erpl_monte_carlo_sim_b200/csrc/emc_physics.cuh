@@ -154,6 +154,20 @@ struct Diag {
     double mach2, qdyn, abs_aoa, stab;
 };
 
+EMC_HD bool finite_d(double v) { return fabs(v) <= 1.7976931348623157e308; }
+
+/* a product the compiler may not contract into a following add: where one value is computed by two code paths (the
+ * regular / general forms of aero_angles, chosen by a warp vote), both must round it the same way or a trajectory would
+ * depend on its warp neighbours */
+EMC_HD double mul_nc(double a, double b)
+{
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+
 /* ---------------- NaN-faithful selects ---------------- */
 EMC_HD double py_max(double a, double b) { return (b > a) ? b : a; }   /* Python max(a, b) */
 EMC_HD double py_min(double a, double b) { return (b < a) ? b : a; }   /* Python min(a, b) */
@@ -496,13 +510,21 @@ template <int MK> EMC_HD bool cfg_solid(const DevModel &M) { return MK < 0 ? (M.
 template <int WK> EMC_HD bool cfg_wind(const DevModel &M) { return WK < 0 ? (M.has_wind != 0) : (WK == 1); }
 
 /* ---------------- wind table (environment.py:267-276 -> three np.interp on one grid) ------------- */
-EMC_HD void wind_bracket_load(const DevModel &M, const double *alt, const double *w, double z, WindBracket &B)
+/* returns true when the altitude is +-inf: np.interp gives the end value there, and the bracket form s*(z - x0) + f0 would
+ * give 0*inf = NaN, so the caller takes f0 as it is (the bracket is left invalid: an infinite altitude reloads every time) */
+EMC_HD bool wind_bracket_load(const DevModel &M, const double *alt, const double *w, double z, WindBracket &B)
 {
     const int n = M.n_wind;
     if (z != z) {                               /* NaN altitude -> NaN wind, never valid */
         B.lo = z; B.hi = z; B.x0 = 0.0;
         B.f0[0] = B.f0[1] = B.f0[2] = z; B.s[0] = B.s[1] = B.s[2] = 0.0;
-        return;
+        return false;
+    }
+    if (!finite_d(z)) {
+        const int e = (z > 0.0) ? n - 1 : 0;
+        B.lo = 1.0; B.hi = 0.0; B.x0 = 0.0;     /* empty interval */
+        for (int k = 0; k < 3; ++k) { B.f0[k] = w[3 * e + k]; B.s[k] = 0.0; }
+        return true;
     }
     int j; bool clamp = false;
     if (z >= alt[n - 1]) { j = n - 1; clamp = true; B.lo = alt[n - 1]; B.hi = INFINITY; }
@@ -526,13 +548,16 @@ EMC_HD void wind_bracket_load(const DevModel &M, const double *alt, const double
         B.f0[k] = f0;
         B.s[k] = clamp ? 0.0 : (w[3 * (j + 1) + k] - f0) / (alt[j + 1] - alt[j]);
     }
+    return false;
 }
 
 template <int WK = -1>
 EMC_HD void wind_at(const DevModel &M, const double *alt, const Sample &S, double z, WindBracket &B, double w[3])
 {
     if (!cfg_wind<WK>(M)) { w[0] = w[1] = w[2] = 0.0; return; }
-    if (!(z >= B.lo && z < B.hi)) wind_bracket_load(M, alt, S.wind, z, B);
+    if (!(z >= B.lo && z < B.hi)) {
+        if (wind_bracket_load(M, alt, S.wind, z, B)) { w[0] = B.f0[0]; w[1] = B.f0[1]; w[2] = B.f0[2]; return; }
+    }
     double dz = z - B.x0;
     w[0] = B.s[0] * dz + B.f0[0];
     w[1] = B.s[1] * dz + B.f0[1];
@@ -571,12 +596,52 @@ EMC_HD bool time_negative(double t)
 #endif
 }
 
+/* Mach number, aerodynamic angles (utils.py:160-172) and their sin/cos (utils.py:194-197, from the velocity ratios) of
+ * one derivative evaluation.  GENERAL = true is the reference's semantics in full: dead zones (|vbx|, |vbz| < 1e-6 ->
+ * alpha = 0; |v_xz| < 1e-6 -> beta = 0), sqrt(0) = 0 and sqrt(inf) = inf, Mach clamped like np.interp's right end.
+ * GENERAL = false assumes !a_dead and finite vb2, under which those guards are dead code: |v_xz| >= 1e-6 follows from
+ * !a_dead, vb2 > 0, and Mach <= 1e152.  Where any lane of the warp needs the sideslip polynomial (3-D flights: always;
+ * planar flights: never, atan2(+-0, vxz) = +-0) the two angles are evaluated together. */
+struct AeroAngles { double mach, alpha, beta, ca, sa, cb, sb; };
+
+template <bool GENERAL>
+EMC_HD void aero_angles(double vbx, double vby, double vbz, double vxz2, double vb2, double rvb, double ya, bool aero, bool a_dead,
+                        AeroAngles &A)
+{
+    double speed = mul_nc(vb2, rvb);
+    if (GENERAL) speed = (vb2 == 0.0 || vb2 > 1.7976931348623157e308) ? vb2 : speed;        /* sqrt(0) = 0, sqrt(inf) = inf */
+    double mach = mul_nc(speed, ya);
+    if (GENERAL) mach = (mach > 1e300) ? 1e300 : mach;     /* +inf clamps like np.interp (right value), NaN stays NaN */
+    A.mach = mach;
+    const double rvxz = fast_rsqrt(vxz2);
+    const double vxz = (GENERAL && !(vxz2 > 0.0)) ? vxz2 : mul_nc(vxz2, rvxz);
+    const bool b_dead = GENERAL ? (vxz < 1e-6) : false;
+    const bool need_beta = aero && !b_dead && vby != 0.0;
+    double alpha, beta;
+    if (any_lane(need_beta)) {
+        fast_atan2_pair(vbz, vbx, vby, vxz, alpha, beta);
+        if (GENERAL) alpha = a_dead ? 0.0 : alpha;
+        beta = need_beta ? beta : ((GENERAL && b_dead) ? 0.0 : vby);
+    } else {
+        alpha = fast_atan2<false, true>(vbz, vbx);      /* not dead: max(|vbx|, |vbz|) >= 1e-6 */
+        if (GENERAL) alpha = a_dead ? 0.0 : alpha;
+        beta = (GENERAL && b_dead) ? 0.0 : vby;
+    }
+    A.alpha = alpha; A.beta = beta;
+    A.ca = (GENERAL && a_dead) ? 1.0 : mul_nc(vbx, rvxz); A.sa = (GENERAL && a_dead) ? 0.0 : mul_nc(vbz, rvxz);
+    A.cb = (GENERAL && b_dead) ? 1.0 : mul_nc(vxz, rvb); A.sb = (GENERAL && b_dead) ? 0.0 : mul_nc(vby, rvb);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * The derivative, simulator.py:295-460.
  *   chute      : sticky parachute flag (self.parachute_deployed), may be latched by any stage (F12)
  *   want_diag  : stage 0 only — export Mach^2, q_inf, |alpha|, stability margin of this state
  * ---------------------------------------------------------------------------------------------- */
-template <int MK = -1, int WK = -1>
+/* REG: the sample is REGULAR — dry mass positive and finite, propellant mass non-negative and finite, inertia constants
+ * positive (sample_regular below).  Then `mass < dry_mass` (simulator.py:315-318) and `Ixx > 0`, `Iyy > 0` (:431-436) are
+ * invariants of the flight, and the flight kernel drops the tests (irregular samples never enter its fast path: they are
+ * handed to the strict continuation before their first step). */
+template <int MK = -1, int WK = -1, bool REG = false>
 EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
                        WindBracket &WB, double t, const State &s, bool &chute, double &chute_time,
                        State &k, bool want_diag, Diag &dg, bool th_safe = false)
@@ -597,9 +662,9 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double ax = s2 * qx, ay = s2 * qy, az = s2 * qz;
 
     /* :311-321  mass properties, rocket.py:110-136 */
-    double mp = S.prop_mass * pf;
+    double mp = mul_nc(S.prop_mass, pf);        /* its own rounding in every instance (with REG nothing stands between it and the sum) */
     double mass = S.dry_mass + mp;
-    if (mass < S.dry_mass) { mass = S.dry_mass; mp = S.prop_mass * 0.0; }      /* :315-318 */
+    if (!REG && mass < S.dry_mass) { mass = S.dry_mass; mp = S.prop_mass * 0.0; }      /* :315-318 */
     const double inv_m = fast_rcp(mass);
     const double cg = (S.dry_cg + mp * M.prop_cg) * inv_m;
     const double dcg = M.prop_cg - cg;
@@ -655,36 +720,25 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
 
     const bool aero = (!chute) && (qdyn > 0.0);
     if (aero || want_diag) {
+        /* Mach, angle of attack, sideslip and their sin/cos.  REGULAR state: the body velocity is outside the dead zone of
+         * utils.py:160-172 and |v|^2 is finite — every step of a real flight.  Then none of the guards of the general
+         * form can fire (no dead-zone selects, sqrt(0) / sqrt(inf) fix-ups or Mach clamp), and a warp whose lanes are all
+         * regular takes the short form; one irregular lane sends the whole warp through the general one (a vote, so the
+         * branch never diverges). */
+        const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
+        const bool regular = (!a_dead) && (vb2 <= 1.7976931348623157e308);
+        AeroAngles A;
+        if (!any_lane(!regular)) aero_angles<false>(vbx, vby, vbz, vxz2, vb2, rvb, ya, aero, a_dead, A);
+        else aero_angles<true>(vbx, vby, vbz, vxz2, vb2, rvb, ya, aero, a_dead, A);
+        const double mach = A.mach, alpha = A.alpha, beta = A.beta;
         /* Mach-table brackets (rocket.py:105-108,156-157): shared by Cd0/Cda, separate knots for CP */
-        double speed = vb2 * rvb;
-        speed = (vb2 == 0.0 || vb2 > 1.7976931348623157e308) ? vb2 : speed;        /* sqrt(0) = 0, sqrt(inf) = inf */
-        double mach = speed * ya;
-        mach = (mach > 1e300) ? 1e300 : mach;     /* +inf clamps like np.interp (right value), NaN stays NaN */
         const int jm = brk_find(Tb.m_lo, Tb.m_hi, M.n_mb, WB.j_m, mach);
         WB.j_m = jm;
         const double cp = M.cp_location + fma(Tb.cp_s[jm], mach - Tb.cp_x0[jm], Tb.cp_f[jm]);
         const double sm = cp - cg;
-        /* utils.py:160-164,167-172: angle of attack and sideslip; their sin/cos (utils.py:194-197) come from the
-         * velocity ratios.  Where any lane of the warp needs the sideslip polynomial (3-D flights: always; planar
-         * flights: never, atan2(+-0, vxz) = +-0) the two angles are evaluated together. */
-        const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
-        const double rvxz = fast_rsqrt(vxz2);
-        const double vxz = (vxz2 > 0.0) ? vxz2 * rvxz : vxz2;
-        const bool b_dead = vxz < 1e-6;
-        const bool need_beta = aero && !b_dead && vby != 0.0;
-        double alpha, beta;
-        if (any_lane(need_beta)) {
-            fast_atan2_pair(vbz, vbx, vby, vxz, alpha, beta);
-            alpha = a_dead ? 0.0 : alpha;
-            beta = need_beta ? beta : (b_dead ? 0.0 : vby);
-        } else {
-            alpha = a_dead ? 0.0 : fast_atan2<false, true>(vbz, vbx);      /* not dead: max(|vbx|, |vbz|) >= 1e-6 */
-            beta = b_dead ? 0.0 : vby;
-        }
         if (want_diag) { dg.mach2 = mach2; dg.qdyn = qdyn; dg.abs_aoa = fabs(alpha); dg.stab = sm * M.inv_ref_diam; }
         if (aero) {
-            const double ca = a_dead ? 1.0 : vbx * rvxz, sa = a_dead ? 0.0 : vbz * rvxz;
-            const double cb = b_dead ? 1.0 : vxz * rvb, sb = b_dead ? 0.0 : vby * rvb;
+            const double ca = A.ca, sa = A.sa, cb = A.cb, sb = A.sb;
 
             /* rocket.py:138-218 */
             const double dm = mach - Tb.cd_x0[jm];
@@ -748,9 +802,9 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     /* :431-436  Euler equations with Izz == Iyy (rocket.py:127); Ixx, Iyy > 0 */
     const double inv_Iyy = fast_rcp(Iyy);
     /* roll: (mx - (Izz-Iyy)*wy*wz)/Ixx with Izz-Iyy == 0 and mx in {0, NaN}: no division needed */
-    k.wx = (Ixx > 0.0) ? (mx - 0.0 * (s.wy * s.wz)) : 0.0;
-    k.wy = (Iyy > 0.0) ? (my - (Ixx - Iyy) * s.wz * s.wx) * inv_Iyy : 0.0;
-    k.wz = (Iyy > 0.0) ? (mz - (Iyy - Ixx) * s.wx * s.wy) * inv_Iyy : 0.0;
+    k.wx = (REG || Ixx > 0.0) ? (mx - 0.0 * (s.wy * s.wz)) : 0.0;
+    k.wy = (REG || Iyy > 0.0) ? (my - (Ixx - Iyy) * s.wz * s.wx) * inv_Iyy : 0.0;
+    k.wz = (REG || Iyy > 0.0) ? (mz - (Iyy - Ixx) * s.wx * s.wy) * inv_Iyy : 0.0;
 
     /* :439  q_dot = 0.5 * qn (x) (0,w) - 0.5*(qn.qn - 1)*qn with qn = q/|q|, utils.py:114-121.  qn.qn - 1 is a
      * rounding residue (<= 3e-16): its term is 1e-16 of q_dot and, times dt, 1e-3 ulp of q — dropped (a non-finite q
@@ -903,7 +957,7 @@ EMC_HD void store_get(const Store &st, State &s)
  * same quantities at the same state).  A lane whose loop has ended (K.finishing) runs stage 0 only,
  * for the diagnostics of its last stored state, with the sticky flag protected: the reference never
  * evaluates the derivative there.  Returns true if a full step was taken. */
-template <class Store, class CA, int MK = -1, int WK = -1>
+template <class Store, class CA, int MK = -1, int WK = -1, bool REG = false>
 EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
                      WindBracket &WB, TrackHot &K, const CA &C, Store &st)
 {
@@ -927,7 +981,7 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
 #endif
     for (int stage = 0; stage < 4; ++stage) {
         const double ts = K.t + M.stage_t[stage];      /* warp-uniform offset */
-        derivative<MK, WK>(M, Tb, wind_alt, S, WB, ts, ys, chute, chute_time, k, stage == 0, dg, th_safe);
+        derivative<MK, WK, REG>(M, Tb, wind_alt, S, WB, ts, ys, chute, chute_time, k, stage == 0, dg, th_safe);
         if (stage == 0) {
             track_diag(C, ys, dg);                      /* ys == s at stage 0 */
             if (fin) return false;                      /* diagnostic pass only: a latch by this evaluation is dropped */
@@ -999,7 +1053,6 @@ EMC_HD bool rk4_step(const DevModel &M, const DevTables &Tb, const double *wind_
  * integrated until it reaches mode 1.  Apogee (first NaN, :488), the NaN maxima and the step count
  * are what the reference produces; max|omega| keeps its value at the fast-forward point (NaN runs:
  * category parity). */
-EMC_HD bool finite_d(double v) { return fabs(v) <= 1.7976931348623157e308; }
 
 EMC_HD int nan_mode(const DevModel &M, const Sample &S, const TrackHot &K, const State &s)
 {
@@ -1133,12 +1186,12 @@ EMC_HD bool strict_trigger(const State &s)
     return (v2 > EMC_STRICT_V2) || (fabs(s.wx) > EMC_STRICT_OMEGA) || (fabs(s.wy) > EMC_STRICT_OMEGA) || (fabs(s.wz) > EMC_STRICT_OMEGA);
 }
 
-template <class Store, class CA, int MK = -1, int WK = -1>
+template <class Store, class CA, int MK = -1, int WK = -1, bool REG = false>
 EMC_HD bool lane_advance(const DevModel &M, const DevTables &Tb, const double *wind_alt, const Sample &S,
                          WindBracket &WB, TrackHot &K, const CA &C, Store &st, bool nan_ff, bool &stepped, int64_t &replayed,
                          bool park = false)
 {
-    stepped = rk4_step<Store, CA, MK, WK>(M, Tb, wind_alt, S, WB, K, C, st);
+    stepped = rk4_step<Store, CA, MK, WK, REG>(M, Tb, wind_alt, S, WB, K, C, st);
     if (!stepped) {                       /* closing pass done */
         if (K.replay) {
             State s; store_get(st, s);
@@ -1194,6 +1247,15 @@ EMC_HD void load_sample(const DevModel &M, const double *col, int64_t ld, const 
     S.pf_rate = -col[EMC_IN_MDOT * ld] / S.prop_mass;
     S.cd_scale = col[EMC_IN_CD_SCALE * ld];
     S.wind = wind;
+}
+
+/* see derivative<., ., REG>: what the flight kernel's fast path assumes about a sample (and about the inertia constants of
+ * the model: Ixx = Ixx_dry + mp d^2/4, Iyy = Iyy_dry + mp (L^2/12 + dcg^2) with mp >= 0) */
+EMC_HD bool sample_regular(const DevModel &M, const Sample &S)
+{
+    return (S.dry_mass > 0.0) && finite_d(S.dry_mass) && (S.prop_mass >= 0.0) && finite_d(S.prop_mass) &&
+           (M.Ixx_dry > 0.0) && (M.Iyy_dry > 0.0) && (M.d4sq >= 0.0) && (M.len2_12 >= 0.0) && finite_d(M.prop_cg) && finite_d(M.cg_dry) &&
+           finite_d(M.Ixx_dry) && finite_d(M.Iyy_dry) && finite_d(M.d4sq) && finite_d(M.len2_12);
 }
 
 EMC_HD void wind_bracket_reset(WindBracket &B)

@@ -120,8 +120,9 @@ EMC_HD double strict_norm3(double a, double b, double c) { return S_SQRT(S_ADD(S
 EMC_HD void strict_wind(const DevModel &M, const double *alt, const Sample &S, double z, WindBracket &B, double w[3])
 {
     if (!M.has_wind) { w[0] = w[1] = w[2] = 0.0; return; }
-    if (!(z >= B.lo && z < B.hi)) wind_bracket_load(M, alt, S.wind, z, B);
-    if (B.lo == -INFINITY || B.hi == INFINITY) {              /* outside the grid np.interp returns the end value itself, also for z = -+inf */
+    bool end_value = false;
+    if (!(z >= B.lo && z < B.hi)) end_value = wind_bracket_load(M, alt, S.wind, z, B);
+    if (end_value || B.lo == -INFINITY || B.hi == INFINITY) {              /* outside the grid np.interp returns the end value itself, also for z = -+inf */
         for (int k = 0; k < 3; ++k) w[k] = B.f0[k];
         return;
     }

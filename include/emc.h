@@ -168,11 +168,13 @@ typedef struct emc_run_opts {
     int32_t cold_state_in_smem; /* 0 (default) or 2: per-lane bookkeeping, base state and RK4 accumulator live in shared memory; 1: bookkeeping only; -1: registers */
     int32_t flags;            /* ABI 2: EMC_RUN_* bits */
 } emc_run_opts;
-#define EMC_RUN_NO_STRICT_TAIL 2   /* finish every trajectory on the fast path.  Default: a trajectory whose stored state shows the reference's
-                                     blow-up in its last steps (|v| > 1e7 m/s or |omega| > 1000 rad/s) is finished by a second kernel that follows the
-                                     reference's arithmetic operation by operation (no FMA contraction, IEEE division / square root, libm), so
-                                     that the inf / NaN pattern of the overflowing steps — step count, termination, first-NaN index — is the
-                                     reference's. */
+#define EMC_RUN_NO_STRICT_TAIL 2   /* accepted and IGNORED (it used to finish every trajectory on the fast path).  A trajectory whose stored
+                                     state shows the reference's blow-up in its last steps (|v| > 1e7 m/s or |omega| > 1000 rad/s) is always
+                                     finished by the strict continuation, which follows the reference's arithmetic operation by operation (no
+                                     FMA contraction, IEEE division / square root, libm), so that the inf / NaN pattern of the overflowing steps
+                                     — step count, termination, first-NaN index — is the reference's; so is every IRREGULAR sample (dry mass
+                                     not positive and finite, propellant mass negative or not finite), from its first state: the fast path
+                                     drops the guards of simulator.py:315-318,431-436 that only such samples can trigger. */
 #define EMC_RUN_COMPACTION 1      /* tail compaction: once the work queue is empty, sparse warps hand their trajectories (lane records in
                                      shared memory, addressed by slot) to one collector warp per block and exit.  Bit-identical outputs.
                                      Off by default: measured on the B200 the slot indirection costs more than the compacted tail

@@ -309,3 +309,34 @@ def test_gpu_components_match_reference(engine):
         engine.set_model(models[kind])
         return engine.component(comp, *cols)
     util.check_components(ev, z)
+
+
+def test_gpu_irregular_samples_fly_the_strict_continuation(engine):
+    """Samples the fast path does not accept (propellant mass negative, dry mass zero / negative / NaN) are handed to the
+    strict continuation before their first step: their outputs are the oracle's, integers exactly."""
+    z = util.golden("mc_solid_csv")
+    md = _abi.model_from_npz(z)
+    sc, wind = z["scalars"][:, :24].copy(), z["wind"][:24].copy()
+    IN = _abi.IN
+    sc[IN["prop_mass"], 1] = -3.0           # mass < dry_mass fires (simulator.py:315-318)
+    sc[IN["prop_mass"], 5] = -1e-3
+    sc[IN["dry_mass"], 9] = -50.0           # negative total mass: the reference flies on
+    sc[IN["dry_mass"], 12] = 0.0
+    sc[IN["prop_mass"], 12] = 0.0           # zero mass: division by zero in the first derivative
+    sc[IN["dry_mass"], 17] = np.nan
+    engine.set_model(md)
+    out, iout = engine.run_batch(sc, wind)
+    c = engine.counters()
+    ref, iref = O.batch(md, sc, wind)
+    np.testing.assert_array_equal(iout, iref)
+    # summaries: the untouched samples under the usual rule; the six irregular ones (all of them end in the reference's
+    # blow-up, where CUDA's libm against glibc's — 1-2 ulp per call — is amplified without bound: 6.49e36 came out 1.8e-4
+    # apart) by category where non-finite and to 1 % on the finite values
+    odd = np.zeros(sc.shape[1], bool); odd[[1, 5, 9, 12, 17]] = True
+    sens = util.oracle_sensitivity(md, sc[:, ~odd], wind[~odd])
+    util.assert_summary_close(out[:, ~odd], ref[:, ~odd], what="regular samples vs oracle", sens=sens)
+    err = util.summary_errors(out[:, odd], ref[:, odd])        # NaN / inf / beyond-1e150 values compare by category (tests/util.py)
+    worst = np.unravel_index(np.argmax(err), err.shape)
+    assert err[worst] <= 1e-2, (f"irregular sample {np.flatnonzero(odd)[worst[1]]}, field {_abi.OUT_FIELDS[worst[0]]}: "
+                                f"{out[:, odd][worst]!r} vs {ref[:, odd][worst]!r}")
+    assert c["parked"] >= 5
