@@ -141,12 +141,12 @@ def test_gpu_vs_oracle_seeded_batch(engine, name, n):
     engine.set_model(md)
     out, iout = engine.run_batch(sc, wind)
     ref, iref = O.batch(md, sc, wind)
-    # a step count may differ only where an event test sits within rounding of its threshold
-    same = np.all(iout == iref, axis=0)
-    assert same.mean() >= 0.99, f"{(~same).sum()} of {n} samples differ in step count/termination"
+    # step count, termination code, apogee index, first-NaN index, rail steps: exact on every sample (round 1 allowed 1 %
+    # of blown-up flights to differ; the strict continuation closed that gap)
+    np.testing.assert_array_equal(iout, iref)
     sens = util.oracle_sensitivity(md, sc, wind)
     assert np.mean(np.isinf(sens).any(axis=0)) < 0.02
-    util.assert_summary_close(*util.drop_nan_run_omega(out[:, same], ref[:, same], iref[:, same]), what=name, sens=sens[:, same])
+    util.assert_summary_close(*util.drop_nan_run_omega(out, ref, iref), what=name, sens=sens)
 
 
 def test_gpu_full_size_properties(engine):
@@ -179,20 +179,17 @@ def test_gpu_full_size_properties(engine):
     # spot-check 256 of the 100k against the oracle
     pick = np.random.RandomState(1).choice(n, 256, replace=False)
     ref, iref = O.batch(md, sc[:, pick].copy(), wind[pick].copy())
-    same = np.all(iout[:, pick] == iref, axis=0)
-    assert same.mean() >= 0.99
+    np.testing.assert_array_equal(iout[:, pick], iref)
     sens = util.oracle_sensitivity(md, sc[:, pick].copy(), wind[pick].copy())
-    util.assert_summary_close(*util.drop_nan_run_omega(out[:, pick][:, same], ref[:, same], iref[:, same]), what="100k spot check",
-                              sens=sens[:, same])
+    util.assert_summary_close(*util.drop_nan_run_omega(out[:, pick], ref, iref), what="100k spot check", sens=sens)
 
 
 def test_gpu_bench_workload_valid_flights_exact(engine):
     """On the headline workload itself (BASELINE C3, reference dispersions): the set of valid (non-outlier) flights is the
     oracle's, every valid flight has the oracle's integer outputs exactly and its summaries within 1e-6 (10x the oracle's
-    own one-ulp sensitivity for the few valid flights that pass through a numerical blow-up), and the only flights whose
-    integers differ are blown-up ones (the speed overflows to inf/NaN within one RK4 step, so which operation
-    first yields NaN instead of +-inf depends on rounding order) -- non-finite maximum speed in both runs, outliers in
-    both."""
+    own one-ulp sensitivity for the few valid flights that pass through a numerical blow-up), and EVERY flight — the
+    blown-up ones included (the speed overflows to inf/NaN within one RK4 step; the strict continuation
+    follows the reference's operation order there) — has the oracle's integer outputs."""
     import sys, os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench
@@ -213,13 +210,11 @@ def test_gpu_bench_workload_valid_flights_exact(engine):
     well = valid & np.all(sens < 1e-8, axis=0)
     assert well.sum() >= 0.9 * valid.sum()
     util.assert_summary_close(out[:, well], ref[:, well], what="well-conditioned valid C3 flights")       # plain 1e-6
-    same = np.all(iout == iref, axis=0)
-    differ = ~same
-    assert differ.mean() < 0.02
-    assert not np.any(np.isfinite(out[OUT["max_speed"]][differ])) and not np.any(np.isfinite(ref[OUT["max_speed"]][differ]))
+    # measured on 50 000 samples of this workload (tools/parity_sweep.py): no sample differs in an integer output
+    np.testing.assert_array_equal(iout, iref)
     # every flight that stays finite (valid or not) within the conditioning-aware tolerance; the ones whose speed reaches
     # inf/NaN are covered above by the identical outlier sets (their diagnostics differ by inf-vs-NaN category only)
-    tame = same & np.isfinite(out[OUT["max_speed"]]) & np.isfinite(ref[OUT["max_speed"]])
+    tame = np.isfinite(out[OUT["max_speed"]]) & np.isfinite(ref[OUT["max_speed"]])
     assert tame.mean() > 0.5
     util.assert_summary_close(out[:, tame], ref[:, tame], what="finite C3 flights", sens=sens[:, tame])
 
