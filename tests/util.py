@@ -193,17 +193,6 @@ def synth(z, n, seed):
 
 
 
-def drop_nan_run_omega(out, ref, iref):
-    """trajectories that go NaN get category-level parity only.  For those flights the one
-    summary field that stays finite and keeps evolving in blown-up arithmetic (max |omega|, 1e100+) is not
-    compared; every other field (NaN pattern included) still is."""
-    out = out.copy(); ref = ref.copy()
-    nan_run = iref[_abi.IOUT["first_nan_step"]] >= 0
-    i = OUT["max_abs_omega"]
-    out[i, nan_run] = 0.0; ref[i, nan_run] = 0.0
-    return out, ref
-
-
 # golden series keys (oracle/make_golden.py SERIES_KEYS) -> rows of the engine's series block
 SERIES_MAP = {"mass": "mass", "center_of_mass": "center_of_mass", "thrust": "thrust", "drag": "drag", "cd": "cd", "cl": "cl",
               "cm": "cm", "cp_location_dynamic": "cp_location_dynamic", "stability_margin": "stability_margin",
