@@ -12,6 +12,7 @@ from . import _abi, _lib, marshal
 from .utils import object_to_serializable_dict
 
 _ENGINES = {}
+_COMPONENT_ENGINES = {}
 
 
 def get_engine(device: int = 0) -> "_lib.Engine":
@@ -30,7 +31,11 @@ def evaluate_component(comp, columns, rocket=None, motor=None, atmosphere=None, 
     from .motor import LiquidMotor
     from .rocket import Rocket
     knobs = type("Knobs", (), dict(max_time=300.0, dt_initial=0.01, pitch_damping=20.0, yaw_damping=20.0))()
-    eng = get_engine(device)
+    # a context of its own: the helpers must not replace the model (or touch the resident batch) of the engine that the
+    # simulator / analyzer of this process fly with (round-1 advisor finding); contexts of one device keep their own model
+    eng = _COMPONENT_ENGINES.get(device)
+    if eng is None:
+        eng = _COMPONENT_ENGINES[device] = _lib.Engine(device)
     eng.set_model(marshal.model_dict(rocket or Rocket(), motor or LiquidMotor(), atmosphere or StandardAtmosphere(), knobs, None))
     return eng.component(comp, *columns)
 

@@ -310,3 +310,19 @@ def test_reference_test_fixes_atmosphere_check():
     assert abs(c["cd"] - 0.568375) < 1e-13 and abs(c["cyaw"] - 0.03557241984551255) < 1e-14
     assert abs(LiquidMotor().get_thrust(1.0, 50000.0) - (2590 * 4.44822 - LiquidMotor().nozzle_exit_area * 50000.0)) < 1e-9
     assert SolidMotor().get_thrust(20.0) == 0.0 and abs(r.get_stability_margin(1.0) - (r.cp_location - 5.620520067834935) / 0.219) < 1e-12
+
+
+def test_helper_methods_leave_the_flying_engine_alone():
+    """Rocket.get_mass_properties & co. are evaluated on the device through a context of their own: the engine the
+    analyzer flies with keeps its model (round-1 advisor finding: they used to call set_model on the shared engine)."""
+    from erpl_monte_carlo_sim_b200.simulator import get_engine
+    mc = MonteCarloAnalyzer(Rocket(), SolidMotor(), StandardAtmosphere(), WindModel())
+    mc.base_altitude_profile, mc.base_wind_profile = CSV_ALT, CSV_WIND
+    ic = {"position": [0.0, 0.0, 10.0], "velocity": [0, 0, 0.0], "attitude": VERTICAL, "angular_velocity": [0.0, 0.0, 0.0]}
+    a1 = mc.run_monte_carlo(ic, n_samples=48)
+    eng = get_engine(0)
+    model_before = eng.model_dict
+    Rocket().get_mass_properties(0.5); StandardAtmosphere().get_properties(12000.0); LiquidMotor().get_thrust(1.0, 50000.0)
+    assert eng.model_dict is model_before
+    a2 = mc.run_monte_carlo(ic, n_samples=48)
+    assert a1["n_samples"] == a2["n_samples"] and a1["apogee_altitude"]["mean"] == a2["apogee_altitude"]["mean"]
