@@ -37,6 +37,21 @@ def test_gpu_single_flights(engine):
         util.assert_summary_close(out, ref, what=str(name))
 
 
+def test_gpu_series_on_the_reference_states(engine):
+    """_extract_results (simulator.py:496-552) on the device, evaluated at the REFERENCE's own stored states of every golden
+    single flight — all of them, the diverging tail included (the API test compares the engine's own states, which the
+    blow-up separates from the reference's after ~2 500 steps; here nothing is amplified)."""
+    z = util.golden("flights_single")
+    for name in z["names"]:
+        name = str(name)
+        md, sc, wind, ref, iref = util.single_case(z, name)
+        idx, rows, sref = util.series_reference(z, name)
+        engine.set_model(md)
+        got = engine.extract_series(sc, wind, rows.copy())
+        assert got.shape == (_abi.SERIES_COUNT, idx.size)
+        util.assert_series_close(got, sref, name)
+
+
 @pytest.mark.parametrize("name", util.MC_SETS)
 def test_gpu_mc_sets(engine, name):
     z = util.golden(name)
