@@ -15,10 +15,28 @@ import util  # noqa: E402
 from erpl_monte_carlo_sim_b200 import _abi, _lib  # noqa: E402
 
 eng = _lib.Engine(0)
-for workload, n, seed0 in (("c3", int(os.environ.get("N_C3", "20000")), 300000), ("planar", int(os.environ.get("N_PLANAR", "1500")), 700000)):
+
+
+def c4_workload(n, first_index):
+    """BASELINE config C4 as the bench flies it: LiquidMotor, default dispersions, 100-knot stochastic wind per sample, drawn
+    and perturbed on the device (Philox); the staged inputs are read back so that the oracle flies the same samples."""
+    from erpl_monte_carlo_sim_b200 import LiquidMotor, MonteCarloAnalyzer, Rocket, StandardAtmosphere, WindModel, marshal
+    mc = MonteCarloAnalyzer(Rocket(), LiquidMotor(), StandardAtmosphere(), WindModel())
+    md = marshal.model_dict(mc.rocket, mc.motor, mc.atmosphere, mc._model_simulator(), mc._altitude_grid())
+    eng.set_model(md)
+    eng.generate_inputs(mc.dispersion_struct(bench.IC_C4), mc.philox_seed, first_index, n)
+    sc, w = eng.staged_inputs(n, want_wind=True)
+    return md, sc, w
+
+
+for workload, n, seed0 in (("c3", int(os.environ.get("N_C3", "20000")), 300000), ("planar", int(os.environ.get("N_PLANAR", "1500")), 700000),
+                           ("c4", int(os.environ.get("N_C4", "10000")), 5000000)):
     if n <= 0:
         continue
-    md, blk, wind, _ = bench.make_workload(workload, n, seed0)
+    if workload == "c4":
+        md, blk, wind = c4_workload(n, seed0)
+    else:
+        md, blk, wind, _ = bench.make_workload(workload, n, seed0)
     eng.set_model(md)
     out, iout = eng.run_batch(blk, wind)
     t0 = time.time()
