@@ -752,14 +752,18 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
             const double cl_alpha = M.two_pi_AR_cos * fast_rcp(2.0 + rad * fast_rsqrt(rad));
             double cl = cl_alpha * alpha;
             double cy = cl_alpha * beta;
-            if (abs_alpha > M.stall_angle) {
+            {
+                /* rocket.py:186-196 as selects, not a branch: the kernel is bound by dependent-instruction latency, and a
+                 * (divergent) branch here ends the basic block in which the force and moment products overlap
+                 * (measured: +1.8 % on C3, +1.3 % on launch->landing, lone trajectory 5.02 -> 4.92 us/step) */
+                const bool stalled = abs_alpha > M.stall_angle;
                 const double over = (abs_alpha - M.stall_angle) * M.inv_stall_span;
-                double sf = 1.0 - over;
-                sf = (sf > 0.0) ? sf : 0.0;
+                const double sf = pos_part(1.0 - over);          /* max(0.0, 1 - over), NaN -> 0 */
                 const double sgn = (alpha > 0.0) ? 1.0 : ((alpha < 0.0) ? -1.0 : alpha);
-                cl = cl_alpha * M.stall_angle * sf * sgn;
-                cd *= 1.0 + 0.5 * over;
-                cy *= sf;
+                const double cl_s = cl_alpha * M.stall_angle * sf * sgn;
+                const double cd_s = cd * (1.0 + 0.5 * over);
+                const double cy_s = cy * sf;
+                cl = stalled ? cl_s : cl; cd = stalled ? cd_s : cd; cy = stalled ? cy_s : cy;
             }
             const double cm = -cl_alpha * sm * alpha;
             const double cyaw = -cl_alpha * sm * beta;
@@ -816,11 +820,9 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
 
     /* :442-450 propellant; the 10 ms taper test pf/|rate| < 0.01 is written as pf < 0.01*|rate| (the two branches are
      * continuous at the boundary; a zero rate gives 0 and the test fails like the reference's `rate != 0`) */
-    double pfr = 0.0;
-    if (burning) {
-        pfr = S.pf_rate;
-        if (pf < 0.01 * fabs(pfr)) pfr = -pf * 100.0;
-    }
+    const double pf_full = S.pf_rate, pf_taper = -pf * 100.0;
+    double pfr = (pf < 0.01 * fabs(pf_full)) ? pf_taper : pf_full;
+    pfr = burning ? pfr : 0.0;
     k.pf = pfr;
 }
 
