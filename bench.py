@@ -23,6 +23,7 @@ One JSON line on stdout (rank 0).
   --impl reference   the CPU port timed as its own arm (all host threads)
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -229,6 +230,7 @@ def secondary_measurements(eng, opts, peak_tf, rank, world, dev, barrier, n_plan
             c = eng_counters_of(mc)
             keep = {k: an[k] for k in ("n_samples", "n_outliers", "apogee_altitude", "landing_ellipse")}
             an = None; mc.last_run = None         # drop the batch: its outputs were never asked for, nothing is downloaded
+            gc.collect()                          # (the engine holds the batch by a weak reference: a cycle awaiting collection would keep it alive and the next run would download its 375 MB first)
             if best is None or wall < best[1]:
                 best = (c, wall, keep)
         an = best[2]
@@ -240,6 +242,7 @@ def secondary_measurements(eng, opts, peak_tf, rank, world, dev, barrier, n_plan
     if n_c3_big > 0:
         mc = c3_analyzer()
         mc.rng = "numpy-device"; mc.trajectory_samples = 0; mc.run_opts = opts
+        gc.collect()
         barrier(); t0 = time.perf_counter()
         run = mc.run_batch_numpy_device(IC_C3, n_c3_big, first_seed=rank * n_c3_big)
         barrier(); wall = time.perf_counter() - t0
@@ -263,6 +266,7 @@ def api_end_to_end(n_total, rank, world, barrier, opts):
         an = None
         for rep in range(3 if mode != "numpy" else 1):
             an = None; mc.last_run = None         # a campaign whose per-sample results were not read leaves nothing to download
+            gc.collect()
             barrier(); t0 = time.perf_counter()
             an = mc.run_monte_carlo(IC_C3, n_samples=n)
             barrier(); dt = time.perf_counter() - t0
