@@ -37,6 +37,14 @@
 #define EMC_KDECL static const double
 #endif
 #define EMC_LIKELY(x) __builtin_expect(!!(x), 1)
+/* rarely executed helper kept OUT of line: ptxas lays a rarely taken block where it stands in the program, so the common
+ * path would otherwise take a branch across it every time (an instruction-fetch bubble); as a call, the block shrinks to a
+ * predicated call instruction */
+#if defined(__CUDACC__)
+#define EMC_COLD __device__ __noinline__
+#else
+#define EMC_COLD EMC_HD
+#endif
 
 namespace emc {
 
@@ -403,12 +411,15 @@ EMC_HD bool any_lane(bool p)
 
 /* remembered-bracket lookup: j stays valid while lo[j] <= x < hi[j]; NaN leaves j alone (the FMA that
  * follows then yields NaN, which is np.interp's answer) */
+EMC_COLD int brk_search(const double *lo, const double *hi, int nb, int j, double x)
+{
+    while (j < nb - 1 && x >= hi[j]) ++j;
+    while (j > 0 && x < lo[j]) --j;
+    return j;
+}
 EMC_HD int brk_find(const double *lo, const double *hi, int nb, int j, double x)
 {
-    if (!(x >= lo[j] && x < hi[j])) {          /* rare; a NaN x fails both searches and keeps j */
-        while (j < nb - 1 && x >= hi[j]) ++j;
-        while (j > 0 && x < lo[j]) --j;
-    }
+    if (!(x >= lo[j] && x < hi[j])) j = brk_search(lo, hi, nb, j, x);      /* rare; a NaN x fails both searches and keeps j */
     return j;
 }
 
@@ -512,7 +523,7 @@ template <int WK> EMC_HD bool cfg_wind(const DevModel &M) { return WK < 0 ? (M.h
 /* ---------------- wind table (environment.py:267-276 -> three np.interp on one grid) ------------- */
 /* returns true when the altitude is +-inf: np.interp gives the end value there, and the bracket form s*(z - x0) + f0 would
  * give 0*inf = NaN, so the caller takes f0 as it is (the bracket is left invalid: an infinite altitude reloads every time) */
-EMC_HD bool wind_bracket_load(const DevModel &M, const double *alt, const double *w, double z, WindBracket &B)
+EMC_COLD bool wind_bracket_load(const DevModel &M, const double *alt, const double *w, double z, WindBracket &B)
 {
     const int n = M.n_wind;
     if (z != z) {                               /* NaN altitude -> NaN wind, never valid */
@@ -555,18 +566,44 @@ template <int WK = -1>
 EMC_HD void wind_at(const DevModel &M, const double *alt, const Sample &S, double z, WindBracket &B, double w[3])
 {
     if (!cfg_wind<WK>(M)) { w[0] = w[1] = w[2] = 0.0; return; }
-    if (!(z >= B.lo && z < B.hi)) {
+    /* every value of the remembered bracket is read before the range test (no short circuit: both bounds and the seven
+     * coefficients are loads the scheduler may issue at once); the rare miss reloads them */
+    const double lo = B.lo, hi = B.hi;
+    double x0 = B.x0, s0 = B.s[0], s1 = B.s[1], s2 = B.s[2], f0 = B.f0[0], f1 = B.f0[1], f2 = B.f0[2];
+    if (!((z >= lo) & (z < hi))) {
         if (wind_bracket_load(M, alt, S.wind, z, B)) { w[0] = B.f0[0]; w[1] = B.f0[1]; w[2] = B.f0[2]; return; }
+        x0 = B.x0; s0 = B.s[0]; s1 = B.s[1]; s2 = B.s[2]; f0 = B.f0[0]; f1 = B.f0[1]; f2 = B.f0[2];
     }
-    double dz = z - B.x0;
-    w[0] = B.s[0] * dz + B.f0[0];
-    w[1] = B.s[1] * dz + B.f0[1];
-    w[2] = B.s[2] * dz + B.f0[2];
+    const double dz = z - x0;
+    w[0] = s0 * dz + f0;
+    w[1] = s1 * dz + f1;
+    w[2] = s2 * dz + f2;
 }
 
 /* ---------------- thrust (motor.py:54-76, 152-156), caller has checked pf>0 && t<=burn ---------- */
 /* thrust inside the burn window (the caller has established 0 <= t <= burn_time) */
 /* th_safe: the caller has established th_lo[j_th] <= t < th_hi[j_th] (rk4_step tests [t, t + dt] once per step) */
+/* the part of the thrust that depends on the time alone (thrust curve x sample factor; a liquid motor has none): the
+ * derivative evaluates it first, off the chain that leads through the atmosphere to the pressure term */
+template <int MK = -1>
+EMC_HD double thrust_time_part(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, bool th_safe)
+{
+    if (!cfg_solid<MK>(M)) return S.thrust_a;
+    int j = C.j_th;
+    double ts = Tb.th_s[j], tx = Tb.th_x0[j], tf = Tb.th_f[j];
+    if (!th_safe) {
+        const int j2 = brk_find(Tb.th_lo, Tb.th_hi, M.n_thrust + 1, j, t);
+        if (j2 != j) { C.j_th = j2; ts = Tb.th_s[j2]; tx = Tb.th_x0[j2]; tf = Tb.th_f[j2]; }
+    }
+    return fma(ts, t - tx, tf) * S.thrust_a;
+}
+template <int MK = -1>
+EMC_HD double thrust_finish(const DevModel &M, const Sample &S, double time_part, double p)
+{
+    if (cfg_solid<MK>(M)) return time_part + S.nozzle_area * (101325.0 - p);
+    return time_part - S.nozzle_area * p;
+}
+
 template <int MK = -1>
 EMC_HD double thrust_core(const DevModel &M, const DevTables &Tb, const Sample &S, WindBracket &C, double t, double p, bool th_safe = false)
 {
@@ -606,14 +643,13 @@ struct AeroAngles { double mach, alpha, beta, ca, sa, cb, sb; };
 
 template <bool GENERAL>
 EMC_HD void aero_angles(double vbx, double vby, double vbz, double vxz2, double vb2, double rvb, double ya, bool aero, bool a_dead,
-                        AeroAngles &A)
+                        AeroAngles &A, double rvxz)
 {
     double speed = mul_nc(vb2, rvb);
     if (GENERAL) speed = (vb2 == 0.0 || vb2 > 1.7976931348623157e308) ? vb2 : speed;        /* sqrt(0) = 0, sqrt(inf) = inf */
     double mach = mul_nc(speed, ya);
     if (GENERAL) mach = (mach > 1e300) ? 1e300 : mach;     /* +inf clamps like np.interp (right value), NaN stays NaN */
     A.mach = mach;
-    const double rvxz = fast_rsqrt(vxz2);
     const double vxz = (GENERAL && !(vxz2 > 0.0)) ? vxz2 : mul_nc(vxz2, rvxz);
     const bool b_dead = GENERAL ? (vxz < 1e-6) : false;
     const bool need_beta = aero && !b_dead && vby != 0.0;
@@ -648,7 +684,13 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
 {
     /* :305  pf = max(0.0, pf)  (NaN -> 0.0) */
     const double pf = pos_part(s.pf);
-    const bool burning = (pf > 0.0) && (t <= S.burn_time);
+    const bool burning = (pf > 0.0) & (t <= S.burn_time);
+    const double thr_t = thrust_time_part<MK>(M, Tb, S, WB, t, th_safe);
+    double w[3];
+    wind_at<WK>(M, wind_alt, S, s.z, WB, w);
+    /* the remembered Mach bracket is read here, long before the Mach number exists */
+    const int jm0 = WB.j_m;
+    const double m_lo0 = Tb.m_lo[jm0], m_hi0 = Tb.m_hi[jm0];
 
     /* :308  the quaternion is normalised by the reference (identity if |q| <= 1e-12 or NaN, utils.py:76-82).  Here the
      * components stay as they are and the norm goes into two scalars: a = 2 v / |q|^2 for the rotations and
@@ -682,8 +724,6 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double ya = fast_rsqrt(M.a2_k * T);
     const double ya2 = ya * ya;
     const double rho = p * (ya2 * M.rho_k);
-    double w[3];
-    wind_at<WK>(M, wind_alt, S, s.z, WB, w);
 
     /* :341-352  v_body = R(q)^T u as a quaternion rotation: u - w tb + v x tb, tb = a x u (utils.py:100-111,129-136) */
     const double ux = s.vx - w[0], uy = s.vy - w[1], uz = s.vz - w[2];
@@ -700,14 +740,10 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
     const double qdyn = 0.5 * rho * vb2;
 
     /* :359-363 thrust along body x */
-#ifndef EMC_NO_SPEC_THRUST
-    /* evaluated in the straight-line code and selected afterwards (np.interp clamps outside the curve, so any time is
-     * a valid argument): no branch region around the table reads */
-    const double thrust = thrust_core<MK>(M, Tb, S, WB, t, p, th_safe);
+    /* :359-363 the time part was evaluated first (above); np.interp clamps outside the curve, so any time is a valid
+     * argument and the value is selected afterwards: no branch region around the table reads */
+    const double thrust = thrust_finish<MK>(M, S, thr_t, p);
     double fbx = (burning && !time_negative(t)) ? thrust : 0.0;                                          /* motor.py:55,153: 0 outside [0, burn_time] */
-#else
-    double fbx = (burning && !time_negative(t)) ? thrust_core<MK>(M, Tb, S, WB, t, p, th_safe) : 0.0;   /* motor.py:55,153: 0 outside [0, burn_time] */
-#endif
     double fby = 0.0, fbz = 0.0;
     double mx = 0.0, my = 0.0, mz = 0.0;
 
@@ -728,22 +764,32 @@ EMC_HD void derivative(const DevModel &M, const DevTables &Tb, const double *win
         const bool a_dead = (fabs(vbx) < 1e-6) && (fabs(vbz) < 1e-6);
         const bool regular = (!a_dead) && (vb2 <= 1.7976931348623157e308);
         AeroAngles A;
-        if (!any_lane(!regular)) aero_angles<false>(vbx, vby, vbz, vxz2, vb2, rvb, ya, aero, a_dead, A);
-        else aero_angles<true>(vbx, vby, vbz, vxz2, vb2, rvb, ya, aero, a_dead, A);
+        const double rvxz = fast_rsqrt(vxz2);
+        if (!any_lane(!regular)) aero_angles<false>(vbx, vby, vbz, vxz2, vb2, rvb, ya, aero, a_dead, A, rvxz);
+        else aero_angles<true>(vbx, vby, vbz, vxz2, vb2, rvb, ya, aero, a_dead, A, rvxz);
         const double mach = A.mach, alpha = A.alpha, beta = A.beta;
         /* Mach-table brackets (rocket.py:105-108,156-157): shared by Cd0/Cda, separate knots for CP */
-        const int jm = brk_find(Tb.m_lo, Tb.m_hi, M.n_mb, WB.j_m, mach);
-        WB.j_m = jm;
-        const double cp = M.cp_location + fma(Tb.cp_s[jm], mach - Tb.cp_x0[jm], Tb.cp_f[jm]);
+        int jm = jm0;
+        double cps = Tb.cp_s[jm0], cpx = Tb.cp_x0[jm0], cpf = Tb.cp_f[jm0];
+        double cdx = Tb.cd_x0[jm0], cd0s = Tb.cd0_s[jm0], cd0f = Tb.cd0_f[jm0], cdas = Tb.cda_s[jm0], cdaf = Tb.cda_f[jm0];
+        if (!((mach >= m_lo0) & (mach < m_hi0))) {          /* rare; a NaN Mach number fails both searches and keeps the bracket */
+            jm = brk_search(Tb.m_lo, Tb.m_hi, M.n_mb, jm0, mach);
+            if (jm != jm0) {
+                WB.j_m = jm;
+                cps = Tb.cp_s[jm]; cpx = Tb.cp_x0[jm]; cpf = Tb.cp_f[jm];
+                cdx = Tb.cd_x0[jm]; cd0s = Tb.cd0_s[jm]; cd0f = Tb.cd0_f[jm]; cdas = Tb.cda_s[jm]; cdaf = Tb.cda_f[jm];
+            }
+        }
+        const double cp = M.cp_location + fma(cps, mach - cpx, cpf);
         const double sm = cp - cg;
         if (want_diag) { dg.mach2 = mach2; dg.qdyn = qdyn; dg.abs_aoa = fabs(alpha); dg.stab = sm * M.inv_ref_diam; }
         if (aero) {
             const double ca = A.ca, sa = A.sa, cb = A.cb, sb = A.sb;
 
             /* rocket.py:138-218 */
-            const double dm = mach - Tb.cd_x0[jm];
-            const double cd0 = fma(Tb.cd0_s[jm], dm, Tb.cd0_f[jm]) * S.cd_scale;
-            const double cda = fma(Tb.cda_s[jm], dm, Tb.cda_f[jm]);
+            const double dm = mach - cdx;
+            const double cd0 = fma(cd0s, dm, cd0f) * S.cd_scale;
+            const double cda = fma(cdas, dm, cdaf);
             double cd = cd0 + cda * (alpha * alpha);
             if (!(pf > 0.0)) cd *= M.power_off_factor;
             const double abs_alpha = fabs(alpha);
