@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_CD_KNOTS = 16
 MAX_CP_KNOTS = 16
 MAX_THRUST_KNOTS = 32
@@ -110,7 +110,7 @@ class EmcCounters(C.Structure):
     _fields_ = [("rk4_steps", C.c_int64), ("replay_steps", C.c_int64), ("rail_steps", C.c_int64),
                 ("refills", C.c_int64), ("kernel_launches", C.c_int64),
                 ("rail_ms", C.c_double), ("flight_ms", C.c_double), ("tape_rows", C.c_int64), ("handovers", C.c_int64), ("parked", C.c_int64), ("strict_steps", C.c_int64),
-                ("strict_ms", C.c_double)]
+                ("strict_ms", C.c_double), ("yielded", C.c_int64)]
 
 
 _MODEL_SCALARS = ["center_of_mass_dry", "Ixx_dry", "Iyy_dry", "diameter", "reference_area",

@@ -137,13 +137,14 @@ def load():
     return L
 
 
-def run_opts(refill_threshold=0, block_threads=0, blocks_per_sm=0, nan_fast_forward=True, cold_state_in_smem=2, compaction=False, strict_tail=True):
+def run_opts(refill_threshold=0, block_threads=0, blocks_per_sm=0, nan_fast_forward=True, cold_state_in_smem=2, compaction=False, strict_tail=True, lane_yield=True):
     o = _abi.EmcRunOpts()
     o.refill_threshold = int(refill_threshold)
     o.block_threads = int(block_threads)
     o.blocks_per_sm = int(blocks_per_sm)
     o.nan_fast_forward = 1 if nan_fast_forward else 0
-    o.flags = (1 if compaction else 0) | (0 if strict_tail else 2)      # EMC_RUN_COMPACTION | EMC_RUN_NO_STRICT_TAIL (ignored by the engine since ABI 2 round 2)
+    # EMC_RUN_COMPACTION | EMC_RUN_NO_STRICT_TAIL (ignored by the engine since ABI 2 round 2) | EMC_RUN_NO_YIELD (ABI 3)
+    o.flags = (1 if compaction else 0) | (0 if strict_tail else 2) | (0 if lane_yield else 4)
     o.cold_state_in_smem = int(cold_state_in_smem) if cold_state_in_smem else -1    # 2 (default): bookkeeping + base state + RK4 accumulator; 1: bookkeeping; False: registers
     return o
 

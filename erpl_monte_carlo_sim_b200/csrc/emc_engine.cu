@@ -37,6 +37,10 @@
 
 using namespace emc;
 
+#ifdef EMC_YIELD_DEBUG
+#include <vector>
+#include <algorithm>
+#endif
 #define EMC_EXPORT extern "C" __attribute__((visibility("default")))
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -66,7 +70,25 @@ struct KernelArgs {
      * started has finished (flight_started == flight_done; blocks that become resident later find the queue empty) */
     int32_t epoch, flight_warps;
     unsigned long long *park_next, *flight_started, *flight_done, *strict_err;
+    /* lane hand-back (emc_counters.yielded): records of the flights that gave their lane to an unstarted sample, claimed in
+     * order once the sample queue is empty; histogram of the attitude-rate amplitudes seen at the hand-back point */
+    struct ParkRec *resume; int32_t resume_cap;      /* resume_cap records per warp, warp w owns [w cap, (w + 1) cap) */
+    int32_t yield_step, yield_half;    /* hand-back point and half of it in stored states; -1: off */
+#ifdef EMC_YIELD_DEBUG
+    unsigned int *dbg;                 /* [n][4] event times (globaltimer >> 10): start, hand-back, resume, end */
+#endif
 };
+#ifdef EMC_YIELD_DEBUG
+__device__ __forceinline__ void dbg_mark(const KernelArgs &a, int64_t idx, int ev)
+{
+    if (!a.dbg) return;
+    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    a.dbg[idx * 4 + ev] = (unsigned int)(t >> 10);
+}
+#define DBG_MARK(a, idx, ev) dbg_mark(a, idx, ev)
+#else
+#define DBG_MARK(a, idx, ev) ((void)0)
+#endif
 
 /* everything the strict kernel needs to finish a parked trajectory (its sample index is C.i[TI_SAMPLE]); `epoch` is
  * written last (after a fence) and marks the record as belonging to this run */
@@ -165,6 +187,7 @@ __device__ __forceinline__ T *opaque_shared(T *p)
 /* base state + RK4 accumulator of this thread's lane record (a column of the [14][BLOCK] pair block at the start of emc_dyn) */
 template <int BLOCK>
 struct SharedStore {
+    static constexpr bool kShared = true;      /* a copy of the object addresses the same state (lane hand-back helpers) */
     Pair *col;
     __device__ __forceinline__ SharedStore() : col(opaque_shared(reinterpret_cast<Pair *>(emc_dyn) + threadIdx.x)) {}
     __device__ __forceinline__ Pair s2(int p) const { return col[p * BLOCK]; }
@@ -178,7 +201,7 @@ struct SharedStore {
         for (int p = 0; p < 14; ++p) col[p * BLOCK] = reinterpret_cast<const Pair *>(emc_dyn)[p * BLOCK + src];
     }
 };
-struct RegStoreLane : RegStore { __device__ __forceinline__ void adopt(int) {} };
+struct RegStoreLane : RegStore { static constexpr bool kShared = false; __device__ __forceinline__ void adopt(int) {} };
 
 /* Tail compaction (north star: "retired with warp ballot/compaction").  Once the work queue is empty the warps of a
  * block thin out: a warp that still flies ONE trajectory costs its scheduler as many issue slots as a full one, and an
@@ -215,6 +238,138 @@ __device__ __forceinline__ void park_lane(const KernelArgs &a, int64_t idx, cons
     *reinterpret_cast<volatile int32_t *>(&P.epoch) = a.epoch;       /* publish */
 }
 
+/* ---- lane hand-back -------------------------------------------------------------------------------------------------
+ * A batch larger than the resident lanes is flown in waves, and the launch ends with its longest trajectory: T = start of
+ * that trajectory + its steps x the single-trajectory step latency.  Which sample flies longest is not known in advance,
+ * but after EMC_YIELD_STEP stored states it shows in the attitude rate: a flight whose amplitude max |omega| is still
+ * GROWING (it has risen by about a half or more since step EMC_YIELD_STEP / 2) is diverging and ends soon; one whose
+ * amplitude has settled flies on, and the longest flights of a batch are all of that kind (measured on the oracle, 6 000
+ * samples of the headline workload: ratio 1.00 .. 1.03 for every flight beyond 3 200 steps, median 8.8 and 10th percentile
+ * 1.9 for the flights of 2 000 .. 3 200 steps, 11 for the shorter ones; launch -> landing flights: 1.0, 90th percentile
+ * 1.3 — they never hand back).  So while unstarted samples are waiting, a flight that reaches that state with a growing
+ * amplitude puts its state aside (one record in global memory) and its lane starts a fresh sample: every sample is
+ * started within about two hand-back periods of the launch, and the long flights never wait.  The records of a warp form
+ * that warp's own list (head and tail are warp-uniform registers, positions come from ballots: no atomics, no waiting —
+ * one list for all warps was measured first: 1 776 warps claiming from one head with compare-and-swap cost more than the
+ * hand-back returns); a warp hands back no more than its share of the unstarted samples and resumes its records, oldest
+ * first, on the lanes that fall idle once the sample queue is empty.  Brackets are caches and the state is stored exactly,
+ * so the outputs are bit-identical to the undisturbed flight. */
+#ifndef EMC_YIELD_STEP
+#define EMC_YIELD_STEP 1000
+#endif
+#define EMC_YIELD_QUORUM 16         /* lanes of a warp that must want to hand back in the same iteration */
+#define EMC_YIELD_GROWTH 7          /* omega_code units: a rise by a factor of 1.7 .. 1.9 or more */
+
+/* max |omega| on a logarithmic scale that fits a byte: exponent and three mantissa bits from 2^-20 rad/s (0) up to
+ * 2^12 rad/s (255); NaN -> 255 */
+__device__ __forceinline__ int omega_code(double om)
+{
+    const int c = (__double2hiint(fabs(om)) >> 17) - ((1023 - 20) << 3);
+    return c < 0 ? 0 : (c > 255 ? 255 : c);
+}
+
+template <class Store, class CA>
+__device__ __forceinline__ void yield_lane(ParkRec &P, int64_t idx, const Store &st, const TrackHot &K, const CA &C)
+{
+    store_get(st, P.s);
+    P.K = K;
+    for (int f = 0; f < TC_DCOUNT; ++f) P.C.d[f] = C.getd(f);
+    for (int f = 0; f < TI_ICOUNT; ++f) P.C.i[f] = C.geti(f);
+    P.C.i[TI_SAMPLE] = (int32_t)idx;
+}
+
+/* The two refill-path pieces of the hand-back are kept OUT of line: inside the persistent loop they would only be code the
+ * hot path has to jump across and registers its allocation has to respect (measured: +2 % on the steady-state rate with
+ * both in line).  Values go in and come back by value so that nothing of the loop's state has to live in memory. */
+struct YieldOut { unsigned act, handed; int active; };
+
+/* the hand-back point of a warp whose lanes started together: the lanes of `ymask` (flights with a growing attitude
+ * oscillation) write their records at consecutive positions of the warp's list and become idle */
+template <int NW, class Store, class LANES>
+__device__ __noinline__ YieldOut yield_write(const KernelArgs a, LANES lanes, Store st, bool active, int64_t idx, unsigned act, unsigned ymask, int *tail_p)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    YieldOut r = { act, 0u, active ? 1 : 0 };
+    /* a warp hands back no more flights than its share of the samples that no lane could start at once: the fresh samples
+     * then spread evenly over the warps, and so do the records that wait for them to finish */
+    const int64_t all_warps = (int64_t)gridDim.x * NW;
+    const int my_share = (a.n > all_warps * 32) ? (int)((a.n - all_warps * 32 + all_warps - 1) / all_warps) : 0;
+    const int tail = *tail_p;
+    const int want = __popc(ymask);
+    int allow = my_share - tail;
+    allow = allow < 0 ? 0 : (allow > a.resume_cap - tail ? a.resume_cap - tail : allow);
+    /* only a warp whose flights are diverging TOGETHER hands back: its records are resumed as soon as those neighbours have
+     * ended, which is soon.  A lone growing flight among settled ones would wait for a lane of its warp for as long as the
+     * settled flights last (measured on launch -> landing flights: 0.4 % of them show a growing amplitude, and each
+     * handed-back one ended a third of a flight late). */
+    if (want < EMC_YIELD_QUORUM || *reinterpret_cast<volatile unsigned long long *>(a.queue) >= (unsigned long long)a.n) allow = 0;
+    allow = want < allow ? want : allow;
+    const int rank = __popc(ymask & ((1u << lane) - 1u));
+    const bool mine = ((ymask >> lane) & 1u) && rank < allow;
+    if (mine) {
+        auto &RC = lanes.rec(threadIdx.x);
+        ParkRec *const my_recs = a.resume + (size_t)(blockIdx.x * NW + (threadIdx.x >> 5)) * (size_t)a.resume_cap;
+        yield_lane(my_recs[tail + rank], idx, st, RC.K, lanes.cold(threadIdx.x));
+        r.active = 0;
+        DBG_MARK(a, idx, 1);
+    }
+    __syncwarp();
+    if (lane == 0) *tail_p = tail + allow;
+    __syncwarp();
+    r.handed = __ballot_sync(0xffffffffu, mine);
+    r.act = act & ~r.handed;
+    return r;
+}
+
+struct ResumeOut { unsigned act; int active; long long idx; };
+
+/* idle lanes (mask `idle`) resume the oldest handed-back flights of this warp */
+template <int NW, class Store, class LANES>
+__device__ __noinline__ ResumeOut yield_resume(const KernelArgs a, LANES lanes, Store st, bool active, int64_t idx, unsigned idle, int *head_p, int tail)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned FULL = 0xffffffffu;
+    ResumeOut r = { 0u, active ? 1 : 0, (long long)idx };
+    const int head = *head_p;
+    int k = tail - head;
+    const int nidle = __popc(idle);
+    const ParkRec *const my_recs = a.resume + (size_t)(blockIdx.x * NW + (threadIdx.x >> 5)) * (size_t)a.resume_cap;
+    k = k < nidle ? k : nidle;
+    const int rank = __popc(idle & ((1u << lane) - 1u));
+    if (((idle >> lane) & 1u) && rank < k) {
+        const ParkRec &P = my_recs[head + rank];
+        /* L2 reads (the record was written by a lane of this warp, before a __syncwarp) straight into the lane's slot */
+        idx = __ldcg(&P.C.i[TI_SAMPLE]);
+        auto &RC = lanes.rec(threadIdx.x);
+        const auto C = lanes.cold(threadIdx.x);
+        load_sample(c_model, a.scalars + idx, a.ld, a.wind ? a.wind + idx * a.wind_stride : nullptr, RC.S);
+        {
+            State s;
+            double *sp = reinterpret_cast<double *>(&s);
+            const double *src = reinterpret_cast<const double *>(&P.s);
+            for (int c = 0; c < 14; ++c) sp[c] = __ldcg(src + c);
+            store_put(st, s);
+        }
+        {
+            static_assert(sizeof(TrackHot) % 8 == 0, "TrackHot is copied word by word");
+            union { TrackHot k; unsigned long long w[sizeof(TrackHot) / 8]; } u;
+            const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&P.K);
+            for (int w = 0; w < (int)(sizeof(TrackHot) / 8); ++w) u.w[w] = __ldcg(src + w);
+            RC.K = u.k;
+        }
+        for (int f = 0; f < TC_DCOUNT; ++f) C.setd(f, __ldcg(&P.C.d[f]));
+        for (int f = 0; f < TI_ICOUNT; ++f) C.seti(f, __ldcg(&P.C.i[f]));
+        wind_bracket_reset(RC.WB);
+        r.active = 1; r.idx = idx;
+        DBG_MARK(a, idx, 2);
+    }
+    __syncwarp();
+    if (lane == 0) *head_p = head + k;
+    __syncwarp();
+    r.act = __ballot_sync(FULL, r.active != 0);
+    return r;
+}
+
 /* the persistent loop, generic over where the lane records live (REC: registers or shared memory) and the cold accessor */
 template <int BLOCK, class Store, bool COMPACT, int MK, int WK, class LANES>
 __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables &Tb, const double *alt, LANES lanes,
@@ -227,7 +382,17 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
     bool active = false, drained = false;
     Store st;
     int64_t idx = -1;
-    unsigned long long n_steps = 0, n_replay = 0, n_refill = 0, n_tape = 0;
+    unsigned long long n_steps = 0, n_replay = 0, n_refill = 0, n_tape = 0, n_yield = 0;
+    /* lane hand-back (above).  Its state is kept out of the registers that live through the step: head and tail of the
+     * warp's list in shared memory, one iteration counter and one flag in registers, everything else is recomputed where it
+     * is needed (the refill path) */
+    constexpr bool YIELD_OK = !COMPACT && Store::kShared;      /* the kernel instances whose lane state lives in shared memory */
+    const bool yield_on = YIELD_OK && a.yield_step > 0;
+    __shared__ int yl_head_s[NW], yl_tail_s[NW];
+    int &my_head = yl_head_s[threadIdx.x >> 5], &my_tail = yl_tail_s[threadIdx.x >> 5];
+    if (lane == 0) { my_head = 0; my_tail = 0; }
+    __syncwarp();
+    bool have_recs = false;         /* my_head < my_tail, warp-uniform: the idle path of the tail does not read shared memory for it */
     const int thr = a.refill_threshold < 1 ? 1 : (a.refill_threshold > 32 ? 32 : a.refill_threshold);
     /* compaction roles: blocks that share an SM (ids differ by the SM count) pick collectors on different schedulers */
     const int warp = threadIdx.x >> 5;
@@ -237,11 +402,40 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
     bool opened = false;          /* collector: `reserved` switched from "closed" to its own lane count */
     int taken = 0, last_cnt = 33; /* collector: board entries adopted; donor: active count at the last donation attempt */
 
+    int it = 0;                     /* steps taken by the lanes that started with the warp */
     for (;;) {
         /* ---- retire/refill: ONE ballot per iteration in the steady state; idle lanes are ranked with
          * popc and fetch their sample indices with one atomic per warp ---- */
         unsigned act = __ballot_sync(FULL, active);
-        if (act != FULL) {
+        /* the hand-back point (and the point half way to it) of the flights that started with this warp: one warp-uniform
+         * test per iteration, nothing in the step section (yield_step = yield_half = -1 when the hand-back is off) */
+        const bool trig = YIELD_OK && (it == a.yield_step || it == a.yield_half);
+        if (act != FULL || trig) {
+            unsigned handed = 0u;        /* lanes that hand their flight back in this iteration: they start fresh samples */
+            if (trig && yield_on) {
+                auto &RC = lanes.rec(threadIdx.x);
+                const bool cohort = active && RC.K.n_steps == it;       /* started with the warp, a step in every iteration since */
+                if (it != a.yield_step) {
+                    if (cohort) RC.K.om_half = (uint8_t)omega_code(lanes.cold(threadIdx.x).getd(TC_MAX_OM));
+                } else {
+                    const bool growing = cohort && !RC.K.finishing &&
+                                         omega_code(lanes.cold(threadIdx.x).getd(TC_MAX_OM)) - (int)RC.K.om_half >= EMC_YIELD_GROWTH;
+                    const unsigned ymask = __ballot_sync(FULL, growing);
+                    if (ymask && !drained) {
+                        const YieldOut r = yield_write<NW>(a, lanes, st, active, idx, act, ymask, &my_tail);
+                        act = r.act; handed = r.handed; active = r.active != 0; n_yield += (unsigned)__popc(r.handed & (1u << lane));
+                        have_recs = my_head < my_tail;
+                    }
+                }
+            }
+            if (have_recs && (~act & ~(drained ? 0u : handed))) {
+                /* a lane whose flight has ENDED resumes the oldest handed-back flight of this warp before it would start a
+                 * fresh sample (a record never waits for the whole queue); the lanes that have just handed back start fresh
+                 * samples — that is what they gave their flight up for — unless the queue is empty */
+                const ResumeOut r = yield_resume<NW>(a, lanes, st, active, idx, ~act & ~(drained ? 0u : handed), &my_head, my_tail);
+                act = r.act; active = r.active != 0; idx = r.idx;
+                have_recs = my_head < my_tail;
+            }
             if (!drained) {
                 const unsigned idle = ~act;
                 const int nidle = __popc(idle);
@@ -279,6 +473,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                             }
                             active = true;
                             ++n_refill;
+                            DBG_MARK(a, idx, 0);
                             /* the fast path assumes a regular sample (derivative<., ., REG>): anything else — a non-positive
                              * or non-finite mass, degenerate inertia constants — is flown by the strict continuation
                              * from its first state, with the reference's own guards */
@@ -347,7 +542,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                 }
             }
             if (act == 0u) {
-                if (drained) break;
+                if (drained && !have_recs) break;
                 continue;
             }
         }
@@ -376,6 +571,7 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                 /* blow-up under way: hand the trajectory to the strict continuation (emc_strict_kernel) */
                 park_lane(a, idx, st, K, C);
                 active = false;
+                DBG_MARK(a, idx, 3);
             } else if (retired) {
                 n_replay += (unsigned long long)rep;
                 State s; store_get(st, s);
@@ -393,8 +589,10 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
                     }
                 }
                 active = false;
+                DBG_MARK(a, idx, 3);
             }
         }
+        ++it;
     }
     if (compact && !collector && lane == 0) atomicAdd(&board->exited, 1);
     for (int o = 16; o > 0; o >>= 1) {
@@ -402,12 +600,14 @@ __device__ __forceinline__ void flight_loop(const KernelArgs &a, const DevTables
         n_replay += __shfl_down_sync(FULL, n_replay, o);
         n_refill += __shfl_down_sync(FULL, n_refill, o);
         n_tape += __shfl_down_sync(FULL, n_tape, o);
+        n_yield += __shfl_down_sync(FULL, n_yield, o);
     }
     if (lane == 0) {
         if (n_steps) atomicAdd(a.counters + 0, n_steps);
         if (n_replay) atomicAdd(a.counters + 1, n_replay);
         if (n_refill) atomicAdd(a.counters + 3, n_refill);
         if (n_tape) atomicAdd(a.counters + 7, n_tape);
+        if (n_yield) atomicAdd(a.counters + 20, n_yield);
         if (a.flight_done) { __threadfence(); atomicAdd(a.flight_done, 1ull); }   /* after every park of this warp */
     }
 }
@@ -526,7 +726,7 @@ struct StrictTape {
  *     (emc_strict_tail_kernel: usually nothing).  So the pair cannot deadlock and cannot lose a record. */
 #ifndef EMC_STRICT_BLOCK
 #define EMC_STRICT_BLOCK 64
-#define EMC_STRICT_MINB 5
+#define EMC_STRICT_MINB 8        /* 128 registers: three flight blocks (<= 144 registers a thread) and a consumer block share an SM */
 #endif
 __device__ __forceinline__ bool no_more_parks(const KernelArgs &a)
 {
@@ -788,6 +988,10 @@ struct emc_ctx {
     int32_t *d_bt_count = nullptr; size_t cap_bt_count = 0;
     int64_t *d_bt_list = nullptr; size_t cap_bt_list = 0;
     unsigned char *d_gcold = nullptr; size_t cap_gcold = 0;     /* GlobalCold arrays of the 16-warp kernel */
+    ParkRec *d_resume = nullptr; size_t cap_resume = 0;         /* flights that handed their lane back (emc_counters.yielded) */
+#ifdef EMC_YIELD_DEBUG
+    unsigned int *dbg = nullptr; int64_t dbg_n = 0;
+#endif
     ParkRec *d_park = nullptr; size_t cap_park = 0;             /* trajectories parked for the strict continuation */
     int64_t bt_n_sel = 0; int32_t bt_stride = 0, bt_max = 0;
     bool bt_armed = false;                    /* a request waits for the next run */
@@ -867,7 +1071,7 @@ EMC_EXPORT int emc_destroy(emc_ctx *ctx)
         std::lock_guard<std::mutex> lk(g_owner_mu);
         if (ctx->device >= 0 && ctx->device < 64 && g_owner[ctx->device] == ctx) g_owner[ctx->device] = nullptr;
     }
-    cudaFree(ctx->d_out1); cudaFree(ctx->d_iout1); cudaFree(ctx->d_bt_slot); cudaFree(ctx->d_bt_rows); cudaFree(ctx->d_bt_count); cudaFree(ctx->d_bt_list); cudaFree(ctx->d_gcold); cudaFree(ctx->d_park);
+    cudaFree(ctx->d_out1); cudaFree(ctx->d_iout1); cudaFree(ctx->d_bt_slot); cudaFree(ctx->d_bt_rows); cudaFree(ctx->d_bt_count); cudaFree(ctx->d_bt_list); cudaFree(ctx->d_gcold); cudaFree(ctx->d_park); cudaFree(ctx->d_resume);
     cudaFree(ctx->d_wind_alt); cudaFree(ctx->d_ctrl); cudaFree(ctx->d_scalars); cudaFree(ctx->d_wind);
     cudaFree(ctx->d_out); cudaFree(ctx->d_iout); cudaFree(ctx->d_tape); cudaFree(ctx->d_scratch); cudaFree(ctx->d_partial); cudaFree(ctx->d_summary); cudaFree(ctx->d_disp); cudaFree(ctx->d_draws);
     for (int i = 0; i < 5; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -993,6 +1197,32 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
         if (ctx->cap_park != cap_before) CK(cudaMemsetAsync(ctx->d_park, 0, sizeof(ParkRec) * ctx->cap_park, ctx->stream));
         a.park = ctx->d_park; a.park_count = ctx->d_ctrl + 11;
     }
+    /* lane hand-back: only where a launch has more samples than resident lanes (otherwise every sample starts at once) and
+     * not so many that its last wave is a small part of it */
+    a.yield_step = -1; a.yield_half = -1; a.resume = nullptr;
+    {
+        const int64_t resident = (int64_t)ctx->sm_count * 384;
+        const char *ys = getenv("EMC_YIELD_STEP");
+        const int step = ys ? atoi(ys) : EMC_YIELD_STEP;
+        if (!(o.flags & EMC_RUN_NO_YIELD) && !a.compact && !a.tape && step > 0 && a.n > resident && a.n <= 8 * resident) {
+            /* one list per warp (at most 16 warps per SM at >= 128 registers): twice a warp's share of the batch, rounded up */
+            const int64_t warps = (int64_t)ctx->sm_count * 16;
+            const int32_t cap = (int32_t)(2 * ((a.n + (int64_t)ctx->sm_count * 12 - 1) / ((int64_t)ctx->sm_count * 12)) + 64);
+            CK(grow(&ctx->d_resume, &ctx->cap_resume, (size_t)(warps * cap)));
+            a.resume_cap = cap;
+            a.resume = ctx->d_resume;
+            a.yield_step = step; a.yield_half = step >> 1;
+        }
+#ifdef EMC_YIELD_DEBUG
+        a.dbg = nullptr;
+        if (getenv("EMC_YIELD_DEBUG") && a.n >= 50000 && a.n <= 200000) {
+            static unsigned int *d_dbg = nullptr; static size_t cap = 0;
+            CK(grow(&d_dbg, &cap, (size_t)a.n * 4));
+            CK(cudaMemsetAsync(d_dbg, 0, sizeof(unsigned int) * 4 * (size_t)a.n, ctx->stream));
+            a.dbg = d_dbg; ctx->dbg = d_dbg; ctx->dbg_n = a.n;
+        } else ctx->dbg = nullptr;
+#endif
+    }
     a.wind_alt = ctx->d_wind_alt;
     a.queue = ctx->d_ctrl; a.counters = ctx->d_ctrl + 1;
     if (a.tape) a.tape_n = reinterpret_cast<int64_t *>(ctx->d_ctrl + 5);
@@ -1103,6 +1333,33 @@ static int finish_counters(emc_ctx *ctx)
     ctx->counters.handovers = (int64_t)h[9];
     ctx->counters.strict_steps = (int64_t)h[10];
     ctx->counters.parked = (int64_t)h[11];
+    ctx->counters.yielded = (int64_t)h[21];
+#ifdef EMC_YIELD_DEBUG
+    if (ctx->dbg) {
+        std::vector<unsigned int> v((size_t)ctx->dbg_n * 4);
+        CK(cudaMemcpy(v.data(), ctx->dbg, v.size() * 4, cudaMemcpyDeviceToHost));
+        unsigned int t0 = 0xffffffffu;
+        for (int64_t i = 0; i < ctx->dbg_n; ++i) if (v[i * 4] && v[i * 4] < t0) t0 = v[i * 4];
+        const char *nm[4] = { "start", "handback", "resume", "end" };
+        for (int e = 0; e < 4; ++e) {
+            std::vector<double> x;
+            for (int64_t i = 0; i < ctx->dbg_n; ++i) if (v[i * 4 + e]) x.push_back((v[i * 4 + e] - t0) * 1.024e-3);
+            std::sort(x.begin(), x.end());
+            if (x.empty()) continue;
+            fprintf(stderr, "[emc-dbg] %-8s n=%zu  min %.2f p10 %.2f p50 %.2f p90 %.2f p99 %.2f max %.2f ms\n", nm[e], x.size(), x[0], x[x.size() / 10], x[x.size() / 2],
+                    x[x.size() * 9 / 10], x[x.size() * 99 / 100], x.back());
+        }
+        /* the five flights that end last: their sample, start, hand-back, resume, end */
+        std::vector<std::pair<unsigned int, int64_t>> ends;
+        for (int64_t i = 0; i < ctx->dbg_n; ++i) ends.push_back({ v[i * 4 + 3], i });
+        std::sort(ends.begin(), ends.end());
+        for (size_t k = ends.size() >= 5 ? ends.size() - 5 : 0; k < ends.size(); ++k) {
+            const int64_t i = ends[k].second;
+            fprintf(stderr, "[emc-dbg] late sample %lld: start %.2f handback %.2f resume %.2f end %.2f ms\n", (long long)i, (v[i * 4] - t0) * 1.024e-3,
+                    v[i * 4 + 1] ? (v[i * 4 + 1] - t0) * 1.024e-3 : -1.0, v[i * 4 + 2] ? (v[i * 4 + 2] - t0) * 1.024e-3 : -1.0, (v[i * 4 + 3] - t0) * 1.024e-3);
+        }
+    }
+#endif
     if (h[14]) return fail(ctx, EMC_ERR_CUDA, "strict continuation: " + std::to_string(h[14]) + " park records do not belong to this run (epoch " +
                            std::to_string(ctx->epoch) + ", parked " + std::to_string(h[11]) + ", tickets " + std::to_string(h[12]) + ")");
     ctx->strict_left_early = (int64_t)h[15];

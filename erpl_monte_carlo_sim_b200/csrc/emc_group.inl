@@ -192,7 +192,7 @@ EMC_EXPORT int emc_group_get_counters(const emc_group *g, emc_counters *c)
         const emc_counters &k = x->counters;
         c->rk4_steps += k.rk4_steps; c->replay_steps += k.replay_steps; c->rail_steps += k.rail_steps; c->refills += k.refills;
         c->kernel_launches += k.kernel_launches; c->tape_rows += k.tape_rows; c->handovers += k.handovers;
-        c->parked += k.parked; c->strict_steps += k.strict_steps;
+        c->parked += k.parked; c->strict_steps += k.strict_steps; c->yielded += k.yielded;
         if (k.rail_ms > c->rail_ms) c->rail_ms = k.rail_ms;
         if (k.flight_ms > c->flight_ms) c->flight_ms = k.flight_ms;
         if (k.strict_ms > c->strict_ms) c->strict_ms = k.strict_ms;

@@ -884,6 +884,8 @@ struct TrackHot {
     bool finishing;   /* loop ended: one more stage-0 pass exports the last stored state's diagnostics */
     int8_t replay;    /* NaN fast-forward mode (0 none, 1 all-NaN, 2 altitude-NaN ballistic): t is replayed to max_time */
     int8_t term;      /* emc_termination */
+    uint8_t om_half;  /* flight kernel: the attitude-rate amplitude half way to the lane hand-back point (emc_counters.yielded), on
+                       * a logarithmic scale (omega_code) */
 };
 /* COLD part: touched once per step at most (running maxima, event times, tape cursor).  The flight kernel may keep it
  * in global memory, field-major over the resident lanes (coalesced, L2-resident), to fit 16 warps per SM into the
@@ -913,7 +915,7 @@ EMC_HD void track_init(TrackHot &K, const CA &C, const State &s, double t_rail)
     C.setd(TC_LATCH, 0.0); C.setd(TC_MAX_COAST, 0.0);
     C.setd(TC_BURNOUT_TIME, 0.0); K.burnout_found = false;
     C.setd(TC_CHUTE_TIME, NAN); K.chute = false; K.apogee_detected = false;
-    K.n_steps = 0; K.term = EMC_TERM_NONE; K.finishing = false; K.replay = 0;
+    K.n_steps = 0; K.term = EMC_TERM_NONE; K.finishing = false; K.replay = 0; K.om_half = 0;
     C.seti(TI_BT_SLOT, -1); C.seti(TI_BT_NEXT, 0);
     C.setd(TC_MAX_MACH2, -INFINITY); C.setd(TC_MAX_Q, -INFINITY); C.setd(TC_MAX_V2, -INFINITY); C.setd(TC_MAX_OM, -INFINITY);
     C.setd(TC_MIN_STAB, INFINITY); C.setd(TC_MAX_STAB, -INFINITY); C.setd(TC_MAX_AOA, -INFINITY);

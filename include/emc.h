@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EMC_ABI_VERSION 2
+#define EMC_ABI_VERSION 3
 
 /* ---- limits of the run-constant tables (rocket.py:43-53, motor.py:31-41) ---- */
 #define EMC_MAX_CD_KNOTS 16
@@ -175,6 +175,7 @@ typedef struct emc_run_opts {
                                      — step count, termination, first-NaN index — is the reference's; so is every IRREGULAR sample (dry mass
                                      not positive and finite, propellant mass negative or not finite), from its first state: the fast path
                                      drops the guards of simulator.py:315-318,431-436 that only such samples can trigger. */
+#define EMC_RUN_NO_YIELD 4        /* ABI 3: switch off the lane hand-back described at emc_counters.yielded (A/B runs, scheduling-invariance tests) */
 #define EMC_RUN_COMPACTION 1      /* tail compaction: once the work queue is empty, sparse warps hand their trajectories (lane records in
                                      shared memory, addressed by slot) to one collector warp per block and exit.  Bit-identical outputs.
                                      Off by default: measured on the B200 the slot indirection costs more than the compacted tail
@@ -196,6 +197,11 @@ typedef struct emc_counters {
     int64_t strict_steps;     /* ABI 2: RK4 steps taken there (not included in rk4_steps) */
     double strict_ms;         /* ABI 2: device time between the end of the flight kernel and the end of the strict continuation (it runs
                                * concurrently on a second stream: normally the cost of the final sweep only) */
+    int64_t yielded;          /* ABI 3: trajectories that gave their lane back once, at stored state EMC_YIELD_STEP, while unstarted
+                               * samples were waiting, and were resumed later (a batch larger than the resident lanes: every sample is
+                               * STARTED early, and the flights whose attitude rate is still small — the stable ones, which fly longest —
+                               * keep their lane, so the longest trajectory of the batch is not one that started in the last wave).
+                               * Outputs are bit-identical with and without (EMC_RUN_NO_YIELD). */
 } emc_counters;
 
 int emc_abi_version(void);

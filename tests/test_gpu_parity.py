@@ -199,6 +199,33 @@ def test_gpu_full_size_properties(engine):
     util.assert_summary_close(out[:, pick], ref, what="100k spot check", sens=sens)
 
 
+def test_gpu_lane_hand_back_is_invisible(engine):
+    """A batch larger than the resident lanes: after 1 000 stored states the flights of a warp whose attitude oscillation is
+    growing put their state aside and their lanes start unstarted samples; the records are resumed once the queue is empty
+    (emc_counters.yielded).  Outputs with and without the hand-back are bit-identical on the headline workload; launch ->
+    landing flights (settled attitude) never hand back; a batch that fits the resident lanes has nothing to hand back for."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    md, blk, wind, _ = bench.make_workload("c3", 100_000, 0)
+    engine.set_model(md)
+    on = engine.run_batch(blk, wind)
+    c = engine.counters()
+    assert c["yielded"] > 20_000 and c["refills"] == 100_000
+    steps = on[1][_abi.IOUT["n_steps"]].astype(np.int64)
+    assert c["rk4_steps"] + c["strict_steps"] + c["replay_steps"] == int(steps.sum())      # a resumed flight repeats no step
+    off = engine.run_batch(blk, wind, opts=_lib.run_opts(lane_yield=False))
+    assert engine.counters()["yielded"] == 0
+    np.testing.assert_array_equal(on[1], off[1]); np.testing.assert_array_equal(on[0], off[0])
+    small = engine.run_batch(np.ascontiguousarray(blk[:, :40_000]), np.ascontiguousarray(wind[:40_000]))
+    assert engine.counters()["yielded"] == 0
+    np.testing.assert_array_equal(small[1], on[1][:, :40_000]); np.testing.assert_array_equal(small[0], on[0][:, :40_000])
+    md, blk, wind, _ = bench.make_workload("planar", 60_000, 0)
+    engine.set_model(md)
+    engine.run_batch(blk, wind)
+    assert engine.counters()["yielded"] == 0
+
+
 def test_gpu_bench_workload_valid_flights_exact(engine):
     """On the headline workload itself (BASELINE C3, reference dispersions): the set of valid (non-outlier) flights is the
     oracle's, every valid flight has the oracle's integer outputs exactly and its summaries within 1e-6 (10x the oracle's

@@ -42,7 +42,7 @@ o100, io100 = eng.run_batch(z["blk"], z["wind"], opts=opts)
 import hashlib  # noqa: E402
 res["c3_100k_sha"] = hashlib.sha1(np.ascontiguousarray(o100).tobytes() + np.ascontiguousarray(io100).tobytes()).hexdigest()[:12]
 del o100, io100
-res["handovers"] = c.get("handovers"); res["parked"] = c.get("parked"); res["strict_ms"] = round(c.get("strict_ms", 0.0), 3); res["strict_steps"] = c.get("strict_steps"); res["c3_100k_ms"] = round(c["flight_ms"], 3); res["c3_100k_gsteps"] = round(c["rk4_steps"] / c["flight_ms"] / 1e6, 3)
+res["handovers"] = c.get("handovers"); res["yielded"] = c.get("yielded"); res["parked"] = c.get("parked"); res["strict_ms"] = round(c.get("strict_ms", 0.0), 3); res["strict_steps"] = c.get("strict_steps"); res["c3_100k_ms"] = round(c["flight_ms"], 3); res["c3_100k_gsteps"] = round(c["rk4_steps"] / c["flight_ms"] / 1e6, 3)
 big_b = np.ascontiguousarray(np.tile(z["blk"], (1, 8))); big_w = np.ascontiguousarray(np.tile(z["wind"], (8, 1, 1)))
 c = best_of(big_b, big_w, 2)
 res["c3_800k_ms"] = round(c["flight_ms"], 3); res["c3_800k_gsteps"] = round(c["rk4_steps"] / c["flight_ms"] / 1e6, 3)
