@@ -37,8 +37,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE flight-kernel launch on this workload (100 k C3 samples), from
-# `ncu --set full` (profiles/): algorithmic bytes are 30.4 MB in + 30 MB out (the rail kernel writes part of the outputs).
-FLIGHT_KERNEL_DRAM_BYTES_100K = 32.82e6
+# `ncu --set full` (profiles/r2e_flight_kernel_bench.txt: 41.9 MB read + 11.3 MB written, of which ~24 MB are the records of the lane
+# hand-back, written once and read once): algorithmic bytes are 30.4 MB in + 30 MB out (the rail kernel writes part of the outputs).
+FLIGHT_KERNEL_DRAM_BYTES_100K = 53.2e6
 STATS_LAUNCHES_FUSED = 2 + 1 + 2 + 12   # the statistics chain: moments1 + finish, plan, moments2 + finish, 6 x (digit histogram + digit decision); NCCL kernels not counted
 FLOP_PER_STEP = 1600.0          # 4*348 + 203 ~ 1.6 kflop per accepted RK4 step
 CSV_ALT = np.array([0.0, 5000.0, 10000.0, 15000.0, 20000.0, 25000.0])                # sample_wind.csv:2-7
@@ -400,11 +401,11 @@ def main():
     sampler = ClockSampler(local); sampler.start()
     barrier()
     t0 = time.perf_counter()
-    flight_ms = rail_ms = strict_ms = 0.0; rk4 = replay = strict_steps = parked = 0
+    flight_ms = rail_ms = strict_ms = 0.0; rk4 = replay = strict_steps = parked = yielded = 0
     for _ in range(a.steps):
         c = step_resident()
         flight_ms += c["flight_ms"]; rail_ms += c["rail_ms"]; rk4 += c["rk4_steps"]; replay += c["replay_steps"]
-        strict_ms += c["strict_ms"]; strict_steps += c["strict_steps"]; parked += c["parked"]
+        strict_ms += c["strict_ms"]; strict_steps += c["strict_steps"]; parked += c["parked"]; yielded += c.get("yielded", 0)
     barrier()
     wall = time.perf_counter() - t0
     sampler.stop_flag = True; sampler.join(timeout=2)
@@ -435,11 +436,11 @@ def main():
 
     per_rank = gather_ranks([flight_ms / a.steps, rail_ms / a.steps], world, dev)
     tmax = torch.tensor([wall, wall_e2e, flight_ms, rail_ms, strict_ms], dtype=torch.float64, device=dev)
-    tsum = torch.tensor([float(rk4), float(replay), float(strict_steps), float(parked)], dtype=torch.float64, device=dev)
+    tsum = torch.tensor([float(rk4), float(replay), float(strict_steps), float(parked), float(yielded)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tsum)
     wall, wall_e2e, flight_ms, rail_ms, strict_ms = tmax.tolist()
-    rk4_all, replay_all, strict_all, parked_all = tsum.tolist()
+    rk4_all, replay_all, strict_all, parked_all, yielded_all = tsum.tolist()
 
     extras = api = None
     if not a.no_extras and a.workload == "c3":
@@ -468,6 +469,9 @@ def main():
             "strict_continuation": {"parked_trajectories_per_step": parked_all / a.steps, "rk4_steps_per_step": strict_all / a.steps,
                                     "what": "blown-up flights (|v| > 1e7 m/s or |omega| > 1000 rad/s) are finished by emc_strict_kernel in the "
                                             "reference's operation order so that step counts / terminations / first-NaN indices are the reference's"},
+            "lane_hand_back": {"trajectories_per_step": yielded_all / a.steps,
+                               "what": "flights (attitude oscillation still growing after 1 000 stored states) that gave their lane to an unstarted sample "
+                                       "and were resumed later: every sample starts early and the long flights never wait; outputs bit-identical"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf * world, "unit": "TFLOP/s",
                          "frac": achieved_tf / (peak_tf * world),
                          "traffic": FLIGHT_KERNEL_DRAM_BYTES_100K if (a.workload == "c3" and n == 100_000) else None, "traffic_unit": "bytes/launch (ncu)",
