@@ -197,11 +197,13 @@ typedef struct emc_counters {
     int64_t strict_steps;     /* ABI 2: RK4 steps taken there (not included in rk4_steps) */
     double strict_ms;         /* ABI 2: device time between the end of the flight kernel and the end of the strict continuation (it runs
                                * concurrently on a second stream: normally the cost of the final sweep only) */
-    int64_t yielded;          /* ABI 3: trajectories that gave their lane back once, at stored state EMC_YIELD_STEP, while unstarted
-                               * samples were waiting, and were resumed later (a batch larger than the resident lanes: every sample is
-                               * STARTED early, and the flights whose attitude rate is still small — the stable ones, which fly longest —
-                               * keep their lane, so the longest trajectory of the batch is not one that started in the last wave).
-                               * Outputs are bit-identical with and without (EMC_RUN_NO_YIELD). */
+    int64_t yielded;          /* ABI 3: trajectories that gave their lane back once, after 1 000 stored states, while unstarted samples
+                               * were waiting, and were resumed later (a batch larger than the resident lanes, up to 8 x as large: every
+                               * sample is STARTED early, and the flights whose attitude oscillation has settled — the ones that fly
+                               * longest — keep their lane, so the longest trajectory of the batch is not one that started in the last
+                               * wave; only warps whose lanes started together and of which at least half show a growing oscillation hand
+                               * back: launch -> landing flights never do).  Outputs are bit-identical with and without it
+                               * (EMC_RUN_NO_YIELD).  DESIGN.md section 5. */
 } emc_counters;
 
 int emc_abi_version(void);
