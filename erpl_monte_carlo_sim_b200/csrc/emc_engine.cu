@@ -1197,32 +1197,7 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
         if (ctx->cap_park != cap_before) CK(cudaMemsetAsync(ctx->d_park, 0, sizeof(ParkRec) * ctx->cap_park, ctx->stream));
         a.park = ctx->d_park; a.park_count = ctx->d_ctrl + 11;
     }
-    /* lane hand-back: only where a launch has more samples than resident lanes (otherwise every sample starts at once) and
-     * not so many that its last wave is a small part of it */
     a.yield_step = -1; a.yield_half = -1; a.resume = nullptr;
-    {
-        const int64_t resident = (int64_t)ctx->sm_count * 384;
-        const char *ys = getenv("EMC_YIELD_STEP");
-        const int step = ys ? atoi(ys) : EMC_YIELD_STEP;
-        if (!(o.flags & EMC_RUN_NO_YIELD) && !a.compact && !a.tape && step > 0 && a.n > resident && a.n <= 8 * resident) {
-            /* one list per warp (at most 16 warps per SM at >= 128 registers): twice a warp's share of the batch, rounded up */
-            const int64_t warps = (int64_t)ctx->sm_count * 16;
-            const int32_t cap = (int32_t)(2 * ((a.n + (int64_t)ctx->sm_count * 12 - 1) / ((int64_t)ctx->sm_count * 12)) + 64);
-            CK(grow(&ctx->d_resume, &ctx->cap_resume, (size_t)(warps * cap)));
-            a.resume_cap = cap;
-            a.resume = ctx->d_resume;
-            a.yield_step = step; a.yield_half = step >> 1;
-        }
-#ifdef EMC_YIELD_DEBUG
-        a.dbg = nullptr;
-        if (getenv("EMC_YIELD_DEBUG") && a.n >= 50000 && a.n <= 200000) {
-            static unsigned int *d_dbg = nullptr; static size_t cap = 0;
-            CK(grow(&d_dbg, &cap, (size_t)a.n * 4));
-            CK(cudaMemsetAsync(d_dbg, 0, sizeof(unsigned int) * 4 * (size_t)a.n, ctx->stream));
-            a.dbg = d_dbg; ctx->dbg = d_dbg; ctx->dbg_n = a.n;
-        } else ctx->dbg = nullptr;
-#endif
-    }
     a.wind_alt = ctx->d_wind_alt;
     a.queue = ctx->d_ctrl; a.counters = ctx->d_ctrl + 1;
     if (a.tape) a.tape_n = reinterpret_cast<int64_t *>(ctx->d_ctrl + 5);
@@ -1266,6 +1241,36 @@ static int run_device(emc_ctx *ctx, KernelArgs a, const emc_run_opts *opts)
     cudaError_t e;
     const bool cold = o.cold_state_in_smem >= 0;
     const bool store = o.cold_state_in_smem == 0 || o.cold_state_in_smem >= 2;   /* default: base state + RK4 accumulator in shared memory as well */
+#ifdef EMC_SLIM
+    const bool default_instance = true;
+#else
+    const bool default_instance = bt == 128 && bps == 3 && store;
+#endif
+    /* lane hand-back: the default kernel instance, and only where a launch has more samples than resident lanes (otherwise
+     * every sample starts at once) and not so many that its last wave is a small part of it */
+    {
+        const int64_t resident = (int64_t)ctx->sm_count * 384;
+        const char *ys = getenv("EMC_YIELD_STEP");
+        const int step = ys ? atoi(ys) : EMC_YIELD_STEP;
+        if (default_instance && !(o.flags & EMC_RUN_NO_YIELD) && !a.compact && !a.tape && step > 0 && a.n > resident && a.n <= 8 * resident) {
+            /* one list per warp (at most 16 warps per SM at >= 128 registers): twice a warp's share of the batch, rounded up */
+            const int64_t warps = (int64_t)ctx->sm_count * 16;
+            const int32_t cap = (int32_t)(2 * ((a.n + (int64_t)ctx->sm_count * 12 - 1) / ((int64_t)ctx->sm_count * 12)) + 64);
+            CK(grow(&ctx->d_resume, &ctx->cap_resume, (size_t)(warps * cap)));
+            a.resume_cap = cap;
+            a.resume = ctx->d_resume;
+            a.yield_step = step; a.yield_half = step >> 1;
+        }
+#ifdef EMC_YIELD_DEBUG
+        a.dbg = nullptr;
+        if (getenv("EMC_YIELD_DEBUG") && a.n >= 50000 && a.n <= 200000) {
+            static unsigned int *d_dbg = nullptr; static size_t cap = 0;
+            CK(grow(&d_dbg, &cap, (size_t)a.n * 4));
+            CK(cudaMemsetAsync(d_dbg, 0, sizeof(unsigned int) * 4 * (size_t)a.n, ctx->stream));
+            a.dbg = d_dbg; ctx->dbg = d_dbg; ctx->dbg_n = a.n;
+        } else ctx->dbg = nullptr;
+#endif
+    }
 #ifdef EMC_SLIM     /* developer builds (tools/build_variant.sh): only the default instances, seconds instead of a minute */
     (void)bt; (void)bps; (void)cold; (void)store;
 #ifndef EMC_SLIM_BLOCK
