@@ -59,6 +59,18 @@ def test_struct_layout_matches_header():
                    C.sizeof(_abi.EmcCounters), _abi.IN_COUNT, _abi.OUT_COUNT, _abi.IOUT_COUNT]
 
 
+def test_run_option_flags_match_header():
+    """The flag bits the Python wrapper sets are the header's EMC_RUN_* values (lane hand-back off = EMC_RUN_NO_YIELD)."""
+    from erpl_monte_carlo_sim_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "emc.h")).read()
+    bits = {k: int(v) for k, v in re.findall(r"#define (EMC_RUN_\w+) (\d+)", hdr)}
+    assert bits == {"EMC_RUN_COMPACTION": 1, "EMC_RUN_NO_STRICT_TAIL": 2, "EMC_RUN_NO_YIELD": 4}
+    assert _lib.run_opts().flags == 0
+    assert _lib.run_opts(lane_yield=False).flags == bits["EMC_RUN_NO_YIELD"]
+    assert _lib.run_opts(compaction=True, lane_yield=False).flags == bits["EMC_RUN_NO_YIELD"] | bits["EMC_RUN_COMPACTION"]
+    assert "yielded" in dict(_abi.EmcCounters._fields_) and _abi.ABI_VERSION == int(re.search(r"#define EMC_ABI_VERSION (\d+)", hdr).group(1))
+
+
 @pytest.mark.skipif(conftest.HAS_CUDA, reason="checks the no-device behaviour")
 def test_no_device_is_a_loud_error():
     with pytest.raises(_lib.EmcError, match="EMC_ERR_NO_DEVICE"):

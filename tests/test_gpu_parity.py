@@ -217,6 +217,18 @@ def test_gpu_lane_hand_back_is_invisible(engine):
     off = engine.run_batch(blk, wind, opts=_lib.run_opts(lane_yield=False))
     assert engine.counters()["yielded"] == 0
     np.testing.assert_array_equal(on[1], off[1]); np.testing.assert_array_equal(on[0], off[0])
+    # the downsampled batch tape of flights that are handed back and resumed is the tape of the undisturbed flights
+    picks = np.arange(0, 100_000, 1563, dtype=np.int64)
+    tapes = []
+    for kw in (dict(), dict(lane_yield=False)):
+        engine.tape_request(picks, 50, 200)
+        engine.run_batch(blk, wind, opts=_lib.run_opts(**kw))
+        tapes.append((engine.counters()["yielded"], engine.counters()["tape_rows"]) + tuple(engine.tape_fetch()))
+    assert tapes[0][0] > 20_000 and tapes[1][0] == 0 and tapes[0][1] == tapes[1][1] > 0
+    np.testing.assert_array_equal(tapes[0][3], tapes[1][3])
+    for k in range(len(picks)):
+        m = int(tapes[0][3][k])
+        np.testing.assert_array_equal(tapes[0][2][k, :m], tapes[1][2][k, :m])
     small = engine.run_batch(np.ascontiguousarray(blk[:, :40_000]), np.ascontiguousarray(wind[:40_000]))
     assert engine.counters()["yielded"] == 0
     np.testing.assert_array_equal(small[1], on[1][:, :40_000]); np.testing.assert_array_equal(small[0], on[0][:, :40_000])
