@@ -37,9 +37,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE flight-kernel launch on this workload (100 k C3 samples), from
-# `ncu --set full` (profiles/r2e_flight_kernel_bench.txt: 41.9 MB read + 11.3 MB written, of which ~24 MB are the records of the lane
+# `ncu --set full` (profiles/r2e_flight_kernel_bench.txt: 41.9 MB read + 11.1 MB written, of which ~24 MB are the records of the lane
 # hand-back, written once and read once): algorithmic bytes are 30.4 MB in + 30 MB out (the rail kernel writes part of the outputs).
-FLIGHT_KERNEL_DRAM_BYTES_100K = 53.2e6
+FLIGHT_KERNEL_DRAM_BYTES_100K = 53.0e6
 STATS_LAUNCHES_FUSED = 2 + 1 + 2 + 12   # the statistics chain: moments1 + finish, plan, moments2 + finish, 6 x (digit histogram + digit decision); NCCL kernels not counted
 FLOP_PER_STEP = 1600.0          # 4*348 + 203 ~ 1.6 kflop per accepted RK4 step
 CSV_ALT = np.array([0.0, 5000.0, 10000.0, 15000.0, 20000.0, 25000.0])                # sample_wind.csv:2-7
@@ -470,7 +470,7 @@ def main():
                                     "what": "blown-up flights (|v| > 1e7 m/s or |omega| > 1000 rad/s) are finished by emc_strict_kernel in the "
                                             "reference's operation order so that step counts / terminations / first-NaN indices are the reference's"},
             "lane_hand_back": {"trajectories_per_step": yielded_all / a.steps,
-                               "what": "flights (attitude oscillation still growing after 1 000 stored states) that gave their lane to an unstarted sample "
+                               "what": "flights (attitude oscillation still growing after 900 stored states) that gave their lane to an unstarted sample "
                                        "and were resumed later: every sample starts early and the long flights never wait; outputs bit-identical"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf * world, "unit": "TFLOP/s",
                          "frac": achieved_tf / (peak_tf * world),

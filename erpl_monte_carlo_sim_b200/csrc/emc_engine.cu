@@ -242,20 +242,22 @@ __device__ __forceinline__ void park_lane(const KernelArgs &a, int64_t idx, cons
  * A batch larger than the resident lanes is flown in waves, and the launch ends with its longest trajectory: T = start of
  * that trajectory + its steps x the single-trajectory step latency.  Which sample flies longest is not known in advance,
  * but after EMC_YIELD_STEP stored states it shows in the attitude rate: a flight whose amplitude max |omega| is still
- * GROWING (it has risen by about a half or more since step EMC_YIELD_STEP / 2) is diverging and ends soon; one whose
- * amplitude has settled flies on, and the longest flights of a batch are all of that kind (measured on the oracle, 6 000
- * samples of the headline workload: ratio 1.00 .. 1.03 for every flight beyond 3 200 steps, median 8.8 and 10th percentile
- * 1.9 for the flights of 2 000 .. 3 200 steps, 11 for the shorter ones; launch -> landing flights: 1.0, 90th percentile
- * 1.3 — they never hand back).  So while unstarted samples are waiting, a flight that reaches that state with a growing
+ * GROWING (it has risen by a factor of ~1.8 or more since step EMC_YIELD_STEP / 2) is diverging and ends soon; one whose
+ * amplitude has settled flies on, and the longest flights of a batch are all of that kind (measured on the oracle, 14 000
+ * samples of the headline workload, states 1 000 against 500: ratio 1.00 .. 1.24 for every flight beyond 3 200 steps,
+ * median 8.8 and 10th percentile 1.9 for the flights of 2 000 .. 3 200 steps, 11 for the shorter ones; states 900 against
+ * 450: at most 1.5 for the long flights, 87 % of the others at 1.8 or more; launch -> landing flights: 1.0, 90th
+ * percentile 1.3 — they never hand back).  So while unstarted samples are waiting, a flight that reaches that state with a growing
  * amplitude puts its state aside (one record in global memory) and its lane starts a fresh sample: every sample is
  * started within about two hand-back periods of the launch, and the long flights never wait.  The records of a warp form
- * that warp's own list (head and tail are warp-uniform registers, positions come from ballots: no atomics, no waiting —
+ * that warp's own list (head and tail live in shared memory, positions come from ballots: no atomics, no waiting —
  * one list for all warps was measured first: 1 776 warps claiming from one head with compare-and-swap cost more than the
  * hand-back returns); a warp hands back no more than its share of the unstarted samples and resumes its records, oldest
  * first, on the lanes that fall idle once the sample queue is empty.  Brackets are caches and the state is stored exactly,
  * so the outputs are bit-identical to the undisturbed flight. */
 #ifndef EMC_YIELD_STEP
-#define EMC_YIELD_STEP 1000
+#define EMC_YIELD_STEP 900          /* measured on the eight per-rank batches of the headline workload: 800 / 900 / 1 000 states give 43.3 /
+                                     * 43.3 / 44.0 ms on average; at 800 one long flight of sixteen already reads x1.9, at 900 none above x1.5 */
 #endif
 #define EMC_YIELD_QUORUM 16         /* lanes of a warp that must want to hand back in the same iteration */
 #define EMC_YIELD_GROWTH 7          /* omega_code units: a rise by a factor of 1.7 .. 1.9 or more */

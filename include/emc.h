@@ -197,7 +197,7 @@ typedef struct emc_counters {
     int64_t strict_steps;     /* ABI 2: RK4 steps taken there (not included in rk4_steps) */
     double strict_ms;         /* ABI 2: device time between the end of the flight kernel and the end of the strict continuation (it runs
                                * concurrently on a second stream: normally the cost of the final sweep only) */
-    int64_t yielded;          /* ABI 3: trajectories that gave their lane back once, after 1 000 stored states, while unstarted samples
+    int64_t yielded;          /* ABI 3: trajectories that gave their lane back once, after 900 stored states, while unstarted samples
                                * were waiting, and were resumed later (a batch larger than the resident lanes, up to 8 x as large: every
                                * sample is STARTED early, and the flights whose attitude oscillation has settled — the ones that fly
                                * longest — keep their lane, so the longest trajectory of the batch is not one that started in the last

@@ -200,7 +200,7 @@ def test_gpu_full_size_properties(engine):
 
 
 def test_gpu_lane_hand_back_is_invisible(engine):
-    """A batch larger than the resident lanes: after 1 000 stored states the flights of a warp whose attitude oscillation is
+    """A batch larger than the resident lanes: after 900 stored states the flights of a warp whose attitude oscillation is
     growing put their state aside and their lanes start unstarted samples; the records are resumed once the queue is empty
     (emc_counters.yielded).  Outputs with and without the hand-back are bit-identical on the headline workload; launch ->
     landing flights (settled attitude) never hand back; a batch that fits the resident lanes has nothing to hand back for."""
